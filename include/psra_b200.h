@@ -1,0 +1,197 @@
+/*
+ * psra_b200.h -- C ABI of libpsra_b200.so, the B200 (sm_100a) implementation of the
+ * HL1 generating-adequacy hot path of Matrixeigs/PowerSystemsReliabilityAssessment.
+ *
+ * The reference has no FFI seam: its boundary is the exported Julia API of
+ * GeneratingAdequacy/PowerSystemAdequacy.jl:8-10 (Generator, LoadModel, ReliabilityResult,
+ * run_analytical, run_non_sequential_mc, run_sequential_mc) plus the script-level
+ * functions named below.  Each entry point here cites the reference function whose body
+ * it replaces (paths relative to /root/reference/GeneratingAdequacy).  The Julia shim that
+ * binds them with ccall is julia/PowerSystemAdequacyB200.jl; INTEGRATION.md shows the
+ * binding.  The Python mirror (ctypes) is powersystemsreliabilityassessment_b200/api.py.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every buffer is caller-owned HOST memory, borrowed for
+ *    the duration of the call (Julia: pass Vectors under GC.@preserve);
+ *  - every function returns 0 on success, <0 on failure (PSRA_E_*); the message is
+ *    available from psra_last_error(); no exceptions, no exit(), no callbacks;
+ *  - calls block until the result is on the host; one handle = one CUDA device + stream,
+ *    not thread-safe per handle, independent handles are;
+ *  - there is NO CPU fallback: without a CUDA device psra_create fails with PSRA_E_CUDA;
+ *  - MW quantities cross the boundary as int32 fixed point (value * fp_scale chosen by the
+ *    host; loads and capacities in the same scale), energies as int64 in the same unit
+ *    (MW*scale * h).  Loss of load is the strict test cap < load (PSA.jl:192,253).
+ */
+#ifndef PSRA_B200_H
+#define PSRA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSRA_OK          0
+#define PSRA_E_INVALID  -1   /* bad argument / call order */
+#define PSRA_E_CUDA     -2   /* CUDA runtime error (no device, OOM, launch failure) */
+#define PSRA_E_OVERFLOW -3   /* injected durations exhausted / table too small */
+#define PSRA_E_NCCL     -4
+
+#define PSRA_INIT_ALL_UP      0  /* PSA.jl:223-224: every unit UP at hour 0 */
+#define PSRA_INIT_STATIONARY  1  /* state ~ Bernoulli(FOR), residual ~ Exp (memoryless) */
+
+typedef struct psra_handle psra_handle;
+
+typedef struct psra_config {
+    int32_t device;           /* CUDA device ordinal */
+    int32_t warps_per_block;  /* sequential kernel: 0 = default */
+    int32_t seg_hours;        /* sequential kernel: hours per shared-memory timeline segment,
+                                 multiple of 32; 0 = default */
+    int32_t blocks_per_sm;    /* 0 = as many as fit */
+    int32_t reserved[4];
+} psra_config;
+
+/* lifetime ------------------------------------------------------------------------- */
+int  psra_create(psra_handle **out, const psra_config *cfg);
+void psra_destroy(psra_handle *h);
+const char *psra_last_error(const psra_handle *h);
+/* (major*1000 + minor) of the library; also proves the .so is the CUDA build */
+int  psra_version(void);
+/* cudaStream_t of the handle as an integer, for external event timing */
+uint64_t psra_stream(const psra_handle *h);
+/* SM count and SM clock (kHz) of the handle's device */
+int  psra_device_info(const psra_handle *h, int32_t *sm_count, int32_t *sm_clock_khz);
+
+/* system data: replaces struct Generator / LoadModel, PSA.jl:20-45 ------------------ */
+/* cap_fp[U] fixed-point MW; mttf_h / mttr_h in hours (lambda = 1/MTTF, mu = 1/MTTR,
+ * FOR = lambda/(lambda+mu), PSA.jl:32-37) */
+int psra_set_system(psra_handle *h, const int32_t *cap_fp, const double *mttf_h,
+                    const double *mttr_h, int32_t n_units);
+/* load_fp[H] fixed-point MW, any H >= 1 (8736 for RTS-79, 8760 in run_full_comparison.jl:19,
+ * 1 for the peak-load mode of Montecarlo_nsq_single/nsqMain.m:290-296) */
+int psra_set_load(psra_handle *h, const int32_t *load_fp, int32_t n_hours);
+
+/* sequential chronological MC: replaces run_sequential_mc, PSA.jl:214-269 ----------- */
+typedef struct psra_seq_summary {
+    int64_t  years;             /* simulated years in this call */
+    int64_t  sum_lol_hours;     /* sum over years of LOL hours (DLC, seqMain.m:166) */
+    int64_t  sum_ens_fp;        /* sum of energy not supplied, fixed-point MWh */
+    int64_t  sum_entries;       /* sum of deficit entries (NLC, calnlc.m:22-34) */
+    int64_t  years_with_loss;
+    uint64_t sum_lol_sq;        /* sum of (LOL hours)^2 */
+    uint64_t sum_ens_sq_lo;     /* sum of ENS^2, 128-bit little-endian pair */
+    uint64_t sum_ens_sq_hi;
+    uint64_t events;            /* state transitions simulated (diagnostic) */
+    float    kernel_ms;         /* CUDA-event time of the kernel(s) of this call */
+    int32_t  reserved;
+} psra_seq_summary;
+
+typedef struct psra_seq_outputs {       /* all optional (NULL = not wanted) */
+    uint32_t *lol_hours;    /* [nyears] */
+    int64_t  *ens_fp;       /* [nyears] */
+    uint32_t *entries;      /* [nyears] */
+    uint32_t *fail_count;   /* [H] number of years in which hour h had loss of load
+                               (tail_risk.jl:81,88 hourly_failure_prob * n_years) */
+    int64_t  *group_lol;    /* [ceil(nyears/group)] LOL-hour sums of consecutive year groups:
+                               cumsum/(group*k) = convergence_history, PSA.jl:263-265 */
+    int32_t   group;        /* 10 for PSA.jl:263 */
+    int32_t   keep_on_device; /* !=0: keep the per-year ENS / LOL vectors on the device for psra_tail */
+} psra_seq_outputs;
+
+/* Years [year0, year0+nyears) of the experiment `seed`.  Years are grouped in chains of
+ * years_per_chain consecutive years (year0 and nyears must be multiples of it); a chain
+ * starts from init_mode and carries unit states across its years like PSA.jl:223-266.
+ * Every chain has its own Philox4x32-10 streams keyed (seed; chain, unit), so results do
+ * not depend on how years are split over calls, blocks or GPUs. */
+int psra_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed,
+                int32_t init_mode, int32_t years_per_chain,
+                const psra_seq_outputs *out, psra_seq_summary *summary);
+
+/* Same kernel fed with injected durations instead of the sampler (bit-exact parity tests):
+ * durations[(chain*U + u)*K + k], k = 0 initial TTF (PSA.jl:224), then TTR, TTF, ...
+ * (PSA.jl:243,246); all units start UP; all durations must be > 0. */
+int psra_seq_eval_injected(psra_handle *h, const double *durations, int64_t nchains,
+                           int32_t years_per_chain, int32_t K,
+                           const psra_seq_outputs *out, psra_seq_summary *summary);
+
+/* non-sequential state sampling: replaces run_non_sequential_mc, PSA.jl:169-208 ------ */
+typedef struct psra_nonseq_summary {
+    int64_t  samples;
+    int64_t  sum_lol_hours;     /* sum over samples of hours with cap < load */
+    int64_t  sum_ens_fp;
+    int64_t  samples_with_loss;
+    uint64_t sum_lol_sq;
+    uint64_t sum_ens_sq_lo, sum_ens_sq_hi;
+    float    kernel_ms;
+    int32_t  reserved;
+} psra_nonseq_summary;
+
+typedef struct psra_nonseq_outputs {    /* all optional */
+    uint32_t *lol_hours;    /* [n] */
+    int64_t  *ens_fp;       /* [n] */
+    int32_t  *cap_avail;    /* [n] fixed-point MW available */
+    uint32_t *states;       /* [n * ceil(U/32)] bit u%32 of word u/32 set = unit u UP */
+    int64_t  *group_lol;    /* [ceil(n/group)], group = 100 for PSA.jl:202-204 */
+    int32_t   group;
+    int32_t   reserved;
+} psra_nonseq_outputs;
+
+/* samples [sample0, sample0+n): unit u of sample i UP iff x >= floor(FOR_u * 2^32), x the
+ * Philox word keyed (seed; i, u) -- the integer form of rand() >= FOR, PSA.jl:183 */
+int psra_nonseq_mc(psra_handle *h, int64_t sample0, int64_t n, uint64_t seed,
+                   const psra_nonseq_outputs *out, psra_nonseq_summary *summary);
+/* injected bit-packed states, layout of psra_nonseq_outputs.states */
+int psra_nonseq_eval_states(psra_handle *h, const uint32_t *states, int64_t n,
+                            const psra_nonseq_outputs *out, psra_nonseq_summary *summary);
+/* injected uniforms r[i*U + u] standing in for rand(): UP iff r >= FOR (PSA.jl:183) */
+int psra_nonseq_eval_uniforms(psra_handle *h, const double *r, int64_t n,
+                              const psra_nonseq_outputs *out, psra_nonseq_summary *summary);
+
+/* analytical engine: replaces add_unit_convolution + run_analytical, PSA.jl:67-163 --- */
+/* System COPT on the grid i*step (capacities / FOR in real MW as doubles, exactly the
+ * reference arithmetic incl. the rounding split PSA.jl:100-107).  probs[max_len] receives
+ * the n_states probabilities; *n_states the table length (PSA.jl:73-75 growth rule). */
+int psra_copt(psra_handle *h, const double *cap_mw, const double *for_rate, int32_t n_units,
+              double step, double *probs, int32_t max_len, int32_t *n_states);
+/* LOLE / EUE of a COPT against an hourly load in MW (PSA.jl:123-160) */
+int psra_copt_indices(psra_handle *h, const double *probs, int32_t n_states, double step,
+                      double total_installed, const double *load_mw, int32_t n_hours,
+                      double *lole, double *eue);
+/* variant of generating_adequacy_assessment.jl:113-146 (installed = last grid state,
+ * strict outage > reserve) */
+int psra_copt_indices_strict(psra_handle *h, const double *probs, int32_t n_states, double step,
+                             const double *ldc_mw, int32_t n_hours, double *lole, double *eue);
+/* frequency & duration recursion, generating_adequacy_frequency.jl:76-129, 1 MW grid;
+ * rates per year from MTBF / MTTR hours (:26-31).  cum_prob / cum_freq [max_len]. */
+int psra_fd_recursion(psra_handle *h, const double *cap_mw, const double *mtbf_h,
+                      const double *mttr_h, int32_t n_units, double *cum_prob, double *cum_freq,
+                      int32_t max_len, int32_t *n_states);
+/* two-state Markov transient, Markov_process.jl:89-110: prob_down[t], t = 1..steps */
+int psra_markov2(psra_handle *h, double lambda, double mu, double dt, int32_t steps,
+                 double *prob_down);
+/* DTMC capacity series, Markov_process.jl:159-195, injected uniforms r[t*U + i] */
+int psra_dtmc_capacity(psra_handle *h, const double *mttf_h, const double *mttr_h,
+                       const double *cap_mw, int32_t n_units, const double *r, int32_t n_steps,
+                       double *avail_mw);
+
+/* tail risk over per-year ENS: outputs of tail_risk.jl:18-19,79-90,168-175 plus the
+ * VaR / CVaR build-side spec: VaR_a = type-7 quantile
+ * (position 1+(N-1)a, linear interpolation), CVaR_a = mean of values >= VaR_a. ---------- */
+typedef struct psra_tail_out {
+    double  var;        /* fixed-point units */
+    double  cvar;
+    int64_t n_tail;     /* values >= VaR */
+    int64_t x_lo, x_hi; /* the two order statistics bracketing the quantile position */
+} psra_tail_out;
+
+/* values[n]: per-year ENS (fixed point).  values == NULL uses the vector kept on the device
+ * by the last psra_seq_mc call with keep_on_device.  hist (optional) receives n_bins counts
+ * of width bin_width starting at 0, last bin open-ended. */
+int psra_tail(psra_handle *h, const int64_t *values, int64_t n, const double *alphas,
+              int32_t n_alpha, psra_tail_out *out, int64_t *hist, int32_t n_bins,
+              int64_t bin_width);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSRA_B200_H */

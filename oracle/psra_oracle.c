@@ -1,0 +1,564 @@
+/*
+ * psra_oracle.c -- CPU restatement of the reference's HL1 generating-adequacy path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under powersystemsreliabilityassessment_b200/
+ * may import, link or execute this file; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs use it, as the checker / CPU baseline.
+ *
+ * The reference (Matrixeigs/PowerSystemsReliabilityAssessment) is interpreted Julia +
+ * MATLAB; neither runtime exists in this image, so the reference itself cannot be
+ * compiled or run here (no oracle/_ref).  Every function below restates, line by line,
+ * the arithmetic of the cited reference lines in plain C (FP64, no FMA contraction,
+ * same operation order).  Pinning: the deterministic functions are checked against the
+ * known-answer values derived in SURVEY.md section 8c / BASELINE.md section 3 (classic
+ * RTS-79 HL1 LOLE 9.394 h/yr, the script demos' printed values) in tests/test_oracle.py.
+ * The Monte Carlo streams of the reference (Julia's unpinned default RNG) cannot be
+ * reproduced: MC parity is "unpinned by the reference" and is established through
+ * injected duration / state matrices instead.
+ *
+ * All citations are path:line under /root/reference/GeneratingAdequacy unless a
+ * directory is given.  PSA.jl = PowerSystemAdequacy.jl.
+ *
+ * Build:  gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (see oracle/Makefile).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------
+ * 1. Sequential chronological MC -- PSA.jl:214-269, literal hour/unit loop.
+ *
+ * The reference draws every duration as -log(rand())/rate from one global stream
+ * (PSA.jl:224,243,246).  Here each draw is replaced by the next entry of a per-unit
+ * duration list dur[u*K + k] (k = 0 is the initial TTF of PSA.jl:224, then TTR, TTF,...),
+ * the injection protocol of SURVEY.md section 8c.  Everything else is the literal loop:
+ * ttf -= 1.0 per hour per unit (PSA.jl:239), while ttf <= 0 toggle and add the next
+ * duration (PSA.jl:240-248), capacity of UP units summed in unit order (PSA.jl:249),
+ * strict cap < load test and deficit accumulation (PSA.jl:253-257).  State carries
+ * across years (PSA.jl:223-224 sit outside the year loop).
+ *
+ * Per-year outputs additionally hold the number of deficit entries per
+ * Montecarlo_seq/calnlc.m:22-34 (0->1 transitions of the hourly flag plus flag(1)),
+ * the MATLAB definition of NLC / LOLF (Montecarlo_seq/seqMain.m:160-169).
+ *
+ * init_status[u] (nullable): 1 = UP at hour 0 (the reference: all UP), 0 = DOWN.
+ * Returns 0, or -1 if a unit ran out of injected durations.
+ * -------------------------------------------------------------------------------- */
+int oracle_seq_literal(int U, const double *cap, int H, const double *load, int years,
+                       const double *dur, int K, const unsigned char *init_status,
+                       double *year_lol, double *year_eue, double *year_entries,
+                       int *draws_used)
+{
+    unsigned char *status = (unsigned char *)malloc((size_t)U);
+    double *ttf = (double *)malloc(sizeof(double) * (size_t)U);
+    int *next = (int *)malloc(sizeof(int) * (size_t)U);
+    int rc = 0;
+    for (int i = 0; i < U; i++) {
+        status[i] = init_status ? init_status[i] : 1;
+        ttf[i] = dur[(size_t)i * K + 0];
+        next[i] = 1;
+    }
+    for (int y = 0; y < years && rc == 0; y++) {
+        double lole = 0.0, eue = 0.0, entries = 0.0;
+        int prev_flag = 0;
+        for (int h = 0; h < H && rc == 0; h++) {
+            double cap_avail = 0.0;
+            for (int i = 0; i < U; i++) {
+                ttf[i] -= 1.0;
+                while (ttf[i] <= 0) {
+                    if (next[i] >= K) { rc = -1; break; }
+                    status[i] = !status[i];
+                    ttf[i] += dur[(size_t)i * K + next[i]];
+                    next[i]++;
+                }
+                if (rc) break;
+                if (status[i]) cap_avail += cap[i];
+            }
+            if (rc) break;
+            int flag = 0;
+            if (cap_avail < load[h]) {
+                double deficit = load[h] - cap_avail;
+                lole += 1.0;
+                eue += deficit;
+                flag = 1;
+            }
+            if (flag && !prev_flag) entries += 1.0; /* calnlc.m:22-34; prev_flag = 0 at h = 0 */
+            prev_flag = flag;
+        }
+        year_lol[y] = lole;
+        year_eue[y] = eue;
+        if (year_entries) year_entries[y] = entries;
+    }
+    if (draws_used) for (int i = 0; i < U; i++) draws_used[i] = next[i];
+    free(status); free(ttf); free(next);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------
+ * 2. Counter-based sampler specification (build-side; DESIGN.md "Sampler").
+ *
+ * The reference's random stream is Julia's unpinned default RNG, so the B200 library
+ * defines its own: Philox4x32-10 (Salmon et al., SC'11; Random123 1.x), key =
+ * (seed_lo, seed_hi), counter = (chain_lo, chain_hi, unit, block).  This is an
+ * independent restatement of that published algorithm, pinned against the Random123
+ * known-answer vectors in tests/test_oracle.py.
+ * -------------------------------------------------------------------------------- */
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* E = -ln(u), u = (x + 0.5) / 2^32, evaluated in IEEE binary32 with a fixed operation
+ * sequence (every step is a single correctly rounded add/mul/div/fma, so any IEEE
+ * machine reproduces it bit for bit):
+ *   n = 2x + 1 (33-bit odd integer), f = RN_binary32(n) = m * 2^e, m in [1,2);
+ *   if m > sqrt(2): m /= 2, e += 1;  t = m - 1;  s = t / (2 + t);  z = s*s;
+ *   ln m = 2s * (1 + z(1/3 + z(1/5 + z(1/7 + z/9))));  k = 33 - e;
+ *   E = fma(k, ln2_lo, fma(k, ln2_hi, -ln m)) with the fdlibm split ln2_hi = 0x3f317180,
+ *   ln2_lo = 0x3717f7d1 (k * ln2_hi is exact), clamped below at 2^-30 so that a duration
+ *   is never zero. */
+static float u32_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static uint32_t float_as_u32(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+
+float oracle_neglog_u32(uint32_t x)
+{
+    uint64_t n = 2ull * x + 1ull;
+    float f = (float)n; /* round to nearest even */
+    uint32_t b = float_as_u32(f);
+    int e = (int)(b >> 23) - 127;
+    float m = u32_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    float t = m - 1.0f;
+    float s = t / (2.0f + t);
+    float z = s * s;
+    float p = fmaf(z, 0.111111112f, 0.142857149f);
+    p = fmaf(z, p, 0.2f);
+    p = fmaf(z, p, 0.333333343f);
+    p = fmaf(z, p, 1.0f);
+    float lnm = (2.0f * s) * p;
+    float k = (float)(33 - e);
+    float E = fmaf(k, 9.0580006145e-06f, fmaf(k, 6.9313812256e-01f, -lnm));
+    return fmaxf(E, 9.31322575e-10f);
+}
+
+/* Per-(chain, unit) draw stream: draw j lives in Philox block j/4, word j%4. */
+typedef struct { uint32_t key[2]; uint32_t ctr[4]; uint32_t buf[4]; uint32_t j; } draw_stream;
+
+static void stream_init(draw_stream *s, uint64_t seed, uint64_t chain, uint32_t unit)
+{
+    s->key[0] = (uint32_t)seed; s->key[1] = (uint32_t)(seed >> 32);
+    s->ctr[0] = (uint32_t)chain; s->ctr[1] = (uint32_t)(chain >> 32);
+    s->ctr[2] = unit; s->ctr[3] = 0; s->j = 0;
+}
+static uint32_t stream_next(draw_stream *s)
+{
+    if ((s->j & 3u) == 0) { s->ctr[3] = s->j >> 2; oracle_philox4x32_10(s->ctr, s->key, s->buf); }
+    return s->buf[(s->j++) & 3u];
+}
+
+/* Sequential MC driven by the sampler above: the same literal loop as section 1
+ * (PSA.jl:230-266) where each -log(rand())/rate of PSA.jl:224,243,246 becomes
+ * (double)(mean_f32 * oracle_neglog_u32(next draw of the unit's stream)).
+ * Chains: years are grouped into chains of years_per_chain consecutive years; each
+ * chain starts from a fresh state (PSA.jl:223-224) and carries it across its years
+ * (years_per_chain = years reproduces the reference's single chain; 1 = independent
+ * years).  init_mode 0 = ALL_UP (the reference; draw 0 is consumed and ignored so that
+ * the duration draws keep the same indices in both modes), 1 = STATIONARY: unit DOWN
+ * iff draw0 < for_thr[u] (= floor(FOR * 2^32)), first residual ~ Exp(mean of that state),
+ * which is the stationary law of the alternating process by memorylessness. */
+int oracle_seq_philox(int U, const double *cap, const float *mttf_f, const float *mttr_f,
+                      const uint32_t *for_thr, int H, const double *load, uint64_t seed,
+                      int64_t chain0, int64_t nchains, int years_per_chain, int init_mode,
+                      double *year_lol, double *year_eue, double *year_entries)
+{
+    draw_stream *st = (draw_stream *)malloc(sizeof(draw_stream) * (size_t)U);
+    unsigned char *status = (unsigned char *)malloc((size_t)U);
+    double *ttf = (double *)malloc(sizeof(double) * (size_t)U);
+    for (int64_t c = 0; c < nchains; c++) {
+        for (int i = 0; i < U; i++) {
+            stream_init(&st[i], seed, (uint64_t)(chain0 + c), (uint32_t)i);
+            uint32_t x0 = stream_next(&st[i]);
+            status[i] = (init_mode == 1 && x0 < for_thr[i]) ? 0 : 1;
+            float mean = status[i] ? mttf_f[i] : mttr_f[i];
+            ttf[i] = (double)(mean * oracle_neglog_u32(stream_next(&st[i])));
+        }
+        for (int y = 0; y < years_per_chain; y++) {
+            double lole = 0.0, eue = 0.0, entries = 0.0;
+            int prev_flag = 0;
+            for (int h = 0; h < H; h++) {
+                double cap_avail = 0.0;
+                for (int i = 0; i < U; i++) {
+                    ttf[i] -= 1.0;
+                    while (ttf[i] <= 0) {
+                        status[i] = !status[i];
+                        float mean = status[i] ? mttf_f[i] : mttr_f[i];
+                        ttf[i] += (double)(mean * oracle_neglog_u32(stream_next(&st[i])));
+                    }
+                    if (status[i]) cap_avail += cap[i];
+                }
+                int flag = 0;
+                if (cap_avail < load[h]) {
+                    lole += 1.0;
+                    eue += load[h] - cap_avail;
+                    flag = 1;
+                }
+                if (flag && !prev_flag) entries += 1.0;
+                prev_flag = flag;
+            }
+            size_t o = (size_t)(c * years_per_chain + y);
+            year_lol[o] = lole; year_eue[o] = eue;
+            if (year_entries) year_entries[o] = entries;
+        }
+    }
+    free(st); free(status); free(ttf);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * 3. Non-sequential state sampling -- PSA.jl:169-208.
+ *
+ * Per iteration: unit UP iff r >= FOR in unit order (PSA.jl:183), capacity summed in
+ * unit order (PSA.jl:184), then every hour: strict cap < load, count + deficit
+ * (PSA.jl:191-197).  r[i*U + u] are the injected uniforms standing in for rand().
+ * Per-iteration outputs are returned so tests can compare them one by one.
+ * -------------------------------------------------------------------------------- */
+void oracle_nonseq_literal(int U, const double *cap, const double *for_rate, int H,
+                           const double *load, int64_t iters, const double *r,
+                           double *iter_lol, double *iter_eue, double *iter_cap)
+{
+    for (int64_t i = 0; i < iters; i++) {
+        double cap_avail = 0.0;
+        for (int u = 0; u < U; u++)
+            if (r[(size_t)i * U + u] >= for_rate[u]) cap_avail += cap[u];
+        double lole = 0.0, eue = 0.0;
+        for (int h = 0; h < H; h++) {
+            if (cap_avail < load[h]) {
+                double deficit = load[h] - cap_avail;
+                lole += 1.0;
+                eue += deficit;
+            }
+        }
+        iter_lol[i] = lole; iter_eue[i] = eue;
+        if (iter_cap) iter_cap[i] = cap_avail;
+    }
+}
+
+/* Same loop with packed states: bit u of word states[i*W + u/32] set = unit u UP
+ * (the MATLAB twin samples DOWN iff rand < U, Montecarlo_nsq_single/mc_sampling.m:35). */
+void oracle_nonseq_states(int U, const double *cap, int H, const double *load, int64_t iters,
+                          const uint32_t *states, double *iter_lol, double *iter_eue)
+{
+    int W = (U + 31) / 32;
+    for (int64_t i = 0; i < iters; i++) {
+        double cap_avail = 0.0;
+        for (int u = 0; u < U; u++)
+            if ((states[(size_t)i * W + (u >> 5)] >> (u & 31)) & 1u) cap_avail += cap[u];
+        double lole = 0.0, eue = 0.0;
+        for (int h = 0; h < H; h++)
+            if (cap_avail < load[h]) { lole += 1.0; eue += load[h] - cap_avail; }
+        iter_lol[i] = lole; iter_eue[i] = eue;
+    }
+}
+
+/* Sampler-driven non-sequential MC: sample i, unit u uses draw (u % 4) of Philox block
+ * counter = (i_lo, i_hi, u / 4, 0xNS) with key = seed; unit UP iff x >= for_thr[u]
+ * (PSA.jl:183 with u = x / 2^32). */
+void oracle_nonseq_philox(int U, const double *cap, const uint32_t *for_thr, int H,
+                          const double *load, uint64_t seed, int64_t i0, int64_t iters,
+                          double *iter_lol, double *iter_eue, uint32_t *states)
+{
+    int W = (U + 31) / 32;
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int64_t i = 0; i < iters; i++) {
+        uint64_t s = (uint64_t)(i0 + i);
+        double cap_avail = 0.0;
+        uint32_t out[4] = {0, 0, 0, 0};
+        for (int w = 0; w < W; w++) if (states) states[(size_t)i * W + w] = 0;
+        for (int u = 0; u < U; u++) {
+            if ((u & 3) == 0) {
+                uint32_t ctr[4] = { (uint32_t)s, (uint32_t)(s >> 32), (uint32_t)(u >> 2), 0x4E53u };
+                oracle_philox4x32_10(ctr, key, out);
+            }
+            if (out[u & 3] >= for_thr[u]) {
+                cap_avail += cap[u];
+                if (states) states[(size_t)i * W + (u >> 5)] |= 1u << (u & 31);
+            }
+        }
+        double lole = 0.0, eue = 0.0;
+        for (int h = 0; h < H; h++)
+            if (cap_avail < load[h]) { lole += 1.0; eue += load[h] - cap_avail; }
+        iter_lol[i] = lole; iter_eue[i] = eue;
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * 4. Analytical COPT -- PSA.jl:67-111 (add_unit_convolution) and PSA.jl:113-163.
+ * -------------------------------------------------------------------------------- */
+static double copt_get(const double *p, int n, double x_val, double step)
+{
+    /* PSA.jl:81-88: idx = Int(round(X/step)) + 1, 0 outside.  Julia's round() is
+     * round-half-even = rint() in the default rounding mode. */
+    double q = rint(x_val / step);
+    if (q < 0.0 || q > (double)(n - 1)) return 0.0;
+    return p[(int)q];
+}
+
+/* One convolution step.  old table has n_old states i*step; returns new length, writes
+ * new_p (caller sized via oracle_copt_next_len). */
+int oracle_copt_next_len(int n_old, double C, double step)
+{
+    /* PSA.jl:73-75: grid max of the OLD table, not the installed sum */
+    double max_old = (n_old > 0) ? (double)(n_old - 1) * step : 0.0;
+    double max_new = max_old + C;
+    return (int)ceil(max_new / step) + 1;
+}
+
+void oracle_copt_add_unit(const double *old_p, int n_old, double C, double q, double step,
+                          double *new_p, int n_new)
+{
+    double p = 1.0 - q;
+    int lower_idx = (int)floor(C / step);
+    double C_lower = lower_idx * step;
+    double C_upper = (lower_idx + 1) * step;
+    if (fabs(C - C_lower) < 1e-5) {                 /* PSA.jl:95-98 */
+        for (int i = 0; i < n_new; i++) {
+            double X = i * step;
+            new_p[i] = copt_get(old_p, n_old, X, step) * p + copt_get(old_p, n_old, X - C, step) * q;
+        }
+    } else {                                        /* PSA.jl:100-107 */
+        double alpha = (C - C_lower) / step;
+        double q_upper = q * alpha;
+        double q_lower = q * (1.0 - alpha);
+        for (int i = 0; i < n_new; i++) {
+            double X = i * step;
+            new_p[i] = copt_get(old_p, n_old, X, step) * p
+                     + copt_get(old_p, n_old, X - C_lower, step) * q_lower
+                     + copt_get(old_p, n_old, X - C_upper, step) * q_upper;
+        }
+    }
+}
+
+/* Build the system COPT (PSA.jl:118-121).  probs must hold max_len doubles; returns n. */
+int oracle_copt_build(int U, const double *cap, const double *for_rate, double step,
+                      double *probs, int max_len)
+{
+    double *a = (double *)calloc((size_t)max_len, sizeof(double));
+    double *b = (double *)calloc((size_t)max_len, sizeof(double));
+    int n = 1; a[0] = 1.0;
+    for (int u = 0; u < U; u++) {
+        int n2 = oracle_copt_next_len(n, cap[u], step);
+        if (n2 > max_len) { free(a); free(b); return -1; }
+        oracle_copt_add_unit(a, n, cap[u], for_rate[u], step, b, n2);
+        double *t = a; a = b; b = t; n = n2;
+    }
+    memcpy(probs, a, sizeof(double) * (size_t)n);
+    free(a); free(b);
+    return n;
+}
+
+/* PSA.jl:123-160: LOLE / EUE of a COPT against the hourly load, literal tail loops. */
+void oracle_analytical_indices(const double *probs, int n, double step, double total_installed,
+                               int H, const double *load, double *lole_out, double *eue_out)
+{
+    double *cum = (double *)malloc(sizeof(double) * (size_t)n);
+    /* reverse(cumsum(reverse(p))): running sum from the last state downwards (PSA.jl:130) */
+    double acc = 0.0;
+    for (int i = n - 1; i >= 0; i--) { acc += probs[i]; cum[i] = acc; }
+    double lole = 0.0, eue = 0.0;
+    for (int h = 0; h < H; h++) {
+        double reserve = total_installed - load[h];
+        long idx = (long)floor(reserve / step) + 2;       /* 1-based, PSA.jl:140 */
+        if (idx <= n && idx >= 1) {
+            lole += cum[idx - 1];
+            for (long k = idx; k <= n; k++) {
+                double outage = (double)(k - 1) * step;
+                eue += (outage - reserve) * probs[k - 1];
+            }
+        } else if (idx < 1) {                             /* PSA.jl:152-159 */
+            lole += 1.0;
+            eue += (load[h] - total_installed);
+            double avg = 0.0;
+            for (int k = 0; k < n; k++) avg += ((double)k * step) * probs[k];
+            eue += avg;
+        }
+    }
+    *lole_out = lole; *eue_out = eue;
+    free(cum);
+}
+
+/* ------------------------------------------------------------------------------------
+ * 5. generating_adequacy_assessment.jl:30-146 -- the stand-alone COPT variant:
+ *    tolerance lookup |x - X| < 1e-5 (:48-56), C_upper = ceil (:70-75), strict
+ *    outage > reserve with installed = last grid state (:125-139).
+ * -------------------------------------------------------------------------------- */
+static double copt_get_tol(const double *p, int n, double x_val, double step)
+{
+    for (int k = 0; k < n; k++)
+        if (fabs((double)k * step - x_val) < 1e-5) return p[k];
+    return 0.0;
+}
+
+void oracle_gaa_add_unit(const double *old_p, int n_old, double C, double q, double step,
+                         double *new_p, int n_new)
+{
+    double p = 1.0 - q;
+    int lower_idx = (int)floor(C / step);
+    int upper_idx = (int)ceil(C / step);
+    double C_lower = lower_idx * step, C_upper = upper_idx * step;
+    if (C_lower == C_upper) {
+        for (int i = 0; i < n_new; i++) {
+            double X = i * step;
+            double term1 = copt_get_tol(old_p, n_old, X, step) * p;
+            double term2 = copt_get_tol(old_p, n_old, X - C, step) * q;
+            new_p[i] = term1 + term2;
+        }
+    } else {
+        double alpha = (C - C_lower) / step;
+        double q_upper = q * alpha, q_lower = q * (1.0 - alpha);
+        for (int i = 0; i < n_new; i++) {
+            double X = i * step;
+            double term1 = copt_get_tol(old_p, n_old, X, step) * p;
+            double term2 = copt_get_tol(old_p, n_old, X - C_lower, step) * q_lower;
+            double term3 = copt_get_tol(old_p, n_old, X - C_upper, step) * q_upper;
+            new_p[i] = term1 + term2 + term3;
+        }
+    }
+}
+
+void oracle_gaa_calculate_indices(const double *probs, int n, double step, int H,
+                                  const double *ldc, double *lole_out, double *eue_out)
+{
+    double lole = 0.0, eue = 0.0;
+    double installed = (double)(n - 1) * step;            /* :125 */
+    for (int h = 0; h < H; h++) {
+        double reserve = installed - ldc[h];
+        double pl = 0.0, es = 0.0;
+        for (int i = 0; i < n; i++) {
+            double outage = (double)i * step;
+            if (outage > reserve) {
+                pl += probs[i];
+                es += (outage - reserve) * probs[i];
+            }
+        }
+        lole += pl; eue += es;
+    }
+    *lole_out = lole; *eue_out = eue;
+}
+
+/* ------------------------------------------------------------------------------------
+ * 6. Frequency & duration recursion -- generating_adequacy_frequency.jl:76-129.
+ *    Cumulative tables on a 1 MW grid 0..max (:69-70); boundary P(x<0)=1, F=0 (:77-82);
+ *    lookup = first level >= x, (0,0) beyond the table (:85-98).
+ *    lam is the failure rate per YEAR (8760/MTBF, :26-27), p/q availability (:30-31).
+ * -------------------------------------------------------------------------------- */
+static void fd_get(const double *P, const double *F, int n, double x, double *p_out, double *f_out)
+{
+    if (x < 0) { *p_out = 1.0; *f_out = 0.0; return; }
+    long idx = (long)ceil(x);              /* first integer level >= x on the 1 MW grid */
+    if (idx >= n) { *p_out = 0.0; *f_out = 0.0; return; }
+    *p_out = P[idx]; *f_out = F[idx];
+}
+
+void oracle_fd_add_unit(const double *P_old, const double *F_old, int n_old, double C, double p,
+                        double q, double lam, double *P_new, double *F_new, int n_new)
+{
+    for (int i = 0; i < n_new; i++) {
+        double X = (double)i;
+        double PX, FX, PXC, FXC;
+        fd_get(P_old, F_old, n_old, X, &PX, &FX);
+        fd_get(P_old, F_old, n_old, X - C, &PXC, &FXC);
+        P_new[i] = (p * PX) + (q * PXC);                   /* :110 */
+        double term1 = p * FX, term2 = q * FXC;            /* :113-116 */
+        double term3 = lam * p * (PXC - PX);
+        F_new[i] = term1 + term2 + term3;
+    }
+}
+
+/* evaluate_risk, generating_adequacy_frequency.jl:155-186 */
+void oracle_fd_evaluate(const double *P, const double *F, int n, double peak, double installed,
+                        double *lole_h, double *lolf, double *lold)
+{
+    double reserve = installed - peak;
+    *lole_h = 0.0; *lolf = 0.0; *lold = 0.0;
+    for (int i = 0; i < n; i++) {
+        if ((double)i > reserve) {
+            *lole_h = P[i] * 8760.0;
+            *lolf = F[i];
+            *lold = (*lolf > 0) ? (*lole_h / *lolf) : 0.0;
+            return;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * 7. Markov_process.jl:89-110 -- two-state chain, pi(t+1) = pi(t) P, P(down) per step;
+ *    Markov_process.jl:159-195 -- DTMC capacity series with injected uniforms
+ *    r[t*U + i] (unit order inside hour order, :172-175).
+ * -------------------------------------------------------------------------------- */
+void oracle_markov2(double lambda, double mu, double dt, int steps, double *prob_down)
+{
+    double p01 = 1 - exp(-lambda * dt), p10 = 1 - exp(-mu * dt);
+    double p00 = 1 - p01, p11 = 1 - p10;
+    double up = 1.0, down = 0.0;
+    for (int t = 0; t < steps; t++) {
+        double nu = up * p00 + down * p10;     /* row vector times P */
+        double nd = up * p01 + down * p11;
+        up = nu; down = nd;
+        prob_down[t] = down;
+    }
+}
+
+void oracle_dtmc_capacity(int U, const double *mttf, const double *mttr, const double *cap,
+                          int T, const double *r, double *avail)
+{
+    int *state = (int *)calloc((size_t)U, sizeof(int));
+    for (int t = 0; t < T; t++) {
+        for (int i = 0; i < U; i++) {
+            double p01 = 1 - exp(-(1 / mttf[i])), p10 = 1 - exp(-(1 / mttr[i]));
+            double x = r[(size_t)t * U + i];
+            if (state[i] == 0) { if (x < p01) state[i] = 1; }
+            else               { if (x < p10) state[i] = 0; }
+        }
+        double c = 0.0;
+        for (int i = 0; i < U; i++) if (state[i] == 0) c += cap[i];
+        avail[t] = c;
+    }
+    free(state);
+}
+
+/* ------------------------------------------------------------------------------------
+ * 8. RTS-79 hourly load factors -- Montecarlo_seq/anloducurve.m:24-88 (1-based hour).
+ *    weekly[52], daily[7], hourly[24*6] row-major (hour, column) as in
+ *    Montecarlo_seq/case24_loadprofile.m:23-73.
+ * -------------------------------------------------------------------------------- */
+void oracle_load_factors(int total_hours, const double *weekly, const double *daily,
+                         const double *hourly, double *factors)
+{
+    for (int h = 1; h <= total_hours; h++) {
+        int week = (int)ceil(h / 168.0);                        /* :27 */
+        int season;                                             /* 0 winter 1 summer 2 spring/fall */
+        if (week <= 8 || week >= 44) season = 0;
+        else if (week >= 18 && week <= 30) season = 1;
+        else season = 2;
+        int day = (int)ceil(fmod(h / 24.0, 7.0));               /* :39 */
+        if (day == 0) day = 7;
+        int weekend = (day <= 5) ? 0 : 1;
+        int hod = h % 24; if (hod == 0) hod = 24;               /* :49-50 */
+        int col = 2 * season + weekend;                         /* :62-84 */
+        factors[h - 1] = weekly[week - 1] * daily[day - 1] * hourly[(hod - 1) * 6 + col];
+    }
+}

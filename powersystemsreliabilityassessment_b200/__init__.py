@@ -1,0 +1,11 @@
+"""B200-native HL1 generating-adequacy Monte Carlo (drop-in for the hot path of
+Matrixeigs/PowerSystemsReliabilityAssessment, GeneratingAdequacy/PowerSystemAdequacy.jl).
+
+The compute path is libpsra_b200.so (hand-written sm_100a CUDA behind the C ABI of
+include/psra_b200.h); this package is the thin host mirror of the reference's Julia API.
+"""
+from . import rts79  # noqa: F401
+from ._lib import INIT_ALL_UP, INIT_STATIONARY, LIB_PATH  # noqa: F401
+from .api import (Engine, Generator, LoadModel, PsraError, ReliabilityResult, SequentialIndices,  # noqa: F401
+                  compare_results, evaluate_risk, indices_from_raw, run_analytical,
+                  run_non_sequential_mc, run_sequential_mc)

@@ -1,0 +1,459 @@
+"""Host-side mirror of the reference's exported API for the HL1 hot path.
+
+Same names, argument meaning and return record as
+GeneratingAdequacy/PowerSystemAdequacy.jl:8-10 (`Generator`, `LoadModel`,
+`ReliabilityResult`, `run_analytical`, `run_non_sequential_mc`, `run_sequential_mc`,
+`compare_results`); every engine body is one call into libpsra_b200.so (CUDA, sm_100a)
+through the C ABI of include/psra_b200.h.  The Julia twin that a maintainer of the reference
+would drop in is julia/PowerSystemAdequacyB200.jl; this Python module exists because Julia is
+not installed in the build image, and it is what tests/ and bench.py drive.
+
+No CPU fallback: constructing an `Engine` without the CUDA library / a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import INIT_ALL_UP, INIT_STATIONARY
+
+
+class PsraError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libpsra_b200 error {code}: {msg}")
+        self.code = code
+
+
+# ------------------------------------------------------------------ data model, PSA.jl:20-53
+@dataclasses.dataclass
+class Generator:
+    """PSA.jl:20-37: lambda = 1/MTTF, mu = 1/MTTR, for_rate = lambda/(lambda+mu)."""
+    id: int
+    capacity: float
+    mttf: float
+    mttr: float
+    lambda_: float = dataclasses.field(init=False)
+    mu: float = dataclasses.field(init=False)
+    for_rate: float = dataclasses.field(init=False)
+
+    def __post_init__(self):
+        self.lambda_ = 1.0 / self.mttf
+        self.mu = 1.0 / self.mttr
+        self.for_rate = self.lambda_ / (self.lambda_ + self.mu)
+
+
+class LoadModel:
+    """PSA.jl:39-45."""
+
+    def __init__(self, hourly_load):
+        self.hourly_load = np.ascontiguousarray(hourly_load, dtype=np.float64)
+        self.peak_load = float(self.hourly_load.max())
+
+
+@dataclasses.dataclass
+class ReliabilityResult:
+    """PSA.jl:47-53."""
+    method: str
+    lole_hours_yr: float
+    eue_mwh_yr: float
+    computation_time: float
+    convergence_history: np.ndarray
+
+
+@dataclasses.dataclass
+class SequentialIndices:
+    """Indices of a sequential run (Montecarlo_seq/seqMain.m:160-176,210-213 definitions)."""
+    years: int
+    lole: float            # h/yr   = mean(DLC)
+    eens: float            # MWh/yr = mean(ENS)
+    lolf: float            # occ/yr = mean(NLC), calnlc.m:22-34
+    lold: float            # h/occ  = sum(DLC)/sum(NLC)
+    lole_se: float         # standard errors of the two means
+    eens_se: float
+    p_loss_year: float     # share of years with any loss of load
+    cov_eens: float        # seqMain.m:183-186 CoV = std(ENS)/(mean*sqrt(n))
+    events: int
+    kernel_ms: float
+    lol_hours: Optional[np.ndarray] = None     # per-year vectors when requested
+    ens: Optional[np.ndarray] = None
+    entries: Optional[np.ndarray] = None
+    fail_count: Optional[np.ndarray] = None
+    group_lol: Optional[np.ndarray] = None
+    raw: Optional[dict] = None                 # exact integer accumulators (shardable)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _fixed(values, scale: float, what: str, strict: bool) -> np.ndarray:
+    v = np.asarray(values, dtype=np.float64) * scale
+    r = np.rint(v)
+    if strict and not np.allclose(v, r, rtol=0, atol=1e-6):
+        raise ValueError(f"{what} is not representable at fp_scale={scale}; choose a finer scale "
+                         "or pass strict=False to round to the grid")
+    if r.size and (r.min() < 0 or r.max() > 0x3fffffff):
+        raise ValueError(f"{what} out of the int32 fixed-point range at fp_scale={scale}")
+    return np.ascontiguousarray(r, dtype=np.int32)
+
+
+class Engine:
+    """One libpsra_b200 handle = one CUDA device + stream."""
+
+    def __init__(self, device: int = 0, warps_per_block: int = 0, seg_hours: int = 0, blocks_per_sm: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        cfg = _lib.Config(device=device, warps_per_block=warps_per_block, seg_hours=seg_hours,
+                          blocks_per_sm=blocks_per_sm)
+        rc = self._L.psra_create(C.byref(self._h), C.byref(cfg))
+        if rc != 0:
+            msg = self._L.psra_last_error(self._h).decode() if self._h else "psra_create failed"
+            if self._h:
+                self._L.psra_destroy(self._h)
+                self._h = C.c_void_p()
+            raise PsraError(rc, msg)
+        self.fp_scale = 1.0
+        self.n_units = 0
+        self.n_hours = 0
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.psra_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PsraError(rc, self._L.psra_last_error(self._h).decode())
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.psra_stream(self._h))
+
+    def device_info(self):
+        sm = C.c_int32(); khz = C.c_int32()
+        self._check(self._L.psra_device_info(self._h, C.byref(sm), C.byref(khz)))
+        return sm.value, khz.value
+
+    # ---- system data
+    def set_system(self, capacity_mw, mttf_h, mttr_h, fp_scale: float = 1.0, strict: bool = True):
+        cap = _fixed(capacity_mw, fp_scale, "capacity", strict)
+        mttf = np.ascontiguousarray(mttf_h, dtype=np.float64)
+        mttr = np.ascontiguousarray(mttr_h, dtype=np.float64)
+        self._check(self._L.psra_set_system(self._h, _ptr(cap), _ptr(mttf), _ptr(mttr), len(cap)))
+        self.fp_scale = float(fp_scale)
+        self.n_units = len(cap)
+
+    def set_load(self, load_mw, strict: bool = False):
+        load = _fixed(load_mw, self.fp_scale, "load", strict)
+        self._check(self._L.psra_set_load(self._h, _ptr(load), len(load)))
+        self.n_hours = len(load)
+        return load
+
+    def set_generators(self, gens: Sequence[Generator], load: LoadModel, fp_scale: float = 1.0,
+                       strict: bool = True):
+        self.set_system([g.capacity for g in gens], [g.mttf for g in gens], [g.mttr for g in gens],
+                        fp_scale, strict)
+        return self.set_load(load.hourly_load, strict=False)
+
+    # ---- sequential MC
+    def _seq_outputs(self, n, per_year, fail_count, group, keep):
+        o = _lib.SeqOutputs()
+        bufs = {}
+        if per_year:
+            bufs["lol_hours"] = np.zeros(n, dtype=np.uint32)
+            bufs["ens"] = np.zeros(n, dtype=np.int64)
+            bufs["entries"] = np.zeros(n, dtype=np.uint32)
+            o.lol_hours = _ptr(bufs["lol_hours"]); o.ens_fp = _ptr(bufs["ens"]); o.entries = _ptr(bufs["entries"])
+        if fail_count:
+            bufs["fail_count"] = np.zeros(self.n_hours, dtype=np.uint32)
+            o.fail_count = _ptr(bufs["fail_count"])
+        if group:
+            bufs["group_lol"] = np.zeros((n + group - 1) // group, dtype=np.int64)
+            o.group_lol = _ptr(bufs["group_lol"]); o.group = group
+        o.keep_on_device = 1 if keep else 0
+        return o, bufs
+
+    def _seq_result(self, s: _lib.SeqSummary, bufs) -> SequentialIndices:
+        raw = dict(years=s.years, sum_lol_hours=s.sum_lol_hours, sum_ens_fp=s.sum_ens_fp,
+                   sum_entries=s.sum_entries, years_with_loss=s.years_with_loss, sum_lol_sq=s.sum_lol_sq,
+                   sum_ens_sq=(s.sum_ens_sq_hi << 64) | s.sum_ens_sq_lo, events=s.events)
+        r = indices_from_raw(raw, self.fp_scale)
+        r.kernel_ms = float(s.kernel_ms)
+        sc = self.fp_scale
+        r.lol_hours = bufs.get("lol_hours")
+        r.ens = None if "ens" not in bufs else bufs["ens"] / sc
+        r.entries = bufs.get("entries")
+        r.fail_count = bufs.get("fail_count")
+        r.group_lol = bufs.get("group_lol")
+        if "ens" in bufs:
+            raw["ens_fp_vector"] = bufs["ens"]
+        return r
+
+    def seq_mc(self, years: int, seed: int = 42, year0: int = 0, init_mode: int = INIT_STATIONARY,
+               years_per_chain: int = 1, per_year: bool = False, fail_count: bool = False,
+               group: int = 0, keep_on_device: bool = False) -> SequentialIndices:
+        o, bufs = self._seq_outputs(years, per_year, fail_count, group, keep_on_device)
+        s = _lib.SeqSummary()
+        self._check(self._L.psra_seq_mc(self._h, year0, years, seed, init_mode, years_per_chain,
+                                        C.byref(o), C.byref(s)))
+        return self._seq_result(s, bufs)
+
+    def seq_eval_injected(self, durations, years_per_chain: int = 1, fail_count: bool = False,
+                          group: int = 0) -> SequentialIndices:
+        """durations[nchains, U, K] (k = 0 initial TTF, then TTR, TTF, ...)."""
+        d = np.ascontiguousarray(durations, dtype=np.float64)
+        if d.ndim == 2:
+            d = d[None]
+        nchains, U, K = d.shape
+        if U != self.n_units:
+            raise ValueError("durations.shape[1] must equal the unit count")
+        n = nchains * years_per_chain
+        o, bufs = self._seq_outputs(n, True, fail_count, group, False)
+        s = _lib.SeqSummary()
+        self._check(self._L.psra_seq_eval_injected(self._h, _ptr(d), nchains, years_per_chain, K,
+                                                   C.byref(o), C.byref(s)))
+        return self._seq_result(s, bufs)
+
+    # ---- non-sequential MC
+    def _ns_outputs(self, n, per_sample, states, group):
+        o = _lib.NonseqOutputs()
+        bufs = {}
+        if per_sample:
+            bufs["lol_hours"] = np.zeros(n, dtype=np.uint32)
+            bufs["ens"] = np.zeros(n, dtype=np.int64)
+            bufs["cap"] = np.zeros(n, dtype=np.int32)
+            o.lol_hours = _ptr(bufs["lol_hours"]); o.ens_fp = _ptr(bufs["ens"]); o.cap_avail = _ptr(bufs["cap"])
+        if states:
+            bufs["states"] = np.zeros((n, (self.n_units + 31) // 32), dtype=np.uint32)
+            o.states = _ptr(bufs["states"])
+        if group:
+            bufs["group_lol"] = np.zeros((n + group - 1) // group, dtype=np.int64)
+            o.group_lol = _ptr(bufs["group_lol"]); o.group = group
+        return o, bufs
+
+    def _ns_result(self, s: _lib.NonseqSummary, bufs):
+        n = max(s.samples, 1)
+        sc = self.fp_scale
+        e2 = (s.sum_ens_sq_hi << 64) | s.sum_ens_sq_lo
+        mean_l = s.sum_lol_hours / n
+        mean_e = s.sum_ens_fp / n
+        var_l = max(s.sum_lol_sq / n - mean_l * mean_l, 0.0)
+        var_e = max(e2 / n - mean_e * mean_e, 0.0)
+        out = dict(samples=s.samples, lole=mean_l, eue=mean_e / sc, lole_se=math.sqrt(var_l / n),
+                   eue_se=math.sqrt(var_e / n) / sc, p_loss=s.samples_with_loss / n,
+                   kernel_ms=float(s.kernel_ms),
+                   raw=dict(samples=s.samples, sum_lol_hours=s.sum_lol_hours, sum_ens_fp=s.sum_ens_fp,
+                            samples_with_loss=s.samples_with_loss, sum_lol_sq=s.sum_lol_sq, sum_ens_sq=e2))
+        out.update(bufs)
+        return out
+
+    def nonseq_mc(self, samples: int, seed: int = 42, sample0: int = 0, per_sample: bool = False,
+                  states: bool = False, group: int = 0):
+        o, bufs = self._ns_outputs(samples, per_sample, states, group)
+        s = _lib.NonseqSummary()
+        self._check(self._L.psra_nonseq_mc(self._h, sample0, samples, seed, C.byref(o), C.byref(s)))
+        return self._ns_result(s, bufs)
+
+    def nonseq_eval_states(self, packed_states, group: int = 0):
+        st = np.ascontiguousarray(packed_states, dtype=np.uint32)
+        if st.ndim == 1:
+            st = st[:, None]
+        n = st.shape[0]
+        o, bufs = self._ns_outputs(n, True, True, group)
+        s = _lib.NonseqSummary()
+        self._check(self._L.psra_nonseq_eval_states(self._h, _ptr(st), n, C.byref(o), C.byref(s)))
+        return self._ns_result(s, bufs)
+
+    def nonseq_eval_uniforms(self, r, group: int = 0):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        n, U = r.shape
+        if U != self.n_units:
+            raise ValueError("r.shape[1] must equal the unit count")
+        o, bufs = self._ns_outputs(n, True, True, group)
+        s = _lib.NonseqSummary()
+        self._check(self._L.psra_nonseq_eval_uniforms(self._h, _ptr(r), n, C.byref(o), C.byref(s)))
+        return self._ns_result(s, bufs)
+
+    # ---- analytical
+    def copt(self, capacity_mw, for_rate, step: float) -> np.ndarray:
+        cap = np.ascontiguousarray(capacity_mw, dtype=np.float64)
+        q = np.ascontiguousarray(for_rate, dtype=np.float64)
+        max_len = int(math.ceil(cap.sum() / step)) + 2 * len(cap) + 8
+        probs = np.zeros(max_len)
+        n = C.c_int32()
+        self._check(self._L.psra_copt(self._h, _ptr(cap), _ptr(q), len(cap), float(step), _ptr(probs),
+                                      max_len, C.byref(n)))
+        return probs[:n.value].copy()
+
+    def copt_indices(self, probs, step: float, total_installed: float, load_mw):
+        p = np.ascontiguousarray(probs, dtype=np.float64)
+        ld = np.ascontiguousarray(load_mw, dtype=np.float64)
+        a = C.c_double(); b = C.c_double()
+        self._check(self._L.psra_copt_indices(self._h, _ptr(p), len(p), float(step), float(total_installed),
+                                              _ptr(ld), len(ld), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def copt_indices_strict(self, probs, step: float, ldc_mw):
+        p = np.ascontiguousarray(probs, dtype=np.float64)
+        ld = np.ascontiguousarray(ldc_mw, dtype=np.float64)
+        a = C.c_double(); b = C.c_double()
+        self._check(self._L.psra_copt_indices_strict(self._h, _ptr(p), len(p), float(step), _ptr(ld), len(ld),
+                                                     C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fd_recursion(self, capacity_mw, mtbf_h, mttr_h):
+        cap = np.ascontiguousarray(capacity_mw, dtype=np.float64)
+        a = np.ascontiguousarray(mtbf_h, dtype=np.float64)
+        b = np.ascontiguousarray(mttr_h, dtype=np.float64)
+        max_len = int(math.floor(cap.sum())) + len(cap) + 8
+        P = np.zeros(max_len); F = np.zeros(max_len)
+        n = C.c_int32()
+        self._check(self._L.psra_fd_recursion(self._h, _ptr(cap), _ptr(a), _ptr(b), len(cap), _ptr(P), _ptr(F),
+                                              max_len, C.byref(n)))
+        return P[:n.value].copy(), F[:n.value].copy()
+
+    def markov2(self, mttf: float, mttr: float, dt: float = 1.0, steps: int = 200) -> np.ndarray:
+        out = np.zeros(steps)
+        self._check(self._L.psra_markov2(self._h, 1.0 / mttf, 1.0 / mttr, float(dt), steps, _ptr(out)))
+        return out
+
+    def dtmc_capacity(self, mttf_h, mttr_h, capacity_mw, r) -> np.ndarray:
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        T, U = r.shape
+        a = np.ascontiguousarray(mttf_h, dtype=np.float64)
+        b = np.ascontiguousarray(mttr_h, dtype=np.float64)
+        c = np.ascontiguousarray(capacity_mw, dtype=np.float64)
+        out = np.zeros(T)
+        self._check(self._L.psra_dtmc_capacity(self._h, _ptr(a), _ptr(b), _ptr(c), U, _ptr(r), T, _ptr(out)))
+        return out
+
+    # ---- tail risk
+    def tail(self, values_fp=None, alphas=(0.95, 0.99), n_bins: int = 0, bin_width: int = 1):
+        """VaR / CVaR (type-7 quantile, mean of values >= VaR) of integer per-year ENS.
+        values_fp=None uses the vector kept on the device by seq_mc(keep_on_device=True)."""
+        al = np.ascontiguousarray(alphas, dtype=np.float64)
+        outs = (_lib.TailOut * len(al))()
+        hist = np.zeros(max(n_bins, 1), dtype=np.int64)
+        if values_fp is None:
+            vp, n = None, 0
+        else:
+            v = np.ascontiguousarray(values_fp, dtype=np.int64)
+            vp, n = _ptr(v), len(v)
+        self._check(self._L.psra_tail(self._h, vp, n, _ptr(al), len(al), outs, _ptr(hist) if n_bins else None,
+                                      n_bins, int(bin_width)))
+        sc = self.fp_scale
+        res = [dict(alpha=float(a), var=o.var / sc, cvar=o.cvar / sc, n_tail=o.n_tail, x_lo=o.x_lo, x_hi=o.x_hi)
+               for a, o in zip(al, outs)]
+        return (res, hist[:n_bins]) if n_bins else res
+
+
+def indices_from_raw(raw: dict, fp_scale: float = 1.0) -> SequentialIndices:
+    """Indices from the exact integer accumulators; the accumulators of several shards
+    (calls / GPUs) add component-wise, so this is also the post-allreduce step."""
+    n = max(int(raw["years"]), 1)
+    sl, se, sn = int(raw["sum_lol_hours"]), int(raw["sum_ens_fp"]), int(raw["sum_entries"])
+    mean_l = sl / n
+    mean_e = se / n
+    var_l = max(int(raw["sum_lol_sq"]) / n - mean_l * mean_l, 0.0) * (n / max(n - 1, 1))
+    var_e = max(int(raw["sum_ens_sq"]) / n - mean_e * mean_e, 0.0) * (n / max(n - 1, 1))
+    cov = math.sqrt(var_e) / (mean_e * math.sqrt(n)) if mean_e > 0 else float("inf")
+    return SequentialIndices(
+        years=int(raw["years"]), lole=mean_l, eens=mean_e / fp_scale, lolf=sn / n,
+        lold=(sl / sn) if sn else 0.0, lole_se=math.sqrt(var_l / n), eens_se=math.sqrt(var_e / n) / fp_scale,
+        p_loss_year=int(raw["years_with_loss"]) / n, cov_eens=cov, events=int(raw.get("events", 0)),
+        kernel_ms=0.0, raw=raw)
+
+
+# ----------------------------------------------------------------- the reference entry points
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine
+
+
+def run_analytical(gens: Sequence[Generator], load: LoadModel, step_size: float = 10.0,
+                   engine: Optional[Engine] = None) -> ReliabilityResult:
+    """PSA.jl:113-163."""
+    eng = engine or default_engine()
+    t0 = time.time()
+    cap = np.array([g.capacity for g in gens], dtype=np.float64)
+    q = np.array([g.for_rate for g in gens], dtype=np.float64)
+    probs = eng.copt(cap, q, step_size)
+    total = 0.0
+    for c in cap:            # sum(g.capacity for g in gens), left to right (PSA.jl:124)
+        total += float(c)
+    lole, eue = eng.copt_indices(probs, step_size, total, load.hourly_load)
+    return ReliabilityResult("Analytical", lole, eue, time.time() - t0, np.zeros(0))
+
+
+def run_non_sequential_mc(gens: Sequence[Generator], load: LoadModel, iterations: int, seed: int = 42,
+                          fp_scale: float = 1.0, engine: Optional[Engine] = None) -> ReliabilityResult:
+    """PSA.jl:169-208: history = running mean of LOLE every 100 iterations (:202-204)."""
+    eng = engine or default_engine()
+    t0 = time.time()
+    eng.set_generators(gens, load, fp_scale)
+    r = eng.nonseq_mc(iterations, seed=seed, group=100)
+    g = r["group_lol"][: iterations // 100]
+    hist = np.cumsum(g) / (100.0 * np.arange(1, len(g) + 1))
+    return ReliabilityResult("Non-Sequential MC", r["lole"], r["eue"], time.time() - t0, hist)
+
+
+def run_sequential_mc(gens: Sequence[Generator], load: LoadModel, years: int, seed: int = 42,
+                      fp_scale: float = 1.0, init_mode: int = INIT_STATIONARY, years_per_chain: int = 1,
+                      engine: Optional[Engine] = None) -> ReliabilityResult:
+    """PSA.jl:214-269: history = running mean of LOLE every 10 years (:263-265)."""
+    eng = engine or default_engine()
+    t0 = time.time()
+    eng.set_generators(gens, load, fp_scale)
+    r = eng.seq_mc(years, seed=seed, init_mode=init_mode, years_per_chain=years_per_chain, group=10)
+    g = r.group_lol[: years // 10]
+    hist = np.cumsum(g) / (10.0 * np.arange(1, len(g) + 1))
+    return ReliabilityResult("Sequential MC", r.lole, r.eens, time.time() - t0, hist)
+
+
+def compare_results(results: List[ReliabilityResult]) -> str:
+    """PSA.jl:275-285 table (the Plots.jl figure of :288-297 is presentation, not reproduced)."""
+    lines = ["", "==========================================", "       METHOD COMPARISON SUMMARY",
+             "==========================================",
+             "%-20s | %-10s | %-10s | %-10s" % ("Method", "LOLE(h/yr)", "EUE(MWh)", "Time(s)"), "-" * 60]
+    for r in results:
+        lines.append("%-20s | %-10.4f | %-10.2f | %-10.4f" % (r.method, r.lole_hours_yr, r.eue_mwh_yr,
+                                                               r.computation_time))
+    lines.append("-" * 60)
+    text = "\n".join(lines)
+    print(text)
+    return text
+
+
+def evaluate_risk(cum_prob, cum_freq, peak_load: float, installed_cap: float):
+    """generating_adequacy_frequency.jl:155-186 on the tables of Engine.fd_recursion (1 MW grid)."""
+    reserve = installed_cap - peak_load
+    for i in range(len(cum_prob)):
+        if float(i) > reserve:
+            lole_h = cum_prob[i] * 8760.0
+            lolf = cum_freq[i]
+            return lole_h, lolf, (lole_h / lolf if lolf > 0 else 0.0)
+    return 0.0, 0.0, 0.0

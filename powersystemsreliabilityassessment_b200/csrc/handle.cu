@@ -1,0 +1,182 @@
+// handle.cu -- lifetime, system / load upload (replaces struct Generator / LoadModel,
+// GeneratingAdequacy/PowerSystemAdequacy.jl:20-45, for the device path).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+#include <vector>
+
+#include "psra_internal.cuh"
+
+int psra_fail(psra_handle *h, int code, const char *fmt, ...)
+{
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int psra_reserve(psra_handle *h, void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap && *p) return PSRA_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t want = bytes < 256 ? 256 : bytes;
+    PSRA_CUDA(h, cudaMalloc(p, want));
+    *cap = want;
+    return PSRA_OK;
+}
+
+int psra_reserve_outputs(psra_handle *h, int64_t n)
+{
+    if (n <= h->out_cap) return PSRA_OK;
+    if (h->d_lol) cudaFree(h->d_lol);
+    if (h->d_ens) cudaFree(h->d_ens);
+    if (h->d_ent) cudaFree(h->d_ent);
+    h->d_lol = nullptr; h->d_ens = nullptr; h->d_ent = nullptr; h->out_cap = 0; h->kept_n = 0;
+    PSRA_CUDA(h, cudaMalloc(&h->d_lol, sizeof(uint32_t) * (size_t)n));
+    PSRA_CUDA(h, cudaMalloc(&h->d_ens, sizeof(int64_t) * (size_t)n));
+    PSRA_CUDA(h, cudaMalloc(&h->d_ent, sizeof(uint32_t) * (size_t)n));
+    h->out_cap = n;
+    return PSRA_OK;
+}
+
+extern "C" int psra_version(void) { return PSRA_VERSION; }
+
+extern "C" const char *psra_last_error(const psra_handle *h) { return h ? h->err : "null handle"; }
+
+extern "C" uint64_t psra_stream(const psra_handle *h) { return h ? (uint64_t)(uintptr_t)h->stream : 0; }
+
+extern "C" int psra_device_info(const psra_handle *h, int32_t *sm_count, int32_t *sm_clock_khz)
+{
+    if (!h) return PSRA_E_INVALID;
+    if (sm_count) *sm_count = h->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = h->sm_clock_khz;
+    return PSRA_OK;
+}
+
+extern "C" int psra_create(psra_handle **out, const psra_config *cfg)
+{
+    if (!out) return PSRA_E_INVALID;
+    *out = nullptr;
+    psra_handle *h = new (std::nothrow) psra_handle();
+    if (!h) return PSRA_E_INVALID;
+    *out = h;  // returned even on failure so that psra_last_error() can be read
+    if (cfg) h->cfg = *cfg;
+    h->device = h->cfg.device;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return psra_fail(h, PSRA_E_CUDA, "no CUDA device available (%s); libpsra_b200 has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (h->device < 0 || h->device >= ndev)
+        return psra_fail(h, PSRA_E_INVALID, "device %d out of range (%d devices)", h->device, ndev);
+    PSRA_CUDA(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    PSRA_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10)
+        return psra_fail(h, PSRA_E_CUDA, "device %s is sm_%d%d; this library holds sm_100a code only",
+                         prop.name, prop.major, prop.minor);
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    h->sm_clock_khz = khz;
+    PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PSRA_CUDA(h, cudaEventCreate(&h->ev0));
+    PSRA_CUDA(h, cudaEventCreate(&h->ev1));
+    PSRA_CUDA(h, cudaMalloc(&h->d_acc, sizeof(unsigned long long) * ACC_COUNT));
+    return PSRA_OK;
+}
+
+extern "C" void psra_destroy(psra_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    void *bufs[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_load, h->d_lmax,
+                    h->d_tab_lol, h->d_tab_ens, h->d_acc, h->d_lol, h->d_ens, h->d_ent, h->d_fail,
+                    h->d_group, h->d_scratch, h->d_scratch2};
+    for (void *p : bufs)
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const double *mttf_h,
+                               const double *mttr_h, int32_t n_units)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, cap_fp && mttf_h && mttr_h, "null system arrays");
+    PSRA_REQUIRE(h, n_units >= 1 && n_units <= (1 << 20), "unit count out of range");
+    PSRA_CUDA(h, cudaSetDevice(h->device));
+    const int U = n_units;
+    std::vector<float> mf(U), mr(U);
+    std::vector<uint32_t> thr(U);
+    std::vector<double> q(U);
+    int64_t total = 0;
+    for (int u = 0; u < U; u++) {
+        PSRA_REQUIRE(h, cap_fp[u] >= 0, "negative capacity");
+        PSRA_REQUIRE(h, mttf_h[u] > 0 && mttr_h[u] > 0, "MTTF / MTTR must be positive");
+        total += cap_fp[u];
+        mf[u] = (float)mttf_h[u];
+        mr[u] = (float)mttr_h[u];
+        // PSA.jl:32-37: lambda = 1/MTTF, mu = 1/MTTR, FOR = lambda/(lambda+mu)
+        const double lam = 1.0 / mttf_h[u], mu = 1.0 / mttr_h[u];
+        q[u] = lam / (lam + mu);
+        double t = floor(q[u] * 4294967296.0);
+        thr[u] = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
+    }
+    PSRA_REQUIRE(h, total <= 0x3fffffff, "installed capacity exceeds the int32 fixed-point range");
+    void *old[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for};
+    for (void *p : old)
+        if (p) cudaFree(p);
+    h->d_cap = nullptr; h->d_mttf = nullptr; h->d_mttr = nullptr; h->d_for_thr = nullptr; h->d_for = nullptr;
+    PSRA_CUDA(h, cudaMalloc(&h->d_cap, sizeof(int32_t) * U));
+    PSRA_CUDA(h, cudaMalloc(&h->d_mttf, sizeof(float) * U));
+    PSRA_CUDA(h, cudaMalloc(&h->d_mttr, sizeof(float) * U));
+    PSRA_CUDA(h, cudaMalloc(&h->d_for_thr, sizeof(uint32_t) * U));
+    PSRA_CUDA(h, cudaMalloc(&h->d_for, sizeof(double) * U));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_cap, cap_fp, sizeof(int32_t) * U, cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_mttf, mf.data(), sizeof(float) * U, cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_mttr, mr.data(), sizeof(float) * U, cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_for_thr, thr.data(), sizeof(uint32_t) * U, cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_for, q.data(), sizeof(double) * U, cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->U = U;
+    h->total_cap = total;
+    h->tab_valid = false;
+    return PSRA_OK;
+}
+
+extern "C" int psra_set_load(psra_handle *h, const int32_t *load_fp, int32_t n_hours)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, load_fp, "null load");
+    PSRA_REQUIRE(h, n_hours >= 1 && n_hours <= (1 << 20), "hour count out of range");
+    PSRA_CUDA(h, cudaSetDevice(h->device));
+    const int H = n_hours, Wd = (H + 31) / 32;
+    std::vector<int32_t> pad((size_t)Wd * 32, 0), lmax(Wd, 0);
+    int32_t mx = 0;
+    for (int i = 0; i < H; i++) {
+        PSRA_REQUIRE(h, load_fp[i] >= 0 && load_fp[i] <= 0x3fffffff, "load out of the int32 fixed-point range");
+        pad[i] = load_fp[i];
+        if (load_fp[i] > lmax[i >> 5]) lmax[i >> 5] = load_fp[i];
+        if (load_fp[i] > mx) mx = load_fp[i];
+    }
+    if (h->d_load) cudaFree(h->d_load);
+    if (h->d_lmax) cudaFree(h->d_lmax);
+    h->d_load = nullptr; h->d_lmax = nullptr;
+    PSRA_CUDA(h, cudaMalloc(&h->d_load, sizeof(int32_t) * pad.size()));
+    PSRA_CUDA(h, cudaMalloc(&h->d_lmax, sizeof(int32_t) * Wd));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_load, pad.data(), sizeof(int32_t) * pad.size(), cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_lmax, lmax.data(), sizeof(int32_t) * Wd, cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->H = H; h->Wd = Wd; h->max_load = mx;
+    h->tab_valid = false;
+    return PSRA_OK;
+}

@@ -1,0 +1,277 @@
+// nonseq_mc.cu -- non-sequential state-sampling Monte Carlo on sm_100a.
+//
+// Replaces the body of run_non_sequential_mc (GeneratingAdequacy/PowerSystemAdequacy.jl:169-208):
+// per sample, unit u is UP iff rand() >= FOR_u (PSA.jl:183; MATLAB twin DOWN iff rand < U,
+// Montecarlo_nsq_single/mc_sampling.m:35), available capacity = sum of UP capacities
+// (PSA.jl:184), and that ONE capacity is evaluated against all H hours: hours with
+// cap < load counted, deficits summed (PSA.jl:191-197).
+//
+// B200 formulation: one thread per sample.  Unit states come from Philox4x32-10 words keyed
+// (seed; sample, unit/4) compared against integer thresholds floor(FOR * 2^32) and are kept
+// bit-packed (bit u%32 of word u/32 = UP); the capacity is the masked sum of the unit
+// capacities staged in shared memory.  The reference's O(H) hour loop per sample collapses to
+// one binary search in the ascending-sorted load curve (staged in shared memory) plus one
+// suffix-sum lookup:  LOL hours = #{h : load_h > cap},  ENS = sum_{load_h > cap} load_h
+// - cap * LOL hours -- integer arithmetic, hence identical to the hour loop bit for bit.
+#include <algorithm>
+#include <vector>
+
+#include "psra_internal.cuh"
+
+struct NsArgs {
+    int U, H, W, group;
+    const int32_t *cap; const uint32_t *for_thr; const double *for_rate;
+    const int32_t *sorted;        // [H] ascending
+    const long long *suffix;      // [H+1] suffix[i] = sum_{k>=i} sorted[k]
+    uint32_t k0, k1;
+    long long i0, n;
+    const uint32_t *in_states;    // injected packed states or nullptr
+    const double *in_uniforms;    // injected uniforms or nullptr
+    uint32_t *lol; long long *ens; int32_t *cap_out; uint32_t *states;
+    unsigned long long *group_lol; unsigned long long *acc;
+};
+
+enum { NS_PHILOX = 0, NS_STATES = 1, NS_UNIFORMS = 2 };
+
+template <int kMode>
+__global__ void __launch_bounds__(256) nonseq_kernel(const NsArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t *s_sorted = reinterpret_cast<int32_t *>(smem_raw);
+    int32_t *s_cap = s_sorted + a.H;
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_cap + a.U);
+    for (int i = threadIdx.x; i < a.H; i += blockDim.x) s_sorted[i] = a.sorted[i];
+    for (int i = threadIdx.x; i < a.U; i += blockDim.x) { s_cap[i] = a.cap[i]; s_thr[i] = a.for_thr[i]; }
+    __syncthreads();
+
+    unsigned long long acc_lol = 0, acc_swl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
+    long long acc_ens = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        int cap = 0;
+        if constexpr (kMode == NS_PHILOX) {
+            const unsigned long long s = (unsigned long long)(a.i0 + i);
+            uint32_t word = 0;
+            for (int u0 = 0; u0 < a.U; u0 += 4) {
+                uint32_t x[4];
+                philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)(u0 >> 2), 0x4E53u, a.k0, a.k1, x);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int u = u0 + q;
+                    if (u < a.U && x[q] >= s_thr[u]) {      // PSA.jl:183 in integer form
+                        cap += s_cap[u];
+                        word |= 1u << (u & 31);
+                    }
+                }
+                if (((u0 + 4) & 31) == 0 || u0 + 4 >= a.U) {
+                    if (a.states) a.states[(size_t)i * a.W + (u0 >> 5)] = word;
+                    word = 0;
+                }
+            }
+        } else if constexpr (kMode == NS_STATES) {
+            for (int w = 0; w < a.W; w++) {
+                uint32_t word = a.in_states[(size_t)i * a.W + w];
+                if (w == a.W - 1 && (a.U & 31)) word &= (1u << (a.U & 31)) - 1u;
+                if (a.states) a.states[(size_t)i * a.W + w] = word;
+                for (; word; word &= word - 1) cap += s_cap[w * 32 + __ffs(word) - 1];
+            }
+        } else {
+            uint32_t word = 0;
+            for (int u = 0; u < a.U; u++) {
+                if (a.in_uniforms[(size_t)i * a.U + u] >= a.for_rate[u]) {   // PSA.jl:183
+                    cap += s_cap[u];
+                    word |= 1u << (u & 31);
+                }
+                if (((u + 1) & 31) == 0 || u + 1 == a.U) {
+                    if (a.states) a.states[(size_t)i * a.W + (u >> 5)] = word;
+                    word = 0;
+                }
+            }
+        }
+        // ub = #{load <= cap}; loss hours are the H - ub largest loads
+        int lo = 0, hi = a.H;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_sorted[mid] <= cap) lo = mid + 1; else hi = mid;
+        }
+        const unsigned int lolh = (unsigned int)(a.H - lo);
+        long long ens = 0;
+        if (lolh) ens = __ldg(&a.suffix[lo]) - (long long)cap * (long long)lolh;
+        if (a.lol) a.lol[i] = lolh;
+        if (a.ens) a.ens[i] = ens;
+        if (a.cap_out) a.cap_out[i] = cap;
+        if (a.group_lol && lolh) atomicAdd(&a.group_lol[i / a.group], (unsigned long long)lolh);
+        acc_lol += lolh; acc_ens += ens; acc_swl += lolh ? 1 : 0;
+        acc_lol2 += (unsigned long long)lolh * lolh;
+        const unsigned long long e = (unsigned long long)ens;
+        const unsigned long long plo = e * e, phi = __umul64hi(e, e);
+        const unsigned long long nlo = acc_e2lo + plo;
+        acc_e2hi += phi + (nlo < acc_e2lo ? 1ull : 0ull);
+        acc_e2lo = nlo;
+    }
+    // warp reduction of the integer accumulators, one atomic set per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc_lol += __shfl_xor_sync(0xffffffffu, acc_lol, d);
+        acc_ens += __shfl_xor_sync(0xffffffffu, acc_ens, d);
+        acc_swl += __shfl_xor_sync(0xffffffffu, acc_swl, d);
+        acc_lol2 += __shfl_xor_sync(0xffffffffu, acc_lol2, d);
+    }
+    if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
+    if ((threadIdx.x & 31) == 0) {
+        if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
+        if (acc_ens) atomicAdd(&a.acc[ACC_ENS], (unsigned long long)acc_ens);
+        if (acc_swl) atomicAdd(&a.acc[ACC_YWL], acc_swl);
+        if (acc_lol2) atomicAdd(&a.acc[ACC_LOL2], acc_lol2);
+    }
+}
+
+// sorted load + suffix sums (host-side preparation at first use after psra_set_load)
+static int prepare_sorted(psra_handle *h)
+{
+    if (h->tab_valid) return PSRA_OK;
+    std::vector<int32_t> ld((size_t)h->Wd * 32);
+    PSRA_CUDA(h, cudaMemcpy(ld.data(), h->d_load, sizeof(int32_t) * ld.size(), cudaMemcpyDeviceToHost));
+    ld.resize(h->H);
+    std::sort(ld.begin(), ld.end());
+    std::vector<long long> suf((size_t)h->H + 1, 0);
+    for (int i = h->H - 1; i >= 0; i--) suf[i] = suf[i + 1] + ld[i];
+    if (h->d_tab_lol) cudaFree(h->d_tab_lol);
+    if (h->d_tab_ens) cudaFree(h->d_tab_ens);
+    h->d_tab_lol = nullptr; h->d_tab_ens = nullptr;
+    PSRA_CUDA(h, cudaMalloc(&h->d_tab_lol, sizeof(int32_t) * (size_t)h->H));
+    PSRA_CUDA(h, cudaMalloc(&h->d_tab_ens, sizeof(long long) * ((size_t)h->H + 1)));
+    PSRA_CUDA(h, cudaMemcpy(h->d_tab_lol, ld.data(), sizeof(int32_t) * (size_t)h->H, cudaMemcpyHostToDevice));
+    PSRA_CUDA(h, cudaMemcpy(h->d_tab_ens, suf.data(), sizeof(long long) * suf.size(), cudaMemcpyHostToDevice));
+    h->tab_valid = true;
+    return PSRA_OK;
+}
+
+static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0, long long n, uint64_t seed,
+                      const psra_nonseq_outputs *out, psra_nonseq_summary *summary)
+{
+    PSRA_REQUIRE(h, h->U > 0, "psra_set_system has not been called");
+    PSRA_REQUIRE(h, h->H > 0, "psra_set_load has not been called");
+    PSRA_REQUIRE(h, summary != nullptr, "summary must not be NULL");
+    PSRA_REQUIRE(h, n >= 0 && i0 >= 0, "negative sample range");
+    PSRA_CUDA(h, cudaSetDevice(h->device));
+    memset(summary, 0, sizeof(*summary));
+    summary->samples = n;
+    if (n == 0) return PSRA_OK;
+    int rc = prepare_sorted(h);
+    if (rc) return rc;
+
+    NsArgs a{};
+    a.U = h->U; a.H = h->H; a.W = (h->U + 31) / 32;
+    a.cap = h->d_cap; a.for_thr = h->d_for_thr; a.for_rate = h->d_for;
+    a.sorted = (const int32_t *)h->d_tab_lol; a.suffix = (const long long *)h->d_tab_ens;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.i0 = i0; a.n = n; a.acc = h->d_acc; a.group = 1;
+
+    const size_t smem = sizeof(int32_t) * ((size_t)h->H + h->U) + sizeof(uint32_t) * (size_t)h->U;
+    PSRA_REQUIRE(h, smem <= h->smem_optin, "load curve + unit table exceed shared memory");
+
+    if (mode == NS_STATES) {
+        const size_t bytes = sizeof(uint32_t) * (size_t)n * a.W;
+        rc = psra_reserve(h, &h->d_scratch, &h->scratch_cap, bytes);
+        if (rc) return rc;
+        PSRA_CUDA(h, cudaMemcpyAsync(h->d_scratch, input, bytes, cudaMemcpyHostToDevice, h->stream));
+        a.in_states = (const uint32_t *)h->d_scratch;
+    } else if (mode == NS_UNIFORMS) {
+        const size_t bytes = sizeof(double) * (size_t)n * a.U;
+        rc = psra_reserve(h, &h->d_scratch, &h->scratch_cap, bytes);
+        if (rc) return rc;
+        PSRA_CUDA(h, cudaMemcpyAsync(h->d_scratch, input, bytes, cudaMemcpyHostToDevice, h->stream));
+        a.in_uniforms = (const double *)h->d_scratch;
+    }
+    const bool want_vec = out && (out->lol_hours || out->ens_fp);
+    if (want_vec) {
+        rc = psra_reserve_outputs(h, n);
+        if (rc) return rc;
+        a.lol = h->d_lol; a.ens = (long long *)h->d_ens;
+    }
+    h->kept_n = 0;
+    size_t cap_bytes = 0, st_bytes = 0;
+    if (out && (out->cap_avail || out->states)) {
+        cap_bytes = out->cap_avail ? sizeof(int32_t) * (size_t)n : 0;
+        st_bytes = out->states ? sizeof(uint32_t) * (size_t)n * a.W : 0;
+        rc = psra_reserve(h, &h->d_scratch2, &h->scratch2_cap, cap_bytes + st_bytes);
+        if (rc) return rc;
+        if (out->cap_avail) a.cap_out = (int32_t *)h->d_scratch2;
+        if (out->states) a.states = (uint32_t *)((unsigned char *)h->d_scratch2 + cap_bytes);
+    }
+    long long ngroups = 0;
+    if (out && out->group_lol) {
+        PSRA_REQUIRE(h, out->group >= 1, "group must be >= 1");
+        a.group = out->group;
+        ngroups = (n + a.group - 1) / a.group;
+        if (h->group_cap < ngroups) {
+            if (h->d_group) cudaFree(h->d_group);
+            h->d_group = nullptr; h->group_cap = 0;
+            PSRA_CUDA(h, cudaMalloc(&h->d_group, sizeof(long long) * (size_t)ngroups));
+            h->group_cap = ngroups;
+        }
+        PSRA_CUDA(h, cudaMemsetAsync(h->d_group, 0, sizeof(long long) * (size_t)ngroups, h->stream));
+        a.group_lol = (unsigned long long *)h->d_group;
+    }
+    PSRA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * ACC_COUNT, h->stream));
+
+    void (*kern)(NsArgs) = mode == NS_PHILOX ? nonseq_kernel<NS_PHILOX>
+                         : mode == NS_STATES ? nonseq_kernel<NS_STATES> : nonseq_kernel<NS_UNIFORMS>;
+    PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    PSRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, smem));
+    if (bps < 1) return psra_fail(h, PSRA_E_CUDA, "non-sequential kernel does not fit on an SM");
+    long long grid = (long long)h->sm_count * bps;
+    const long long need = (n + 255) / 256;
+    if (grid > need) grid = need;
+
+    PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    kern<<<(unsigned)grid, 256, smem, h->stream>>>(a);
+    PSRA_CUDA(h, cudaGetLastError());
+    PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+
+    unsigned long long acc[ACC_COUNT];
+    PSRA_CUDA(h, cudaMemcpyAsync(acc, h->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, h->stream));
+    if (out) {
+        if (out->lol_hours) PSRA_CUDA(h, cudaMemcpyAsync(out->lol_hours, h->d_lol, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        if (out->ens_fp)    PSRA_CUDA(h, cudaMemcpyAsync(out->ens_fp, h->d_ens, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        if (out->cap_avail) PSRA_CUDA(h, cudaMemcpyAsync(out->cap_avail, a.cap_out, cap_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (out->states)    PSRA_CUDA(h, cudaMemcpyAsync(out->states, a.states, st_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (out->group_lol) PSRA_CUDA(h, cudaMemcpyAsync(out->group_lol, h->d_group, sizeof(long long) * (size_t)ngroups, cudaMemcpyDeviceToHost, h->stream));
+    }
+    PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    PSRA_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    summary->kernel_ms = ms;
+    summary->sum_lol_hours = (int64_t)acc[ACC_LOL];
+    summary->sum_ens_fp = (int64_t)acc[ACC_ENS];
+    summary->samples_with_loss = (int64_t)acc[ACC_YWL];
+    summary->sum_lol_sq = acc[ACC_LOL2];
+    summary->sum_ens_sq_lo = acc[ACC_ENS2_LO];
+    summary->sum_ens_sq_hi = acc[ACC_ENS2_HI];
+    return PSRA_OK;
+}
+
+extern "C" int psra_nonseq_mc(psra_handle *h, int64_t sample0, int64_t n, uint64_t seed,
+                              const psra_nonseq_outputs *out, psra_nonseq_summary *summary)
+{
+    if (!h) return PSRA_E_INVALID;
+    return run_nonseq(h, NS_PHILOX, nullptr, sample0, n, seed, out, summary);
+}
+
+extern "C" int psra_nonseq_eval_states(psra_handle *h, const uint32_t *states, int64_t n,
+                                       const psra_nonseq_outputs *out, psra_nonseq_summary *summary)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, states != nullptr || n == 0, "null state matrix");
+    return run_nonseq(h, NS_STATES, states, 0, n, 0, out, summary);
+}
+
+extern "C" int psra_nonseq_eval_uniforms(psra_handle *h, const double *r, int64_t n,
+                                         const psra_nonseq_outputs *out, psra_nonseq_summary *summary)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, r != nullptr || n == 0, "null uniform matrix");
+    return run_nonseq(h, NS_UNIFORMS, r, 0, n, 0, out, summary);
+}

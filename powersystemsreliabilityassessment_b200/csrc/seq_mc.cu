@@ -1,0 +1,453 @@
+// seq_mc.cu -- sequential chronological Monte Carlo on sm_100a.
+//
+// Replaces the body of run_sequential_mc (GeneratingAdequacy/PowerSystemAdequacy.jl:214-269)
+// and adds the per-year index definitions of Montecarlo_seq/seqMain.m:160-176 +
+// Montecarlo_seq/calnlc.m:22-34 (DLC = LOL hours, ENS, NLC = deficit entries).
+//
+// Formulation.  The reference walks every hour and decrements every
+// unit's residual time (PSA.jl:237-250).  This kernel uses the bit-equivalent event form:
+// a unit whose residual is t > 0 after hour g toggles next in hour g + ceil(t); the residual
+// left after that hour's decrement is r = fl(fl(t - (ceil(t) - 1)) - 1) (all earlier
+// decrements are exact in FP64 because t >= 1 there); the next residual is fl(r + D) with D
+// the next duration, and while it is <= 0 the unit toggles again in the same hour
+// (PSA.jl:240-248).  One warp owns one chain of years at a time:
+//   1. event generation: lane = unit (lane-strided over units when U > 32); each lane draws
+//      durations (Philox4x32-10 keyed (seed; chain, unit), or an injected list) and scatters
+//      the integer capacity delta of every toggle into the warp's shared-memory hour
+//      timeline (atomicAdd) and sets the hour's bit in an event bitmap (atomicOr);
+//   2. evaluation: lane = 32-hour word of the timeline.  A lane gathers the deltas of the
+//      set bits of its word, a warp-shuffle prefix scan turns the word sums into the
+//      capacity at every word start, and a word is "flagged" when a lower bound of its
+//      minimum capacity is below the word's maximum load (table staged in shared memory).
+//      Flagged words are rare; the warp resolves them hour by hour (lane = hour): shuffle
+//      scan of the 32 deltas, compare against the staged load curve, __ballot_sync/__popc
+//      for LOL hours and deficit entries, per-lane ENS accumulators reduced once per year.
+// A year is processed in `nseg` timeline segments so that the per-warp shared-memory
+// footprint stays small enough for >= 16 resident warps per SM; unit states live in
+// registers between segments (U <= 32) or in shared memory (U > 32, multi-year chains).
+#include <limits.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "psra_internal.cuh"
+
+struct SeqArgs {
+    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist;
+    const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
+    const int32_t *load; const int32_t *lmax;
+    uint32_t k0, k1;
+    long long chain_base;   // absolute index of local chain 0 (Philox counter)
+    long long nchains;
+    const double *dur;      // injected durations or nullptr
+    uint32_t *lol; long long *ens; uint32_t *ent; uint32_t *fail;
+    unsigned long long *group_lol; unsigned long long *acc;
+};
+
+struct UnitState {
+    double r;        // residual after the decrement of hour `next` (<= 0)
+    int next;        // chain-relative 0-based hour slot of the next toggle
+    uint32_t j;      // next draw index of the unit's stream
+    int status;      // 1 = UP
+    uint32_t buf[4]; // unread words of the current Philox block (buf[0] is next)
+};
+
+template <bool kInjected>
+__device__ __forceinline__ uint32_t next_word(const SeqArgs &a, long long chain, int u, UnitState &s)
+{
+    if ((s.j & 3u) == 0u)
+        philox4x32_10((uint32_t)chain, (uint32_t)((unsigned long long)chain >> 32), (uint32_t)u, s.j >> 2,
+                      a.k0, a.k1, s.buf);
+    const uint32_t x = s.buf[0];
+    s.buf[0] = s.buf[1]; s.buf[1] = s.buf[2]; s.buf[2] = s.buf[3];
+    s.j++;
+    return x;
+}
+
+// duration of the state the unit has just entered (PSA.jl:243 / :246 / :224)
+template <bool kInjected>
+__device__ __forceinline__ double next_duration(const SeqArgs &a, long long chain_local, long long chain, int u,
+                                                UnitState &s, float mf, float mr)
+{
+    if constexpr (kInjected) {
+        if (s.j >= (uint32_t)a.K) {
+            atomicExch(&a.acc[ACC_OVERFLOW], 1ull);
+            return 1.0e300;
+        }
+        const double d = __ldg(&a.dur[((size_t)chain_local * a.U + u) * (size_t)a.K + s.j]);
+        s.j++;
+        return d;
+    } else {
+        const uint32_t x = next_word<false>(a, chain, u, s);
+        return (double)__fmul_rn(s.status ? mf : mr, neglog_u32(x));
+    }
+}
+
+__device__ __forceinline__ void schedule(UnitState &s, double t, int base)
+{
+    // t > 0: next toggle ceil(t) hours after `base`; residual r = fl(fl(t-(c-1)) - 1)
+    const double c = ceil(t);
+    s.r = __dadd_rn(__dsub_rn(t, c - 1.0), -1.0);
+    s.next = (c >= 1.0e9) ? INT_MAX : base + (int)c;
+}
+
+template <bool kInjected, bool kOneUnit>
+__global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int Hpad = a.Wd * 32;
+    int32_t *s_load = reinterpret_cast<int32_t *>(smem_raw);
+    int32_t *s_lmax = s_load + Hpad;
+    const int seg_slots = a.seg_words * 32;
+    int32_t *tl_all = s_lmax + a.Wd;
+    int32_t *tl = tl_all + (size_t)warp * seg_slots;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(tl_all + (size_t)wpb * seg_slots) + (size_t)warp * a.seg_words;
+    // persistent unit states for the generic path (U > 32 with multi-year chains)
+    double *st_r = nullptr; int *st_next = nullptr; uint32_t *st_j = nullptr;
+    if (!kOneUnit && a.persist) {
+        unsigned char *p = reinterpret_cast<unsigned char *>(tl_all + (size_t)wpb * seg_slots) +
+                           sizeof(uint32_t) * (size_t)wpb * a.seg_words;
+        p = reinterpret_cast<unsigned char *>(((uintptr_t)p + 7) & ~(uintptr_t)7);
+        st_r = reinterpret_cast<double *>(p) + (size_t)warp * a.U;
+        st_next = reinterpret_cast<int *>(reinterpret_cast<double *>(p) + (size_t)wpb * a.U) + (size_t)warp * a.U;
+        st_j = reinterpret_cast<uint32_t *>(reinterpret_cast<int *>(reinterpret_cast<double *>(p) + (size_t)wpb * a.U) +
+                                            (size_t)wpb * a.U) + (size_t)warp * a.U;
+    }
+
+    // stage the load curve and the per-word maxima once per block
+    for (int i = threadIdx.x; i < Hpad; i += blockDim.x) s_load[i] = a.load[i];
+    for (int i = threadIdx.x; i < a.Wd; i += blockDim.x) s_lmax[i] = a.lmax[i];
+    for (int i = lane; i < seg_slots; i += 32) tl[i] = 0;
+    for (int i = lane; i < a.seg_words; i += 32) bm[i] = 0u;
+    __syncthreads();
+
+    unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
+    long long acc_ens = 0;
+    unsigned int n_events = 0;
+
+    const long long gw = (long long)blockIdx.x * wpb + warp;
+    const long long nw = (long long)gridDim.x * wpb;
+
+    // one-unit path: per-lane constants
+    int capu = 0; float mf = 1.f, mr = 1.f; uint32_t thr = 0;
+    if (kOneUnit && lane < a.U) {
+        capu = a.cap[lane]; mf = a.mttf[lane]; mr = a.mttr[lane]; thr = a.for_thr[lane];
+    }
+
+    for (long long cl = gw; cl < a.nchains; cl += nw) {
+        const long long chain = a.chain_base + cl;
+        UnitState st;
+        st.r = 0.0; st.next = INT_MAX; st.j = 0; st.status = 1;
+        st.buf[0] = st.buf[1] = st.buf[2] = st.buf[3] = 0;
+        int capacity = 0;   // capacity after the last evaluated hour (warp-uniform)
+
+        for (int y = 0; y < a.ypc; y++) {
+            unsigned int lolh = 0, entries = 0;
+            long long ens_lane = 0;
+            for (int seg = 0; seg < a.nseg; seg++) {
+                const int seg_h0 = seg * seg_slots;
+                const int seg_h1 = min(a.H, seg_h0 + seg_slots);
+                const int abs0 = y * a.H + seg_h0, abs1 = y * a.H + seg_h1;
+                const bool chain_start = (y == 0 && seg == 0);
+                int cap_part = 0;
+
+                // ---------------- 1. event generation ----------------
+                for (int u = lane; u < (kOneUnit ? 32 : a.U); u += 32) {
+                    if (kOneUnit && u >= a.U) break;
+                    if constexpr (!kOneUnit) {
+                        capu = a.cap[u]; mf = a.mttf[u]; mr = a.mttr[u]; thr = a.for_thr[u];
+                    }
+                    if (chain_start) {
+                        st.j = 0; st.status = 1;
+                        if constexpr (!kInjected) {
+                            const uint32_t x0 = next_word<false>(a, chain, u, st);
+                            if (a.init_mode == PSRA_INIT_STATIONARY && x0 < thr) st.status = 0;
+                        }
+                        const double d0 = next_duration<kInjected>(a, cl, chain, u, st, mf, mr);
+                        schedule(st, d0, -1);
+                        cap_part += st.status ? capu : 0;
+                    } else if constexpr (!kOneUnit) {
+                        st.r = st_r[u]; st.next = st_next[u];
+                        const uint32_t jj = st_j[u];
+                        st.status = (int)(jj >> 31); st.j = jj & 0x7fffffffu;
+                        if constexpr (!kInjected) {
+                            const uint32_t jm = st.j & 3u;
+                            if (jm) {   // re-create the partially consumed Philox block
+                                philox4x32_10((uint32_t)chain, (uint32_t)((unsigned long long)chain >> 32),
+                                              (uint32_t)u, st.j >> 2, a.k0, a.k1, st.buf);
+                                for (uint32_t q = 0; q < jm; q++) {
+                                    st.buf[0] = st.buf[1]; st.buf[1] = st.buf[2]; st.buf[2] = st.buf[3];
+                                }
+                            }
+                        }
+                    }
+                    while (st.next < abs1) {
+                        const int slot = st.next - abs0;
+                        int delta = 0;
+                        double t = st.r;
+                        do {   // PSA.jl:240-248: toggle until the residual is positive again
+                            st.status ^= 1;
+                            delta += st.status ? capu : -capu;
+                            t = __dadd_rn(t, next_duration<kInjected>(a, cl, chain, u, st, mf, mr));
+                            n_events++;
+                        } while (t <= 0.0);
+                        atomicAdd(&tl[slot], delta);
+                        atomicOr(&bm[slot >> 5], 1u << (slot & 31));
+                        schedule(st, t, st.next);
+                    }
+                    if constexpr (!kOneUnit) {
+                        if (a.persist) {
+                            st_r[u] = st.r; st_next[u] = st.next;
+                            st_j[u] = st.j | ((uint32_t)st.status << 31);
+                        }
+                    }
+                }
+                if (chain_start) {
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) cap_part += __shfl_xor_sync(0xffffffffu, cap_part, d);
+                    capacity = cap_part;
+                }
+                __syncwarp();
+
+                // ---------------- 2. evaluation of the segment ----------------
+                const int nwords = (seg_h1 - seg_h0 + 31) >> 5;
+                for (int base = 0; base < nwords; base += 32) {
+                    const int w = base + lane;
+                    const bool valid = w < nwords;
+                    const uint32_t m = valid ? bm[w] : 0u;
+                    int s = 0, neg = 0;
+                    for (uint32_t mm = m; mm; mm &= mm - 1) {
+                        const int d = tl[w * 32 + (__ffs(mm) - 1)];
+                        s += d;
+                        neg += min(d, 0);
+                    }
+                    const int incl = warp_incl_scan(s, lane);
+                    const int cs = capacity + incl - s;          // capacity entering word w
+                    const int wy = seg * a.seg_words + w;        // word index within the year
+                    const bool flagged = valid && (cs + neg < s_lmax[min(wy, a.Wd - 1)]);
+                    uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+                    while (fm) {   // rare: resolve the word hour by hour, lane = hour
+                        const int src = __ffs(fm) - 1;
+                        fm &= fm - 1;
+                        const int wq = base + src;
+                        const int csq = __shfl_sync(0xffffffffu, cs, src);
+                        const int c = csq + warp_incl_scan(tl[wq * 32 + lane], lane);
+                        const int hy0 = seg_h0 + wq * 32;        // year-relative hour of lane 0
+                        const int L = s_load[hy0 + lane];
+                        const bool lol = c < L;                  // PSA.jl:253 strict
+                        const uint32_t mask = __ballot_sync(0xffffffffu, lol);
+                        if (mask) {
+                            const uint32_t prev = (hy0 > 0 && csq < s_load[hy0 - 1]) ? 1u : 0u;
+                            lolh += __popc(mask);
+                            entries += __popc(mask & ~((mask << 1) | prev));   // calnlc.m:22-34
+                            if (lol) {
+                                ens_lane += (long long)(L - c);
+                                if (a.fail) atomicAdd(&a.fail[hy0 + lane], 1u);
+                            }
+                        }
+                    }
+                    for (uint32_t mm = m; mm; mm &= mm - 1) tl[w * 32 + (__ffs(mm) - 1)] = 0;
+                    if (valid) bm[w] = 0u;
+                    capacity += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                __syncwarp();
+            }
+
+            // ---------------- 3. per-year indices ----------------
+            long long ens = 0;
+            if (lolh) ens = warp_sum_ll(ens_lane);
+            const long long yi = cl * a.ypc + y;
+            if (lane == 0) {
+                if (a.lol) a.lol[yi] = lolh;
+                if (a.ens) a.ens[yi] = ens;
+                if (a.ent) a.ent[yi] = entries;
+                if (a.group_lol && lolh) atomicAdd(&a.group_lol[yi / a.group], (unsigned long long)lolh);
+            }
+            acc_lol += lolh; acc_ens += ens; acc_ent += entries;
+            acc_ywl += lolh ? 1 : 0;
+            acc_lol2 += (unsigned long long)lolh * lolh;
+            const unsigned long long e = (unsigned long long)ens;
+            const unsigned long long plo = e * e, phi = __umul64hi(e, e);
+            const unsigned long long nlo = acc_e2lo + plo;
+            acc_e2hi += phi + (nlo < acc_e2lo ? 1ull : 0ull);
+            acc_e2lo = nlo;
+        }
+    }
+
+    unsigned long long ev = n_events;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ev += __shfl_xor_sync(0xffffffffu, ev, d);
+    if (lane == 0) {
+        if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
+        if (acc_ens) atomicAdd(&a.acc[ACC_ENS], (unsigned long long)acc_ens);
+        if (acc_ent) atomicAdd(&a.acc[ACC_ENT], acc_ent);
+        if (acc_ywl) atomicAdd(&a.acc[ACC_YWL], acc_ywl);
+        if (acc_lol2) atomicAdd(&a.acc[ACC_LOL2], acc_lol2);
+        if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
+        if (ev) atomicAdd(&a.acc[ACC_EVENTS], ev);
+    }
+}
+
+// ------------------------------------------------------------------------------- host side
+static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, long long chain_base,
+                   long long nchains, int ypc, int init_mode, uint64_t seed, const psra_seq_outputs *out,
+                   psra_seq_summary *summary)
+{
+    PSRA_REQUIRE(h, h->U > 0, "psra_set_system has not been called");
+    PSRA_REQUIRE(h, h->H > 0, "psra_set_load has not been called");
+    PSRA_REQUIRE(h, summary != nullptr, "summary must not be NULL");
+    PSRA_REQUIRE(h, nchains >= 0 && ypc >= 1, "bad year / chain counts");
+    PSRA_REQUIRE(h, (long long)ypc * h->H < (1ll << 30), "years_per_chain * hours must stay below 2^30");
+    PSRA_CUDA(h, cudaSetDevice(h->device));
+    memset(summary, 0, sizeof(*summary));
+    const long long nyears = nchains * ypc;
+    summary->years = nyears;
+    if (nyears == 0) return PSRA_OK;
+
+    const bool one_unit = h->U <= 32;
+    SeqArgs a{};
+    a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode; a.K = K;
+    a.cap = h->d_cap; a.mttf = h->d_mttf; a.mttr = h->d_mttr; a.for_thr = h->d_for_thr;
+    a.load = h->d_load; a.lmax = h->d_lmax;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.chain_base = chain_base; a.nchains = nchains;
+    a.acc = h->d_acc;
+
+    // launch geometry: segment length and warps per block under the shared-memory budget
+    int seg_words = h->Wd;
+    if (one_unit) {
+        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : 2208;
+        seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
+    }
+    a.seg_words = seg_words;
+    a.nseg = (h->Wd + seg_words - 1) / seg_words;
+    a.persist = (!one_unit && (ypc > 1 || a.nseg > 1)) ? 1 : 0;
+    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : 8;
+    wpb = std::max(1, std::min(16, wpb));
+    auto smem_for = [&](int w) -> size_t {
+        size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
+        b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
+        if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
+        return b;
+    };
+    while (wpb > 1 && smem_for(wpb) > h->smem_optin) wpb--;
+    const size_t smem = smem_for(wpb);
+    if (smem > h->smem_optin)
+        return psra_fail(h, PSRA_E_INVALID, "system too large for the shared-memory timeline (%zu B needed, %zu B available)",
+                         smem, h->smem_optin);
+
+    // device inputs / outputs
+    if (injected) {
+        const size_t bytes = sizeof(double) * (size_t)nchains * a.U * (size_t)K;
+        int rc = psra_reserve(h, &h->d_scratch, &h->scratch_cap, bytes);
+        if (rc) return rc;
+        PSRA_CUDA(h, cudaMemcpyAsync(h->d_scratch, h_dur, bytes, cudaMemcpyHostToDevice, h->stream));
+        a.dur = (const double *)h->d_scratch;
+    }
+    const bool want_vec = out && (out->lol_hours || out->ens_fp || out->entries || out->keep_on_device);
+    if (want_vec) {
+        int rc = psra_reserve_outputs(h, nyears);
+        if (rc) return rc;
+        a.lol = h->d_lol; a.ens = (long long *)h->d_ens; a.ent = h->d_ent;
+    }
+    h->kept_n = 0;
+    if (out && out->fail_count) {
+        if (h->fail_cap < h->Wd * 32) {
+            if (h->d_fail) cudaFree(h->d_fail);
+            h->d_fail = nullptr; h->fail_cap = 0;
+            PSRA_CUDA(h, cudaMalloc(&h->d_fail, sizeof(uint32_t) * (size_t)h->Wd * 32));
+            h->fail_cap = h->Wd * 32;
+        }
+        PSRA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(uint32_t) * (size_t)h->Wd * 32, h->stream));
+        a.fail = h->d_fail;
+    }
+    long long ngroups = 0;
+    if (out && out->group_lol) {
+        PSRA_REQUIRE(h, out->group >= 1, "group must be >= 1");
+        a.group = out->group;
+        ngroups = (nyears + a.group - 1) / a.group;
+        if (h->group_cap < ngroups) {
+            if (h->d_group) cudaFree(h->d_group);
+            h->d_group = nullptr; h->group_cap = 0;
+            PSRA_CUDA(h, cudaMalloc(&h->d_group, sizeof(long long) * (size_t)ngroups));
+            h->group_cap = ngroups;
+        }
+        PSRA_CUDA(h, cudaMemsetAsync(h->d_group, 0, sizeof(long long) * (size_t)ngroups, h->stream));
+        a.group_lol = (unsigned long long *)h->d_group;
+    } else {
+        a.group = 1;
+    }
+    PSRA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * ACC_COUNT, h->stream));
+
+    void (*kern)(SeqArgs) = nullptr;
+    if (injected) kern = one_unit ? seq_mc_kernel<true, true> : seq_mc_kernel<true, false>;
+    else          kern = one_unit ? seq_mc_kernel<false, true> : seq_mc_kernel<false, false>;
+    PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    PSRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
+    if (bps < 1) return psra_fail(h, PSRA_E_CUDA, "sequential kernel does not fit on an SM (smem %zu B)", smem);
+    if (h->cfg.blocks_per_sm > 0) bps = std::min(bps, h->cfg.blocks_per_sm);
+    long long grid = (long long)h->sm_count * bps;
+    const long long need = (nchains + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+
+    PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
+    PSRA_CUDA(h, cudaGetLastError());
+    PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+
+    unsigned long long acc[ACC_COUNT];
+    PSRA_CUDA(h, cudaMemcpyAsync(acc, h->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, h->stream));
+    if (out) {
+        if (out->lol_hours) PSRA_CUDA(h, cudaMemcpyAsync(out->lol_hours, h->d_lol, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
+        if (out->ens_fp)    PSRA_CUDA(h, cudaMemcpyAsync(out->ens_fp, h->d_ens, sizeof(int64_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
+        if (out->entries)   PSRA_CUDA(h, cudaMemcpyAsync(out->entries, h->d_ent, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
+        if (out->fail_count) PSRA_CUDA(h, cudaMemcpyAsync(out->fail_count, h->d_fail, sizeof(uint32_t) * (size_t)h->H, cudaMemcpyDeviceToHost, h->stream));
+        if (out->group_lol) PSRA_CUDA(h, cudaMemcpyAsync(out->group_lol, h->d_group, sizeof(long long) * (size_t)ngroups, cudaMemcpyDeviceToHost, h->stream));
+    }
+    PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    PSRA_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    summary->kernel_ms = ms;
+    summary->sum_lol_hours = (int64_t)acc[ACC_LOL];
+    summary->sum_ens_fp = (int64_t)acc[ACC_ENS];
+    summary->sum_entries = (int64_t)acc[ACC_ENT];
+    summary->years_with_loss = (int64_t)acc[ACC_YWL];
+    summary->sum_lol_sq = acc[ACC_LOL2];
+    summary->sum_ens_sq_lo = acc[ACC_ENS2_LO];
+    summary->sum_ens_sq_hi = acc[ACC_ENS2_HI];
+    summary->events = acc[ACC_EVENTS];
+    if (want_vec && out->keep_on_device) h->kept_n = nyears;
+    if (acc[ACC_OVERFLOW])
+        return psra_fail(h, PSRA_E_OVERFLOW, "injected durations exhausted: a unit needed more than K=%d draws", K);
+    return PSRA_OK;
+}
+
+extern "C" int psra_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed, int32_t init_mode,
+                           int32_t years_per_chain, const psra_seq_outputs *out, psra_seq_summary *summary)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, years_per_chain >= 1, "years_per_chain must be >= 1");
+    PSRA_REQUIRE(h, year0 >= 0 && nyears >= 0, "negative year range");
+    PSRA_REQUIRE(h, year0 % years_per_chain == 0 && nyears % years_per_chain == 0,
+                 "year0 and nyears must be multiples of years_per_chain");
+    PSRA_REQUIRE(h, init_mode == PSRA_INIT_ALL_UP || init_mode == PSRA_INIT_STATIONARY, "unknown init_mode");
+    return run_seq(h, false, nullptr, 0, year0 / years_per_chain, nyears / years_per_chain, years_per_chain,
+                   init_mode, seed, out, summary);
+}
+
+extern "C" int psra_seq_eval_injected(psra_handle *h, const double *durations, int64_t nchains,
+                                      int32_t years_per_chain, int32_t K, const psra_seq_outputs *out,
+                                      psra_seq_summary *summary)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, durations != nullptr && K >= 1 && nchains >= 0, "bad injected duration matrix");
+    PSRA_REQUIRE(h, years_per_chain >= 1, "years_per_chain must be >= 1");
+    PSRA_REQUIRE(h, h->U > 0, "psra_set_system has not been called");
+    const size_t n = (size_t)nchains * h->U * (size_t)K;
+    for (size_t i = 0; i < n; i++)
+        if (!(durations[i] > 0.0)) return psra_fail(h, PSRA_E_INVALID, "injected durations must be > 0 (entry %zu)", i);
+    return run_seq(h, true, durations, K, 0, nchains, years_per_chain, PSRA_INIT_ALL_UP, 0, out, summary);
+}

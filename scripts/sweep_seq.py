@@ -1,0 +1,23 @@
+"""Launch-geometry sweep of the sequential kernel (RTS-79): years/s vs segment length and warps/block."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from powersystemsreliabilityassessment_b200 import Engine, rts79
+
+years = int(float(sys.argv[1])) if len(sys.argv) > 1 else 2_000_000
+cap, mttf, mttr = rts79.units()
+load = rts79.load_curve_int()
+rows = []
+for seg in (8736, 4384, 2208, 1120, 576, 288):
+    for wpb in (4, 8, 16):
+        try:
+            with Engine(seg_hours=seg, warps_per_block=wpb) as e:
+                e.set_system(cap, mttf, mttr); e.set_load(load)
+                e.seq_mc(200_000, seed=1)
+                best = min(e.seq_mc(years, seed=2 + i).kernel_ms for i in range(3))
+                r = e.seq_mc(years, seed=2)
+                rows.append(dict(seg=seg, wpb=wpb, ms=best, yps=years / best * 1e3, lole=r.lole, events_per_year=r.events / years))
+                print(rows[-1], flush=True)
+        except Exception as ex:
+            print("fail", seg, wpb, ex, flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(rows, open("gpurun_out/sweep_seq.json", "w"), indent=1)

@@ -1,0 +1,156 @@
+"""GPU parity of the sequential chronological MC (psra_seq_mc / psra_seq_eval_injected) against the
+CPU oracle's literal restatement of PSA.jl:214-269 -- bit-exact per-year integers."""
+import numpy as np
+import pytest
+
+from helpers import draws_needed, injected_durations
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_vs_literal(engine, cap, mttf, mttr, load_int, nchains, ypc, seed, dur_scale=1.0):
+    rng = np.random.default_rng(seed)
+    H = len(load_int)
+    K = draws_needed(mttf * dur_scale, mttr * dur_scale, H * ypc)
+    dur = injected_durations(rng, mttf, mttr, nchains, K, dur_scale)
+    engine.set_system(cap, mttf, mttr)
+    engine.set_load(load_int)
+    r = engine.seq_eval_injected(dur, years_per_chain=ypc, fail_count=True)
+    lol = []; ens = []; ent = []
+    for c in range(nchains):
+        a, b, e, used = O.seq_literal(cap, load_int.astype(np.float64), ypc, dur[c])
+        assert used.max() <= K
+        lol.append(a); ens.append(b); ent.append(e)
+    lol = np.concatenate(lol); ens = np.concatenate(ens); ent = np.concatenate(ent)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol)
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    assert np.array_equal(r.entries.astype(np.float64), ent)
+    assert r.raw["sum_lol_hours"] == int(lol.sum())
+    assert r.raw["sum_ens_fp"] == int(ens.sum())
+    assert r.raw["sum_entries"] == int(ent.sum())
+    assert r.raw["sum_lol_sq"] == int((lol.astype(np.int64) ** 2).sum())
+    assert r.raw["sum_ens_sq"] == sum(int(x) ** 2 for x in ens)
+    assert int(r.fail_count.sum()) == int(lol.sum())
+    return lol
+
+
+def test_injected_rts79_independent_years(engine, rts):
+    lol = _check_vs_literal(engine, rts["cap"], rts["mttf"], rts["mttr"], rts["load_int"], 48, 1, 1)
+    assert lol.sum() > 0          # the comparison is not vacuous
+
+
+def test_injected_rts79_chain_carry(engine, rts):
+    """State carries across the years of a chain exactly like PSA.jl:223-266."""
+    _check_vs_literal(engine, rts["cap"], rts["mttf"], rts["mttr"], rts["load_int"], 6, 8, 2)
+
+
+def test_injected_stressed_system(engine, rts):
+    """Short MTTF/MTTR: many toggles per hour slot, same-hour multi-toggles, frequent loss."""
+    _check_vs_literal(engine, rts["cap"], rts["mttf"], rts["mttr"], rts["load_int"], 8, 1, 3, dur_scale=0.02)
+
+
+def test_injected_8760_hours_ragged_word(engine, rts):
+    """H = 8760 (run_full_comparison.jl:19) is not a multiple of the 32-hour timeline word."""
+    rng = np.random.default_rng(5)
+    load = np.rint(1100 + 500 * np.sin((np.arange(1, 8761) - 2000) / 8760 * 2 * np.pi)
+                   + 100 * rng.standard_normal(8760)).clip(0).astype(np.int32)
+    cap = np.array([400, 400, 300, 300, 150, 150, 50, 50], dtype=np.float64)
+    mttf = np.array([1100, 1100, 1200, 1200, 900, 900, 500, 500], dtype=np.float64)
+    mttr = np.array([50, 50, 60, 60, 40, 40, 20, 20], dtype=np.float64)
+    lol = _check_vs_literal(engine, cap, mttf, mttr, load, 16, 3, 7)
+    assert lol.sum() > 0
+
+
+def test_injected_many_units_generic_path(engine, rts):
+    """U = 96 > 32 exercises the lane-strided unit loop and shared-memory unit states."""
+    cap = np.tile(rts["cap"], 3); mttf = np.tile(rts["mttf"], 3); mttr = np.tile(rts["mttr"], 3)
+    load = np.rint(3.05 * rts["load_mw"]).astype(np.int32)
+    _check_vs_literal(engine, cap, mttf, mttr, load, 6, 1, 11)
+    _check_vs_literal(engine, cap, mttf, mttr, load, 3, 2, 12)
+
+
+def test_injected_tiny_and_edge_shapes(engine):
+    cap = np.array([10.0, 5.0]); mttf = np.array([30.0, 20.0]); mttr = np.array([10.0, 15.0])
+    for H in (1, 31, 32, 33, 100):
+        load = np.full(H, 12, dtype=np.int32)
+        _check_vs_literal(engine, cap, mttf, mttr, load, 4, 5, 100 + H)
+
+
+def test_injected_overflow_is_reported(engine, rts):
+    from powersystemsreliabilityassessment_b200 import PsraError
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"])
+    engine.set_load(rts["load_int"])
+    dur = np.full((1, 32, 4), 10.0)
+    with pytest.raises(PsraError) as e:
+        engine.seq_eval_injected(dur)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("init_mode", [0, 1])
+def test_philox_mode_bit_exact_vs_oracle(engine, rts, init_mode):
+    """Sampler mode: the oracle runs the literal hour loop with the same Philox/neg-log spec."""
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"])
+    engine.set_load(rts["load_int"])
+    r = engine.seq_mc(64, seed=1234, year0=128, init_mode=init_mode, per_year=True)
+    lol, ens, ent = O.seq_philox(rts["cap"], rts["mttf"], rts["mttr"], rts["load_int"].astype(np.float64),
+                                 1234, 128, 64, 1, init_mode)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol)
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    assert np.array_equal(r.entries.astype(np.float64), ent)
+    assert lol.sum() > 0
+
+
+def test_philox_chain_mode_bit_exact(engine, rts):
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"])
+    engine.set_load(rts["load_int"])
+    r = engine.seq_mc(40, seed=7, year0=20, init_mode=0, years_per_chain=10, per_year=True)
+    lol, ens, ent = O.seq_philox(rts["cap"], rts["mttf"], rts["mttr"], rts["load_int"].astype(np.float64),
+                                 7, 2, 4, 10, 0)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol)
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    assert np.array_equal(r.entries.astype(np.float64), ent)
+
+
+def test_philox_generic_path_bit_exact(engine, rts):
+    cap = np.tile(rts["cap"], 2); mttf = np.tile(rts["mttf"], 2); mttr = np.tile(rts["mttr"], 2)
+    load = np.rint(2.05 * rts["load_mw"]).astype(np.int32)
+    engine.set_system(cap, mttf, mttr); engine.set_load(load)
+    r = engine.seq_mc(24, seed=99, init_mode=1, per_year=True)
+    lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 99, 0, 24, 1, 1)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol)
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    assert np.array_equal(r.entries.astype(np.float64), ent)
+
+
+def test_sharding_invariance_and_segments(engine, rts):
+    """Per-year integers do not depend on how years are split over calls (= GPUs) nor on the
+    launch geometry (segment length, warps per block)."""
+    from powersystemsreliabilityassessment_b200 import Engine
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(rts["load_int"])
+    full = engine.seq_mc(4096, seed=5, per_year=True)
+    a = engine.seq_mc(1024, seed=5, year0=0, per_year=True)
+    b = engine.seq_mc(3072, seed=5, year0=1024, per_year=True)
+    assert np.array_equal(full.lol_hours, np.concatenate([a.lol_hours, b.lol_hours]))
+    assert np.array_equal(full.raw["ens_fp_vector"], np.concatenate([a.raw["ens_fp_vector"], b.raw["ens_fp_vector"]]))
+    for k in ("sum_lol_hours", "sum_ens_fp", "sum_entries", "sum_lol_sq", "sum_ens_sq", "years_with_loss"):
+        assert full.raw[k] == a.raw[k] + b.raw[k]
+    for seg, wpb in ((8736, 4), (1120, 16), (320, 8), (32, 2)):
+        with Engine(seg_hours=seg, warps_per_block=wpb) as e2:
+            e2.set_system(rts["cap"], rts["mttf"], rts["mttr"]); e2.set_load(rts["load_int"])
+            r2 = e2.seq_mc(4096, seed=5, per_year=True, group=10)
+            assert np.array_equal(full.lol_hours, r2.lol_hours)
+            assert np.array_equal(full.raw["ens_fp_vector"], r2.raw["ens_fp_vector"])
+            assert np.array_equal(full.entries, r2.entries)
+            assert np.array_equal(r2.group_lol[:409], full.lol_hours[:4090].reshape(-1, 10).sum(1))
+
+
+def test_statistics_match_analytical_rts79(engine, rts):
+    """Indices within the combined 95 % CI of the analytical COPT value (PSA.jl:293-294 benchmark):
+    LOLE 9.3677 h/yr, EUE 1176.18 MWh/yr for the integer load curve."""
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(rts["load_int"])
+    r = engine.seq_mc(400_000, seed=42)
+    assert abs(r.lole - 9.3677375218) < 3.0 * r.lole_se + 1e-9
+    assert abs(r.eens - 1176.181257) < 3.0 * r.eens_se + 1e-9
+    assert 1.7 < r.lolf < 2.2 and 4.3 < r.lold < 5.4      # BASELINE.md ballparks: 1.90 occ/yr, 4.86 h
+    assert 0.50 < r.p_loss_year < 0.60
