@@ -1,0 +1,3 @@
+set -x
+make -C oracle -s
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -30
