@@ -423,15 +423,18 @@ def run_non_sequential_mc(gens: Sequence[Generator], load: LoadModel, iterations
 
 def run_sequential_mc(gens: Sequence[Generator], load: LoadModel, years: int, seed: int = 42,
                       fp_scale: float = 1.0, init_mode: int = INIT_STATIONARY, years_per_chain: int = 1,
-                      engine: Optional[Engine] = None) -> ReliabilityResult:
-    """PSA.jl:214-269: history = running mean of LOLE every 10 years (:263-265)."""
+                      year0: int = 0, engine: Optional[Engine] = None, details: bool = False):
+    """PSA.jl:214-269: history = running mean of LOLE every 10 years (:263-265).
+    year0 selects the shard [year0, year0+years) of the experiment `seed` (multi-GPU / resume);
+    details=True additionally returns the SequentialIndices (LOLF, LOLD, CIs, raw accumulators)."""
     eng = engine or default_engine()
     t0 = time.time()
     eng.set_generators(gens, load, fp_scale)
-    r = eng.seq_mc(years, seed=seed, init_mode=init_mode, years_per_chain=years_per_chain, group=10)
+    r = eng.seq_mc(years, seed=seed, year0=year0, init_mode=init_mode, years_per_chain=years_per_chain, group=10)
     g = r.group_lol[: years // 10]
     hist = np.cumsum(g) / (10.0 * np.arange(1, len(g) + 1))
-    return ReliabilityResult("Sequential MC", r.lole, r.eens, time.time() - t0, hist)
+    res = ReliabilityResult("Sequential MC", r.lole, r.eens, time.time() - t0, hist)
+    return (res, r) if details else res
 
 
 def compare_results(results: List[ReliabilityResult]) -> str:

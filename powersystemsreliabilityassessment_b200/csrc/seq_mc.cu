@@ -318,13 +318,13 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     // launch geometry: segment length and warps per block under the shared-memory budget
     int seg_words = h->Wd;
     if (one_unit) {
-        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : 2208;
+        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : 1120;
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
     a.seg_words = seg_words;
     a.nseg = (h->Wd + seg_words - 1) / seg_words;
     a.persist = (!one_unit && (ypc > 1 || a.nseg > 1)) ? 1 : 0;
-    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : 8;
+    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : 16;
     wpb = std::max(1, std::min(16, wpb));
     auto smem_for = [&](int w) -> size_t {
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);

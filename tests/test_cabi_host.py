@@ -1,0 +1,107 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/psra_b200.h declares (no
+compute calls -- there is no GPU here), fails loudly without a device, and the host mirror's logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import powersystemsreliabilityassessment_b200 as P
+from powersystemsreliabilityassessment_b200 import _lib, api, sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include/psra_b200.h")).read()
+    declared = set(re.findall(r"\b(psra_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS)
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.psra_version() == 1001
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Config) == 32
+    assert ctypes.sizeof(_lib.SeqSummary) == 80
+    assert ctypes.sizeof(_lib.SeqOutputs) == 48
+    assert ctypes.sizeof(_lib.NonseqSummary) == 64
+    assert ctypes.sizeof(_lib.NonseqOutputs) == 48
+    assert ctypes.sizeof(_lib.TailOut) == 40
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(P.PsraError) as e:
+        P.Engine()
+    assert e.value.code == _lib.PSRA_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "powersystemsreliabilityassessment_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), f
+
+
+def test_generator_and_loadmodel_mirror_reference():
+    g = P.Generator(1, 400.0, 1100.0, 150.0)         # PSA.jl:32-37
+    assert g.lambda_ == 1 / 1100.0 and g.mu == 1 / 150.0
+    assert g.for_rate == g.lambda_ / (g.lambda_ + g.mu) and abs(g.for_rate - 0.12) < 1e-12
+    lm = P.LoadModel([1.0, 5.0, 3.0])
+    assert lm.peak_load == 5.0 and lm.hourly_load.dtype == np.float64
+
+
+def test_fixed_point_conversion():
+    assert list(api._fixed([1.0, 2.5], 2.0, "x", True)) == [2, 5]
+    with pytest.raises(ValueError):
+        api._fixed([1.3], 1.0, "x", True)
+    assert list(api._fixed([1.3, 2.5, 3.5], 1.0, "x", False)) == [1, 2, 4]     # rint = half-even
+    with pytest.raises(ValueError):
+        api._fixed([-1.0], 1.0, "x", False)
+
+
+def test_indices_from_raw():
+    lol = np.array([0, 4, 0, 10]); ens = np.array([0, 300, 0, 900]); ent = np.array([0, 2, 0, 3])
+    raw = dict(years=4, sum_lol_hours=int(lol.sum()), sum_ens_fp=int(ens.sum()), sum_entries=int(ent.sum()),
+               years_with_loss=2, sum_lol_sq=int((lol ** 2).sum()), sum_ens_sq=int((ens ** 2).sum()), events=7)
+    r = P.indices_from_raw(raw, fp_scale=2.0)
+    assert r.lole == 3.5 and r.eens == 150.0 and r.lolf == 1.25 and r.lold == 14 / 5 and r.p_loss_year == 0.5
+    assert r.lole_se == pytest.approx(lol.std(ddof=1) / 2.0)
+    assert r.cov_eens == pytest.approx(ens.std(ddof=1) / (ens.mean() * 2.0))   # seqMain.m:183-186
+
+
+def test_compare_results_table(capsys):
+    txt = P.compare_results([P.ReliabilityResult("Analytical", 9.3941, 1176.29, 0.01, np.zeros(0))])
+    assert "METHOD COMPARISON SUMMARY" in txt and "Analytical" in txt and "9.3941" in txt
+
+
+def test_evaluate_risk_first_level_above_reserve():
+    P_ = np.array([1.0, 0.5, 0.25, 0.1]); F_ = np.array([0.0, 4.0, 2.0, 1.0])
+    lole, lolf, lold = P.evaluate_risk(P_, F_, 2.0, 3.0)       # reserve 1 -> level 2
+    assert lole == 0.25 * 8760 and lolf == 2.0 and lold == lole / 2.0
+    assert P.evaluate_risk(P_, F_, 0.0, 10.0) == (0.0, 0.0, 0.0)
+
+
+def test_shard_range_partitions_exactly():
+    for total, world, mult in ((10_000_000, 8, 1), (1000, 3, 10), (70, 8, 10), (0, 4, 1)):
+        spans = [sharding.shard_range(total, r, world, mult) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and a % mult == 0 and b % mult == 0
+    with pytest.raises(ValueError):
+        sharding.shard_range(15, 0, 2, 10)
+
+
+def test_pack_unpack_raw_128bit():
+    raw = dict(years=7, sum_lol_hours=11, sum_ens_fp=13, sum_entries=5, years_with_loss=3, sum_lol_sq=99,
+               events=12345678901234, sum_ens_sq=(1 << 100) + 12345)
+    assert sharding.unpack_raw(sharding.pack_raw(raw)) == raw
+    two = [a + b for a, b in zip(sharding.pack_raw(raw), sharding.pack_raw(raw))]
+    assert sharding.unpack_raw(two)["sum_ens_sq"] == 2 * raw["sum_ens_sq"]

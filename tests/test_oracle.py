@@ -1,0 +1,157 @@
+"""Pins the CPU oracle: every deterministic function against the known answers of SURVEY.md 8c /
+BASELINE.md section 3 (derived by restating the cited reference lines; the reference ships no tests
+and cannot run here), the sampler against the Random123 Philox4x32-10 known-answer vectors, and the
+event-form identities the CUDA kernel relies on."""
+import hashlib
+import math
+
+import numpy as np
+import pytest
+
+from helpers import injected_durations
+from oracle import oracle as O
+from powersystemsreliabilityassessment_b200 import rts79
+
+
+def _for(mttf, mttr):
+    lam = 1.0 / mttf; mu = 1.0 / mttr
+    return lam / (lam + mu)
+
+
+def test_rts79_unit_table():
+    cap, mttf, mttr = rts79.units()
+    assert len(cap) == 32 and cap.sum() == 3405.0
+    q = _for(mttf, mttr)
+    cls = {12: .02, 20: .10, 50: .01, 76: .02, 100: .04, 155: .04, 197: .05, 350: .08, 400: .12}
+    for c, qq in zip(cap, q):
+        assert abs(qq - cls[int(c)]) < 1e-12
+    assert abs(32 + (2 * 8736 / (mttf + mttr)).sum() - 494.4) < 0.1     # events per system-year
+
+
+def test_rts79_load_curve_known_answers():
+    mw = rts79.load_curve_mw()
+    assert len(mw) == 8736 and mw.max() == 2850.0 and mw.argmax() + 1 == 8442
+    assert abs(mw.min() - 965.615625) < 1e-9 and mw.argmin() + 1 == 6365
+    assert abs(mw.sum() - 15296714.91378) < 1e-4
+    assert np.allclose(mw[:3], [1530.76977, 1439.38053, 1370.8386], rtol=0, atol=1e-9)
+    li = rts79.load_curve_int()
+    assert li.sum() == 15296715
+    assert hashlib.sha256(li.astype("<i4").tobytes()).hexdigest() == \
+        "5c0b9e7f53d086294047f5494c9eddaff1a9d3c89cc69f0ead05d865a0fe90ca"
+    assert np.array_equal(rts79.load_factors(), O.load_factors(8736, rts79.WEEKLY, rts79.DAILY, rts79.HOURLY))
+
+
+@pytest.mark.parametrize("load_kind,step,lole,eue,nstates", [
+    ("float", 1.0, 9.3941103566, 1176.291677, 3406),
+    ("int", 1.0, 9.3677375218, 1176.181257, 3406),
+    ("float", 10.0, 9.4204746080, 1177.243237, 350)])
+def test_run_analytical_known_answers(load_kind, step, lole, eue, nstates):
+    cap, mttf, mttr = rts79.units()
+    load = rts79.load_curve_mw() if load_kind == "float" else rts79.load_curve_int().astype(float)
+    l, e, p = O.analytical(cap, _for(mttf, mttr), load, step)
+    assert len(p) == nstates
+    assert abs(l - lole) < 5e-10 and abs(e - eue) < 5e-7
+    assert abs(p.sum() - 1.0) < 1e-12
+
+
+def test_lolp_at_peak_and_golden_copt():
+    cap, mttf, mttr = rts79.units()
+    p = O.copt_build(cap, _for(mttf, mttr), 1.0)
+    cum = np.cumsum(p[::-1])[::-1]
+    assert abs(cum[556] - 0.084578060826) < 1e-12
+    g = np.load("tests/golden/rts79_copt_step10.npy")
+    assert np.array_equal(O.copt_build(cap, _for(mttf, mttr), 10.0), g)
+
+
+def test_script_demos_known_answers():
+    gp = O.gaa_build([50, 50, 56, 100], [0.02, 0.02, 0.04, 0.05], 10.0)
+    ldc = np.array([200.0 - (100.0 / 8760) * (h - 1) for h in range(1, 8761)])
+    l, e = O.gaa_indices(gp, 10.0, ldc)
+    assert len(gp) == 27 and abs(l - 200.789852160021) < 1e-9 and abs(e - 4930.134560000009) < 1e-8
+    P, F = O.fd_build([16.0, 16.0], [4380.0, 4380.0], [89.39, 89.39])
+    a, b, c = O.fd_evaluate(P, F, 20.0, 32.0)
+    assert abs(a - 346.9045) < 5e-5 and abs(b - 3.8416) < 5e-5 and abs(c - 90.3022) < 5e-5
+    m = O.markov2(1000.0, 50.0, 1.0, 200)
+    assert abs(m[-1] - 0.047333337093) < 1e-12
+    assert abs((1 - math.exp(-1 / 1000)) - 9.995001666250e-4) < 1e-15
+
+
+def test_philox_known_answer_vectors():
+    """Random123 kat_vectors, philox4x32 10 rounds."""
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, out in kat:
+        assert list(O.philox(ctr, key)) == out
+
+
+def test_neglog_accuracy_and_range():
+    rng = np.random.default_rng(0)
+    for x in list(rng.integers(0, 2**32, 5000)) + [0, 1, 2**31, 2**32 - 1, 2**32 - 2]:
+        e = O.neglog_u32(int(x))
+        ref = -math.log((int(x) + 0.5) / 2**32)
+        assert e > 0 and abs(e - ref) < 2e-7 * max(ref, 1.0) + 1.5e-7
+    assert O.neglog_u32(0) == pytest.approx(-math.log(0.5 / 2**32), rel=1e-6)
+
+
+def test_event_form_identity():
+    """the literal `ttf -= 1.0` loop and the closed event form give the same toggle
+    hours and residuals bit for bit (this is what seq_mc.cu relies on)."""
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        t = float(rng.exponential(rng.choice([0.3, 5.0, 900.0])))
+        if t <= 0:
+            continue
+        x = t; h = 0
+        while True:
+            x = x - 1.0; h += 1
+            if x <= 0:
+                break
+        c = math.ceil(t)
+        r = (t - (c - 1.0)) - 1.0
+        assert h == c and x == r
+
+
+def test_seq_literal_sanity_and_fixture():
+    cap, mttf, mttr = rts79.units()
+    load = rts79.load_curve_int().astype(float)
+    rng = np.random.default_rng(123)
+    dur = injected_durations(rng, mttf, mttr, 1, 200)[0]
+    lol, eue, ent, used = O.seq_literal(cap, load, 3, dur)
+    g = np.load("tests/golden/seq_literal_seed123.npz")
+    assert np.array_equal(lol, g["lol"]) and np.array_equal(eue, g["eue"]) and np.array_equal(ent, g["ent"])
+    assert (ent <= lol).all() and ((lol > 0) == (eue > 0)).all()
+    with pytest.raises(RuntimeError):
+        O.seq_literal(cap, load, 3, dur[:, :4])
+
+
+def test_seq_philox_statistics_vs_analytical():
+    """The oracle's sampler-driven literal loop reproduces the analytical LOLE within its CI."""
+    cap, mttf, mttr = rts79.units()
+    load = rts79.load_curve_int().astype(float)
+    lol, eue, ent = O.seq_philox(cap, mttf, mttr, load, 42, 0, 1500, 1, 1)
+    se = lol.std(ddof=1) / math.sqrt(len(lol))
+    assert abs(lol.mean() - 9.3677375218) < 3.5 * se
+    g = np.load("tests/golden/seq_philox_seed42.npz")
+    assert np.array_equal(lol[:64], g["lol"]) and np.array_equal(eue[:64], g["eue"]) and np.array_equal(ent[:64], g["ent"])
+
+
+def test_nonseq_literal_vs_lookup_identity():
+    """The sorted-load lookup used on the GPU equals the reference's hour loop (integer loads)."""
+    cap, mttf, mttr = rts79.units()
+    li = rts79.load_curve_int()
+    rng = np.random.default_rng(9)
+    r = rng.random((400, 32)) * 0.2
+    lol, eue, cp = O.nonseq_literal(cap, _for(mttf, mttr), li.astype(float), r)
+    s = np.sort(li); suf = np.concatenate([np.cumsum(s[::-1])[::-1], [0]])
+    for i in range(400):
+        ub = np.searchsorted(s, cp[i], side="right")
+        assert lol[i] == len(s) - ub and eue[i] == suf[ub] - cp[i] * (len(s) - ub)
+
+
+def test_quantile_type7_matches_numpy():
+    rng = np.random.default_rng(2)
+    x = rng.integers(0, 50000, 1001)
+    for a in (0.0, 0.5, 0.95, 0.99, 1.0):
+        assert O.quantile_type7(x, a) == pytest.approx(np.quantile(x, a, method="linear"), rel=1e-15)
