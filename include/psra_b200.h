@@ -48,7 +48,8 @@ typedef struct psra_config {
     int32_t seg_hours;        /* sequential kernel: hours per shared-memory timeline segment,
                                  multiple of 32; 0 = default */
     int32_t blocks_per_sm;    /* 0 = as many as fit */
-    int32_t reserved[4];
+    int32_t reserved[4];      /* reserved[0] != 0: force the generic sequential kernel (seq_mc.cu) also
+                                 for systems of <= 32 units (cross-checks; the default picks seq_fast.cu) */
 } psra_config;
 
 /* lifetime ------------------------------------------------------------------------- */

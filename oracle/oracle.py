@@ -45,6 +45,8 @@ def lib():
         L.oracle_philox4x32_10.argtypes = [_u32p, _u32p, _u32p]
         L.oracle_neglog_u32.restype = C.c_float
         L.oracle_neglog_u32.argtypes = [C.c_uint32]
+        L.oracle_duration_hours.restype = C.c_double
+        L.oracle_duration_hours.argtypes = [C.c_float, C.c_uint32]
         L.oracle_seq_philox.restype = C.c_int
         L.oracle_seq_philox.argtypes = [C.c_int, _dp, _fp, _fp, _u32p, C.c_int, _dp, C.c_uint64,
                                         C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp]
@@ -128,6 +130,10 @@ def philox(ctr, key):
     out = np.zeros(4, dtype=np.uint32)
     lib().oracle_philox4x32_10(np.asarray(ctr, dtype=np.uint32), np.asarray(key, dtype=np.uint32), out)
     return out
+
+
+def duration_hours(mean: float, x: int) -> float:
+    return float(lib().oracle_duration_hours(float(np.float32(mean)), int(x)))
 
 
 def neglog_u32(x: int) -> float:

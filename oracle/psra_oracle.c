@@ -122,38 +122,51 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* E = -ln(u), u = (x + 0.5) / 2^32, evaluated in IEEE binary32 with a fixed operation
- * sequence (every step is a single correctly rounded add/mul/div/fma, so any IEEE
- * machine reproduces it bit for bit):
- *   n = 2x + 1 (33-bit odd integer), f = RN_binary32(n) = m * 2^e, m in [1,2);
- *   if m > sqrt(2): m /= 2, e += 1;  t = m - 1;  s = t / (2 + t);  z = s*s;
- *   ln m = 2s * (1 + z(1/3 + z(1/5 + z(1/7 + z/9))));  k = 33 - e;
- *   E = fma(k, ln2_lo, fma(k, ln2_hi, -ln m)) with the fdlibm split ln2_hi = 0x3f317180,
- *   ln2_lo = 0x3717f7d1 (k * ln2_hi is exact), clamped below at 2^-30 so that a duration
- *   is never zero. */
+/* E = -ln(u) for the draw x, evaluated with integer bit operations and IEEE binary32
+ * add/mul/fma only (every step correctly rounded, so any IEEE machine reproduces it bit for bit):
+ *   w = x | 1;  lz = clz32(w);  X = w << lz;  u = w / 2^32 = m * 2^-(lz+1), m = X / 2^31 in [1,2);
+ *   m is truncated to 24 bits: bits(m) = (X >> 8) + 0x3F000000;  k = lz + 1;
+ *   range reduction to [sqrt(1/2), sqrt(2)) on the bit pattern (fdlibm logf):
+ *     ix = bits + 0x004AFB0D;  k -= (ix >> 23) - 127;  bits(m_r) = (ix & 0x007FFFFF) + 0x3F3504F3;
+ *   t = m_r - 1;  ln m_r = t + t^2 * P7(t) (Horner, fma);  E = fma(k, ln2_lo, fma(k, ln2_hi, -ln m_r))
+ *   with the fdlibm split ln2_hi = 0x3f317180, ln2_lo = 0x3717f7d1.  0 < E <= 32 ln 2. */
 static float u32_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
-static uint32_t float_as_u32(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+
+static const float LOGP[8] = { -0x1.fffff4p-2f, 0x1.5557acp-2f, -0x1.000688p-2f, 0x1.98a666p-3f,
+                               -0x1.52fdeep-3f, 0x1.32c6a8p-3f, -0x1.27c4d6p-3f, 0x1.65b9f8p-4f };
 
 float oracle_neglog_u32(uint32_t x)
 {
-    uint64_t n = 2ull * x + 1ull;
-    float f = (float)n; /* round to nearest even */
-    uint32_t b = float_as_u32(f);
-    int e = (int)(b >> 23) - 127;
-    float m = u32_as_float((b & 0x007FFFFFu) | 0x3F800000u);
-    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    uint32_t w = x | 1u;
+    int lz = __builtin_clz(w);
+    uint32_t X = w << lz;
+    uint32_t bits = (X >> 8) + 0x3F000000u;
+    int k = lz + 1;
+    uint32_t ix = bits + 0x004AFB0Du;
+    k -= (int)(ix >> 23) - 127;
+    float m = u32_as_float((ix & 0x007FFFFFu) + 0x3F3504F3u);
     float t = m - 1.0f;
-    float s = t / (2.0f + t);
-    float z = s * s;
-    float p = fmaf(z, 0.111111112f, 0.142857149f);
-    p = fmaf(z, p, 0.2f);
-    p = fmaf(z, p, 0.333333343f);
-    p = fmaf(z, p, 1.0f);
-    float lnm = (2.0f * s) * p;
-    float k = (float)(33 - e);
-    float E = fmaf(k, 9.0580006145e-06f, fmaf(k, 6.9313812256e-01f, -lnm));
-    return fmaxf(E, 9.31322575e-10f);
+    float p = LOGP[7];
+    for (int i = 6; i >= 0; i--) p = fmaf(p, t, LOGP[i]);
+    float q = t * t;
+    float r = fmaf(q, p, t);
+    float kf = (float)k;
+    return fmaf(kf, 9.0580006145e-06f, fmaf(kf, 6.9313812256e-01f, -r));
 }
+
+/* Duration of one draw in hours: quantised to ticks of 2^-24 h so that every residual of the
+ * literal `ttf -= 1.0` / `ttf += D` recurrence below is an exact FP64 number (event times are then
+ * plain prefix sums, which is what lets the GPU generate them in parallel):
+ *   D = RN_int64(max(RN_f32(RN_f32(mean * 2^24) * E), 1)) / 2^24,  E = oracle_neglog_u32(draw). */
+static double duration_hours(float mean_f32, uint32_t x)
+{
+    float mt = mean_f32 * 16777216.0f;
+    float p = fmaxf(mt * oracle_neglog_u32(x), 1.0f);
+    long long t = llrintf(p);          /* round to nearest even (default rounding mode) */
+    return (double)t / 16777216.0;
+}
+
+double oracle_duration_hours(float mean_f32, uint32_t x) { return duration_hours(mean_f32, x); }
 
 /* Per-(chain, unit) draw stream: draw j lives in Philox block j/4, word j%4. */
 typedef struct { uint32_t key[2]; uint32_t ctr[4]; uint32_t buf[4]; uint32_t j; } draw_stream;
@@ -172,7 +185,8 @@ static uint32_t stream_next(draw_stream *s)
 
 /* Sequential MC driven by the sampler above: the same literal loop as section 1
  * (PSA.jl:230-266) where each -log(rand())/rate of PSA.jl:224,243,246 becomes
- * (double)(mean_f32 * oracle_neglog_u32(next draw of the unit's stream)).
+
+ * duration_hours(mean_f32, next draw of the unit's stream) (tick-quantised, see above).
  * Chains: years are grouped into chains of years_per_chain consecutive years; each
  * chain starts from a fresh state (PSA.jl:223-224) and carries it across its years
  * (years_per_chain = years reproduces the reference's single chain; 1 = independent
@@ -194,7 +208,7 @@ int oracle_seq_philox(int U, const double *cap, const float *mttf_f, const float
             uint32_t x0 = stream_next(&st[i]);
             status[i] = (init_mode == 1 && x0 < for_thr[i]) ? 0 : 1;
             float mean = status[i] ? mttf_f[i] : mttr_f[i];
-            ttf[i] = (double)(mean * oracle_neglog_u32(stream_next(&st[i])));
+            ttf[i] = duration_hours(mean, stream_next(&st[i]));
         }
         for (int y = 0; y < years_per_chain; y++) {
             double lole = 0.0, eue = 0.0, entries = 0.0;
@@ -206,7 +220,7 @@ int oracle_seq_philox(int U, const double *cap, const float *mttf_f, const float
                     while (ttf[i] <= 0) {
                         status[i] = !status[i];
                         float mean = status[i] ? mttf_f[i] : mttr_f[i];
-                        ttf[i] += (double)(mean * oracle_neglog_u32(stream_next(&st[i])));
+                        ttf[i] += duration_hours(mean, stream_next(&st[i]));
                     }
                     if (status[i]) cap_avail += cap[i];
                 }

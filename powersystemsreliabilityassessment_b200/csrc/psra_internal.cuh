@@ -82,37 +82,46 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0;
-        const uint32_t n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;   // IMAD.WIDE.U32
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;                    // one LOP3
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-// E = -ln((x + 0.5) / 2^32) in binary32 with a fixed sequence of correctly rounded
-// operations (DESIGN.md "Sampler"): reproducible bit for bit on any IEEE-754 machine.
+// E = -ln(u) of the draw x, u = (x | 1) / 2^32: integer normalisation + binary32 fma polynomial,
+// a fixed sequence of correctly rounded operations (DESIGN.md "Sampler"), reproducible bit for bit
+// on any IEEE-754 machine.  0 < E <= 32 ln 2.
 __device__ __forceinline__ float neglog_u32(uint32_t x)
 {
-    const unsigned long long n = 2ull * x + 1ull;
-    const float f = __ull2float_rn(n);
-    const uint32_t b = __float_as_uint(f);
-    int e = (int)(b >> 23) - 127;
-    float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
-    if (m > 1.41421354f) { m = __fmul_rn(m, 0.5f); e += 1; }
+    const uint32_t w = x | 1u;
+    const int lz = __clz((int)w);
+    const uint32_t X = w << lz;
+    const uint32_t bits = (X >> 8) + 0x3F000000u;           // m = X / 2^31 truncated to 24 bits
+    const uint32_t ix = bits + 0x004AFB0Du;                 // fdlibm range reduction to [sqrt(.5), sqrt(2))
+    const int k = lz + 1 - ((int)(ix >> 23) - 127);
+    const float m = __uint_as_float((ix & 0x007FFFFFu) + 0x3F3504F3u);
     const float t = __fadd_rn(m, -1.0f);
-    const float s = __fdiv_rn(t, __fadd_rn(2.0f, t));
-    const float z = __fmul_rn(s, s);
-    float p = __fmaf_rn(z, 0.111111112f, 0.142857149f);
-    p = __fmaf_rn(z, p, 0.2f);
-    p = __fmaf_rn(z, p, 0.333333343f);
-    p = __fmaf_rn(z, p, 1.0f);
-    const float lnm = __fmul_rn(__fmul_rn(2.0f, s), p);
-    const float k = (float)(33 - e);
-    const float E = __fmaf_rn(k, 9.0580006145e-06f, __fmaf_rn(k, 6.9313812256e-01f, -lnm));
-    return fmaxf(E, 9.31322575e-10f);
+    float p = 0x1.65b9f8p-4f;
+    p = __fmaf_rn(p, t, -0x1.27c4d6p-3f);
+    p = __fmaf_rn(p, t, 0x1.32c6a8p-3f);
+    p = __fmaf_rn(p, t, -0x1.52fdeep-3f);
+    p = __fmaf_rn(p, t, 0x1.98a666p-3f);
+    p = __fmaf_rn(p, t, -0x1.000688p-2f);
+    p = __fmaf_rn(p, t, 0x1.5557acp-2f);
+    p = __fmaf_rn(p, t, -0x1.fffff4p-2f);
+    const float r = __fmaf_rn(__fmul_rn(t, t), p, t);       // ln m
+    const float kf = (float)k;
+    return __fmaf_rn(kf, 9.0580006145e-06f, __fmaf_rn(kf, 6.9313812256e-01f, -r));
+}
+
+// duration of one draw in ticks of 2^-24 h: RN_int64(max(mean_ticks * E, 1)), mean_ticks = mean * 2^24
+__device__ __forceinline__ unsigned long long dur_ticks(float mean_ticks, uint32_t x)
+{
+    return (unsigned long long)__float2ll_rn(fmaxf(__fmul_rn(mean_ticks, neglog_u32(x)), 1.0f));
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)

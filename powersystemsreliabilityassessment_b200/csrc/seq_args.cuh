@@ -1,0 +1,26 @@
+// seq_args.cuh -- kernel arguments shared by the sequential-MC kernels (seq_mc.cu, seq_fast.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct SeqArgs {
+    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist;
+    const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
+    const int32_t *load; const int32_t *lmax;
+    uint32_t k0, k1;
+    long long chain_base;   // absolute index of local chain 0 (Philox counter)
+    long long nchains;
+    const double *dur;      // injected durations or nullptr
+    uint32_t *lol; long long *ens; uint32_t *ent; uint32_t *fail;
+    unsigned long long *group_lol; unsigned long long *acc;
+};
+
+// duration of one sampler draw in ticks of 2^-24 h (DESIGN.md "Sampler"): mean_ticks = mean * 2^24
+// in binary32, D = max(1, RN_int64(mean_ticks * E)).  All event-time arithmetic on ticks is exact.
+#define PSRA_TICK_SHIFT 24
+
+// seq_fast.cu
+size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block);
+int seq_fast_max_threads();
+cudaError_t seq_fast_prepare(size_t smem, int threads, int *blocks_per_sm);
+void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);

@@ -1,0 +1,356 @@
+// seq_fast.cu -- sampler-driven sequential chronological MC for systems of <= 32 units (RTS-79).
+//
+// Same model and same per-year integers as seq_mc.cu (run_sequential_mc,
+// GeneratingAdequacy/PowerSystemAdequacy.jl:214-269; indices per Montecarlo_seq/seqMain.m:160-176,
+// Montecarlo_seq/calnlc.m:22-34), reorganised so that lanes are busy:
+//
+//  * Time is kept in integer ticks of 2^-24 h.  A sampler duration is D = max(1, RN(mean*2^24*E))
+//    ticks, so every residual of the reference's `ttf -= 1.0` / `ttf += D` recurrence
+//    (PSA.jl:239-246) is an exact FP64 number and the event times are plain prefix sums
+//    T_k = D_0 + ... + D_k; event k toggles the unit in hour ceil(T_k / 2^24).
+//  * Prefix sums parallelise: in a "wave" every unit that does not yet cover the current timeline
+//    segment asks for 1..4 Philox blocks (4 draws each); the requested (unit, block) jobs are
+//    spread over the 32 lanes (lane = job, not lane = unit), each lane turns its block into four
+//    durations and a local prefix, and a segmented warp-shuffle scan chains the blocks of a unit.
+//    Lane utilisation no longer depends on the 6x spread of the units' event rates.
+//  * Events inside the segment are scattered into the warp's shared-memory hour timeline
+//    (atomicAdd of the integer MW delta, atomicOr into the event bitmap); events beyond it wait in
+//    a small pending list.  A wave is one round of <= 32 jobs: mandatory blocks for the units
+//    that are short, spare lanes pre-generate one block for units that run short next segment.
+//  * Evaluation: lane = run of consecutive 32-hour words.  Gather of the set bits, one shuffle
+//    scan per segment for the capacity entering each lane's run, conservative flag
+//    min-capacity-bound < max-load-of-word; flagged runs (rare) are resolved hour by hour with
+//    ballot/popc (LOL hours, deficit entries) and per-lane ENS accumulators.  The timeline segment
+//    is then cleared with 16-byte stores.
+#include <limits.h>
+
+#include "psra_internal.cuh"
+#include "seq_args.cuh"
+
+#define FAST_NB_MAX 4                  // Philox blocks a unit may request per wave
+#define FAST_PEND_CAP 512              // 32 units x 4 blocks x 4 draws
+#define FAST_MAX_THREADS 768
+
+struct FastWarpSmem {                  // per-warp scratch that precedes the timeline
+    unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit
+    uint32_t pend[FAST_PEND_CAP];      // (hour << 6) | (unit << 1) | (delta > 0)
+    unsigned char jobmap[32 * FAST_NB_MAX];
+};
+
+__host__ __device__ inline size_t fast_warp_bytes(int seg_words)
+{
+    size_t b = sizeof(FastWarpSmem) + sizeof(int32_t) * (size_t)seg_words * 32 +
+               sizeof(uint32_t) * (size_t)((seg_words + 3) & ~3);
+    return (b + 15) & ~(size_t)15;
+}
+
+size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block)
+{
+    size_t b = sizeof(int32_t) * ((size_t)Wd * 32 + (size_t)((Wd + 3) & ~3));   // load curve + word maxima
+    b += 32 * (sizeof(int32_t) + 2 * sizeof(float) + sizeof(uint32_t));       // unit tables
+    return b + (size_t)warps_per_block * fast_warp_bytes(seg_words);
+}
+
+int seq_fast_max_threads() { return FAST_MAX_THREADS; }
+
+__global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int Hpad = a.Wd * 32;
+    int32_t *s_load = reinterpret_cast<int32_t *>(smem_raw);
+    int32_t *s_lmax = s_load + Hpad;
+    int32_t *s_cap = s_lmax + ((a.Wd + 3) & ~3);
+    float *s_mup = reinterpret_cast<float *>(s_cap + 32);
+    float *s_mdn = s_mup + 32;
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_mdn + 32);
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_thr + 32) + (size_t)warp * fast_warp_bytes(a.seg_words);
+    FastWarpSmem *ws = reinterpret_cast<FastWarpSmem *>(wbase);
+    int32_t *tl = reinterpret_cast<int32_t *>(wbase + sizeof(FastWarpSmem));
+    const int seg_slots = a.seg_words * 32;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(tl + seg_slots);
+    const int bm_words = (a.seg_words + 3) & ~3;
+
+    for (int i = threadIdx.x; i < Hpad; i += blockDim.x) s_load[i] = a.load[i];
+    for (int i = threadIdx.x; i < a.Wd; i += blockDim.x) s_lmax[i] = a.lmax[i];
+    if (threadIdx.x < 32) {
+        const bool v = threadIdx.x < a.U;
+        s_cap[threadIdx.x] = v ? a.cap[threadIdx.x] : 0;
+        s_mup[threadIdx.x] = v ? __fmul_rn(a.mttf[threadIdx.x], 16777216.0f) : 1.0f;
+        s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
+        s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
+    }
+    for (int i = lane; i < seg_slots; i += 32) tl[i] = 0;
+    for (int i = lane; i < bm_words; i += 32) bm[i] = 0u;
+    __syncthreads();
+
+    unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
+    long long acc_ens = 0;
+    unsigned int n_events = 0;
+
+    const bool unit_valid = lane < a.U;
+    const int capu = s_cap[lane];
+    // expected Philox blocks per hour of horizon: a block holds 4 durations = 2 up/down cycles
+    const float inv_span = unit_valid ? __fdividef(0.5f, a.mttf[min(lane, a.U - 1)] + a.mttr[min(lane, a.U - 1)]) : 0.f;
+
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const int chain_end_h = a.ypc * a.H;
+
+    for (long long cl = gw; cl < a.nchains; cl += nw) {
+        const unsigned long long chain = (unsigned long long)(a.chain_base + cl);
+        uint32_t nb = 0;              // next Philox block of unit `lane`
+        uint32_t s0mask = 0;          // initial states (bit u = UP)
+        int pend_cnt = 0;
+        int capacity = 0;
+        ws->t_run[lane] = 0ull;
+        __syncwarp();
+        bool init_wave = true;
+
+        for (int y = 0; y < a.ypc; y++) {
+            unsigned int lolh = 0, entries = 0;
+            long long ens_lane = 0;
+            for (int seg = 0; seg < a.nseg; seg++) {
+                const int seg_h0 = seg * seg_slots;
+                const int seg_h1 = min(a.H, seg_h0 + seg_slots);
+                const int abs0 = y * a.H + seg_h0, abs1 = y * a.H + seg_h1;   // chain-relative hours
+                const unsigned long long seg_end_t = (unsigned long long)abs1 << PSRA_TICK_SHIFT;
+
+                // ---- pending events that fall into this segment
+                if (pend_cnt) {
+                    int outc = 0;
+                    for (int base = 0; base < pend_cnt; base += 32) {
+                        const int i = base + lane;
+                        const bool v = i < pend_cnt;
+                        const uint32_t e = v ? ws->pend[i] : 0u;
+                        const int hs = (int)(e >> 6);
+                        const bool take = v && hs < abs1;
+                        if (take) {
+                            const int c = s_cap[(e >> 1) & 31];
+                            const int slot = hs - abs0;
+                            atomicAdd(&tl[slot], (e & 1u) ? c : -c);
+                            atomicOr(&bm[slot >> 5], 1u << (slot & 31));
+                        }
+                        const bool keep = v && !take;
+                        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+                        __syncwarp();
+                        if (keep) ws->pend[outc + __popc(km & lt_mask)] = e;
+                        outc += __popc(km);
+                    }
+                    pend_cnt = outc;
+                }
+
+                // ---- waves: one round of <= 32 (unit, block) jobs each, until every unit covers the segment
+                const unsigned long long ahead_t = seg_end_t + ((unsigned long long)seg_slots << PSRA_TICK_SHIFT);
+                const unsigned long long chain_end_t = (unsigned long long)chain_end_h << PSRA_TICK_SHIFT;
+                while (true) {
+                    const unsigned long long tlast = ws->t_run[lane];
+                    const bool is_short = unit_valid && tlast <= seg_end_t;
+                    if (!__any_sync(0xffffffffu, is_short)) break;
+                    int n_u = 0;
+                    if (is_short) {
+                        if (init_wave) n_u = 1;
+                        else {
+                            const float rem_h = (float)(int)((seg_end_t - tlast) >> PSRA_TICK_SHIFT);
+                            n_u = min(FAST_NB_MAX, 1 + (int)(rem_h * inv_span));
+                        }
+                    }
+                    const int incl = warp_incl_scan(n_u, lane);
+                    int off = incl - n_u;
+                    int J = __shfl_sync(0xffffffffu, incl, 31);
+                    if (J > 32) {                  // truncate; the remaining demand is served by the next wave
+                        n_u = max(0, min(n_u, 32 - off));
+                        J = 32;
+                    } else if (J < 32 && !init_wave && pend_cnt <= FAST_PEND_CAP / 2) {
+                        // spare lanes: one block ahead for units that run short within the next segment
+                        const bool elig = unit_valid && !is_short && tlast <= ahead_t && tlast <= chain_end_t;
+                        const uint32_t em = __ballot_sync(0xffffffffu, elig);
+                        const int rank = __popc(em & lt_mask);
+                        if (elig && rank < 32 - J) { n_u = 1; off = J + rank; }
+                        J = min(32, J + __popc(em));
+                    }
+#pragma unroll
+                    for (int k = 0; k < FAST_NB_MAX; k++)
+                        if (k < n_u) ws->jobmap[off + k] = (unsigned char)lane;
+                    __syncwarp();
+                    {
+                        const bool act = lane < J;               // lane = job
+                        const int u = act ? (int)ws->jobmap[lane] : 0;
+                        const int offu = __shfl_sync(0xffffffffu, off, u);
+                        const int nu = __shfl_sync(0xffffffffu, n_u, u);
+                        const uint32_t b = __shfl_sync(0xffffffffu, nb, u) + (uint32_t)(lane - offu);
+                        const bool is_last = act && (lane - offu) == nu - 1;
+
+                        uint32_t x[4];
+                        philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, b, a.k0, a.k1, x);
+                        bool s0u;
+                        if (b == 0u) s0u = !(a.init_mode == PSRA_INIT_STATIONARY && x[0] < s_thr[u]);
+                        else s0u = (s0mask >> u) & 1u;
+                        const float mup = s_mup[u], mdn = s_mdn[u];
+                        const float m_a = s0u ? mdn : mup;      // draws 0, 2 of a block: state s0^1
+                        const float m_b = s0u ? mup : mdn;      // draws 1, 3: state s0
+                        const unsigned long long p1 = (b == 0u) ? 0ull : dur_ticks(m_a, x[0]);
+                        const unsigned long long p2 = p1 + dur_ticks(m_b, x[1]);
+                        const unsigned long long p3 = p2 + dur_ticks(m_a, x[2]);
+                        const unsigned long long p4 = p3 + dur_ticks(m_b, x[3]);
+                        const unsigned long long tot = act ? p4 : 0ull;
+                        unsigned long long inc2 = tot;
+#pragma unroll
+                        for (int d = 1; d <= 2; d <<= 1) {       // runs are <= FAST_NB_MAX = 4 lanes long
+                            const unsigned long long o = __shfl_up_sync(0xffffffffu, inc2, d);
+                            if (lane - d >= offu) inc2 += o;
+                        }
+                        const unsigned long long base_t = ws->t_run[u] + (inc2 - tot);
+                        __syncwarp();
+                        if (is_last) ws->t_run[u] = base_t + tot;
+
+                        const int cu = s_cap[u];
+                        const int delta_a = s0u ? cu : -cu;      // draws 0, 2 toggle the unit back to s0
+                        if (b == 0u && act) s0mask = s0u ? 1u : 0u;   // init wave (job lane == unit lane), ballot below
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const unsigned long long te = base_t + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
+                            const bool valid = act && !(b == 0u && q == 0);
+                            const unsigned long long h64 = (te - 1ull) >> PSRA_TICK_SHIFT;
+                            const bool inhor = valid && h64 < (unsigned long long)chain_end_h;
+                            const int hs = (int)h64;
+                            const int delta = (q & 1) ? -delta_a : delta_a;
+                            const bool in_seg = inhor && hs < abs1;
+                            if (in_seg) {
+                                const int slot = hs - abs0;
+                                atomicAdd(&tl[slot], delta);
+                                atomicOr(&bm[slot >> 5], 1u << (slot & 31));
+                            }
+                            const bool pnd = inhor && !in_seg;
+                            const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
+                            if (pm) {
+                                const int pos = pend_cnt + __popc(pm & lt_mask);
+                                if (pnd && pos < FAST_PEND_CAP)
+                                    ws->pend[pos] = ((uint32_t)hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
+                                pend_cnt += __popc(pm);
+                            }
+                            n_events += inhor ? 1u : 0u;
+                        }
+                        __syncwarp();
+                    }
+                    nb += (uint32_t)n_u;
+                    if (init_wave) {
+                        s0mask = __ballot_sync(0xffffffffu, unit_valid && (s0mask & 1u));
+                        int cp = (unit_valid && ((s0mask >> lane) & 1u)) ? capu : 0;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) cp += __shfl_xor_sync(0xffffffffu, cp, d);
+                        capacity = cp;
+                        init_wave = false;
+                    }
+                }
+                if (pend_cnt > FAST_PEND_CAP) {                  // reported as PSRA_E_OVERFLOW (never seen in practice)
+                    if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 2ull);
+                    pend_cnt = FAST_PEND_CAP;
+                }
+                __syncwarp();
+
+                // ---- evaluation: lane = run of `wpl` consecutive words
+                const int nwords = (seg_h1 - seg_h0 + 31) >> 5;
+                const int wpl = (nwords + 31) >> 5;
+                const int wb = lane * wpl;
+                int loc = 0, lmin = INT_MAX;
+                for (int k = 0; k < wpl; k++) {
+                    const int w = wb + k;
+                    if (w < nwords) {
+                        int s = 0, neg = 0;
+                        for (uint32_t mm = bm[w]; mm; mm &= mm - 1) {
+                            const int d = tl[w * 32 + (__ffs(mm) - 1)];
+                            s += d;
+                            neg += min(d, 0);
+                        }
+                        lmin = min(lmin, loc + neg - s_lmax[seg * a.seg_words + w]);
+                        loc += s;
+                    }
+                }
+                const int incl = warp_incl_scan(loc, lane);
+                const int cs_lane = capacity + incl - loc;       // capacity entering the lane's run
+                const bool flagged = (lmin != INT_MAX) && (cs_lane + lmin < 0);
+                uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+                while (fm) {                                     // rare: hour-by-hour, lane = hour
+                    const int src = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    int c_in = __shfl_sync(0xffffffffu, cs_lane, src);
+                    for (int k = 0; k < wpl; k++) {
+                        const int wq = src * wpl + k;
+                        if (wq >= nwords) break;
+                        const int c = c_in + warp_incl_scan(tl[wq * 32 + lane], lane);
+                        const int hy0 = seg_h0 + wq * 32;
+                        const int L = s_load[hy0 + lane];
+                        const bool lol = c < L;                  // PSA.jl:253 strict
+                        const uint32_t mask = __ballot_sync(0xffffffffu, lol);
+                        if (mask) {
+                            const uint32_t prev = (hy0 > 0 && c_in < s_load[hy0 - 1]) ? 1u : 0u;
+                            lolh += __popc(mask);
+                            entries += __popc(mask & ~((mask << 1) | prev));   // calnlc.m:22-34
+                            if (lol) {
+                                ens_lane += (long long)(L - c);
+                                if (a.fail) atomicAdd(&a.fail[hy0 + lane], 1u);
+                            }
+                        }
+                        c_in = __shfl_sync(0xffffffffu, c, 31);
+                    }
+                }
+                capacity += __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
+                {   // clear the segment with 16-byte stores
+                    int4 *t4 = reinterpret_cast<int4 *>(tl);
+                    const int n4 = nwords * 8;
+                    for (int i = lane; i < n4; i += 32) t4[i] = make_int4(0, 0, 0, 0);
+                    for (int i = lane; i < nwords; i += 32) bm[i] = 0u;
+                }
+                __syncwarp();
+            }
+
+            // ---- per-year indices
+            long long ens = 0;
+            if (lolh) ens = warp_sum_ll(ens_lane);
+            const long long yi = cl * a.ypc + y;
+            if (lane == 0) {
+                if (a.lol) a.lol[yi] = lolh;
+                if (a.ens) a.ens[yi] = ens;
+                if (a.ent) a.ent[yi] = entries;
+                if (a.group_lol && lolh) atomicAdd(&a.group_lol[yi / a.group], (unsigned long long)lolh);
+            }
+            acc_lol += lolh; acc_ens += ens; acc_ent += entries;
+            acc_ywl += lolh ? 1 : 0;
+            acc_lol2 += (unsigned long long)lolh * lolh;
+            const unsigned long long e = (unsigned long long)ens;
+            const unsigned long long plo = e * e, phi = __umul64hi(e, e);
+            const unsigned long long nlo = acc_e2lo + plo;
+            acc_e2hi += phi + (nlo < acc_e2lo ? 1ull : 0ull);
+            acc_e2lo = nlo;
+        }
+        __syncwarp();
+    }
+
+    unsigned long long ev = n_events;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ev += __shfl_xor_sync(0xffffffffu, ev, d);
+    if (lane == 0) {
+        if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
+        if (acc_ens) atomicAdd(&a.acc[ACC_ENS], (unsigned long long)acc_ens);
+        if (acc_ent) atomicAdd(&a.acc[ACC_ENT], acc_ent);
+        if (acc_ywl) atomicAdd(&a.acc[ACC_YWL], acc_ywl);
+        if (acc_lol2) atomicAdd(&a.acc[ACC_LOL2], acc_lol2);
+        if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
+        if (ev) atomicAdd(&a.acc[ACC_EVENTS], ev);
+    }
+}
+
+cudaError_t seq_fast_prepare(size_t smem, int threads, int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(seq_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, seq_fast_kernel, threads, smem);
+}
+
+void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
+{
+    seq_fast_kernel<<<grid, threads, smem, stream>>>(a);
+}

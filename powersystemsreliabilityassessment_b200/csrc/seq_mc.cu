@@ -32,18 +32,8 @@
 #include <vector>
 
 #include "psra_internal.cuh"
+#include "seq_args.cuh"
 
-struct SeqArgs {
-    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist;
-    const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
-    const int32_t *load; const int32_t *lmax;
-    uint32_t k0, k1;
-    long long chain_base;   // absolute index of local chain 0 (Philox counter)
-    long long nchains;
-    const double *dur;      // injected durations or nullptr
-    uint32_t *lol; long long *ens; uint32_t *ent; uint32_t *fail;
-    unsigned long long *group_lol; unsigned long long *acc;
-};
 
 struct UnitState {
     double r;        // residual after the decrement of hour `next` (<= 0)
@@ -80,7 +70,9 @@ __device__ __forceinline__ double next_duration(const SeqArgs &a, long long chai
         return d;
     } else {
         const uint32_t x = next_word<false>(a, chain, u, s);
-        return (double)__fmul_rn(s.status ? mf : mr, neglog_u32(x));
+        // tick-quantised duration (2^-24 h), same definition as seq_fast.cu / DESIGN.md "Sampler"
+        const float mt = __fmul_rn(s.status ? mf : mr, 16777216.0f);
+        return (double)dur_ticks(mt, x) * 5.9604644775390625e-08;
     }
 }
 
@@ -307,6 +299,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (nyears == 0) return PSRA_OK;
 
     const bool one_unit = h->U <= 32;
+    const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0];
     SeqArgs a{};
     a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode; a.K = K;
     a.cap = h->d_cap; a.mttf = h->d_mttf; a.mttr = h->d_mttr; a.for_thr = h->d_for_thr;
@@ -318,15 +311,16 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     // launch geometry: segment length and warps per block under the shared-memory budget
     int seg_words = h->Wd;
     if (one_unit) {
-        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : 1120;
+        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : (fast ? 2208 : 1120);
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
     a.seg_words = seg_words;
     a.nseg = (h->Wd + seg_words - 1) / seg_words;
     a.persist = (!one_unit && (ypc > 1 || a.nseg > 1)) ? 1 : 0;
-    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : 16;
-    wpb = std::max(1, std::min(16, wpb));
+    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 24 : 16);
+    wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
+        if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w);
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
         if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
@@ -384,9 +378,13 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     void (*kern)(SeqArgs) = nullptr;
     if (injected) kern = one_unit ? seq_mc_kernel<true, true> : seq_mc_kernel<true, false>;
     else          kern = one_unit ? seq_mc_kernel<false, true> : seq_mc_kernel<false, false>;
-    PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = 0;
-    PSRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
+    if (fast) {
+        PSRA_CUDA(h, seq_fast_prepare(smem, wpb * 32, &bps));
+    } else {
+        PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PSRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
+    }
     if (bps < 1) return psra_fail(h, PSRA_E_CUDA, "sequential kernel does not fit on an SM (smem %zu B)", smem);
     if (h->cfg.blocks_per_sm > 0) bps = std::min(bps, h->cfg.blocks_per_sm);
     long long grid = (long long)h->sm_count * bps;
@@ -394,7 +392,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (grid > need) grid = need;
 
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
+    if (fast) seq_fast_launch(a, (unsigned)grid, wpb * 32, smem, h->stream);
+    else kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
     PSRA_CUDA(h, cudaGetLastError());
     PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));
 
@@ -420,6 +419,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     summary->sum_ens_sq_hi = acc[ACC_ENS2_HI];
     summary->events = acc[ACC_EVENTS];
     if (want_vec && out->keep_on_device) h->kept_n = nyears;
+    if (acc[ACC_OVERFLOW] == 2ull)
+        return psra_fail(h, PSRA_E_OVERFLOW, "internal error: pending-event list overflow in the sequential kernel");
     if (acc[ACC_OVERFLOW])
         return psra_fail(h, PSRA_E_OVERFLOW, "injected durations exhausted: a unit needed more than K=%d draws", K);
     return PSRA_OK;

@@ -7,8 +7,8 @@ years = int(float(sys.argv[1])) if len(sys.argv) > 1 else 2_000_000
 cap, mttf, mttr = rts79.units()
 load = rts79.load_curve_int()
 rows = []
-for seg in (8736, 4384, 2208, 1120, 576, 288):
-    for wpb in (4, 8, 16):
+for seg in (8736, 4384, 2944, 2208, 1472, 1120, 576):
+    for wpb in (8, 12, 16, 24):
         try:
             with Engine(seg_hours=seg, warps_per_block=wpb) as e:
                 e.set_system(cap, mttf, mttr); e.set_load(load)

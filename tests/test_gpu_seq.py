@@ -135,14 +135,46 @@ def test_sharding_invariance_and_segments(engine, rts):
     assert np.array_equal(full.raw["ens_fp_vector"], np.concatenate([a.raw["ens_fp_vector"], b.raw["ens_fp_vector"]]))
     for k in ("sum_lol_hours", "sum_ens_fp", "sum_entries", "sum_lol_sq", "sum_ens_sq", "years_with_loss"):
         assert full.raw[k] == a.raw[k] + b.raw[k]
-    for seg, wpb in ((8736, 4), (1120, 16), (320, 8), (32, 2)):
-        with Engine(seg_hours=seg, warps_per_block=wpb) as e2:
+    for seg, wpb, gen in ((8736, 4, False), (1120, 16, False), (320, 8, False), (32, 2, False), (2208, 24, False),
+                          (8736, 4, True), (1120, 16, True), (320, 8, True)):
+        with Engine(seg_hours=seg, warps_per_block=wpb, force_generic=gen) as e2:
             e2.set_system(rts["cap"], rts["mttf"], rts["mttr"]); e2.set_load(rts["load_int"])
             r2 = e2.seq_mc(4096, seed=5, per_year=True, group=10)
             assert np.array_equal(full.lol_hours, r2.lol_hours)
             assert np.array_equal(full.raw["ens_fp_vector"], r2.raw["ens_fp_vector"])
             assert np.array_equal(full.entries, r2.entries)
             assert np.array_equal(r2.group_lol[:409], full.lol_hours[:4090].reshape(-1, 10).sum(1))
+            assert r2.raw["events"] == full.raw["events"]
+
+
+def test_fast_and_generic_kernels_agree_in_chain_mode(engine, rts):
+    """seq_fast.cu (wave / prefix-sum formulation) and seq_mc.cu (FP64 residual recurrence) are two
+    independent implementations of the same chain; multi-year chains exercise the pending list."""
+    from powersystemsreliabilityassessment_b200 import Engine
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(rts["load_int"])
+    for init_mode, ypc in ((0, 5), (1, 25)):
+        a = engine.seq_mc(3000, seed=17, init_mode=init_mode, years_per_chain=ypc, per_year=True, fail_count=True)
+        with Engine(force_generic=True, seg_hours=4384) as g:
+            g.set_system(rts["cap"], rts["mttf"], rts["mttr"]); g.set_load(rts["load_int"])
+            b = g.seq_mc(3000, seed=17, init_mode=init_mode, years_per_chain=ypc, per_year=True, fail_count=True)
+        assert np.array_equal(a.lol_hours, b.lol_hours) and np.array_equal(a.entries, b.entries)
+        assert np.array_equal(a.raw["ens_fp_vector"], b.raw["ens_fp_vector"])
+        assert np.array_equal(a.fail_count, b.fail_count)
+        assert a.raw["events"] == b.raw["events"] and a.lol_hours.sum() > 0
+
+
+def test_small_unit_counts_and_short_years_fast_path(engine):
+    """U < 32 and tiny H through the sampler path vs the oracle's literal loop."""
+    cap = np.array([10.0, 5.0, 7.0]); mttf = np.array([30.0, 20.0, 3.0]); mttr = np.array([10.0, 15.0, 2.0])
+    for H in (1, 31, 33, 100, 1000):
+        load = np.full(H, 14, dtype=np.int32)
+        engine.set_system(cap, mttf, mttr); engine.set_load(load)
+        for ypc in (1, 4):
+            r = engine.seq_mc(32 * ypc, seed=H, init_mode=1, years_per_chain=ypc, per_year=True)
+            lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), H, 0, 32, ypc, 1)
+            assert np.array_equal(r.lol_hours.astype(np.float64), lol)
+            assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+            assert np.array_equal(r.entries.astype(np.float64), ent)
 
 
 def test_statistics_match_analytical_rts79(engine, rts):

@@ -87,12 +87,20 @@ def test_philox_known_answer_vectors():
 
 
 def test_neglog_accuracy_and_range():
+    """E(x) = -ln((x|1) / 2^32) to binary32 accuracy (mantissa truncated to 24 bits: |du/u| < 2^-23)."""
     rng = np.random.default_rng(0)
-    for x in list(rng.integers(0, 2**32, 5000)) + [0, 1, 2**31, 2**32 - 1, 2**32 - 2]:
+    for x in list(rng.integers(0, 2**32, 5000)) + [0, 1, 2, 3, 2**31, 2**32 - 1, 2**32 - 2, 2**24, 2**24 - 1]:
         e = O.neglog_u32(int(x))
-        ref = -math.log((int(x) + 0.5) / 2**32)
-        assert e > 0 and abs(e - ref) < 2e-7 * max(ref, 1.0) + 1.5e-7
-    assert O.neglog_u32(0) == pytest.approx(-math.log(0.5 / 2**32), rel=1e-6)
+        ref = -math.log((int(x) | 1) / 2**32)
+        assert 0 < e <= 32 * math.log(2) * (1 + 1e-6)
+        assert abs(e - ref) < 1.3e-7 * max(ref, 1.0) + 1.3e-7
+    assert O.neglog_u32(0) == pytest.approx(32 * math.log(2), rel=1e-6)
+    es = np.array([O.neglog_u32(int(x)) for x in rng.integers(0, 2**32, 200000)])
+    assert abs(es.mean() - 1.0) < 4 / math.sqrt(len(es))
+    # durations are whole ticks of 2^-24 h, at least one tick
+    for mean, x in ((1100.0, 12345), (1e-5, 2**32 - 1), (2940.0, 0)):
+        d = O.duration_hours(mean, x)
+        assert d >= 2.0**-24 and d * 2**24 == int(d * 2**24)
 
 
 def test_event_form_identity():
