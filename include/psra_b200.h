@@ -63,6 +63,10 @@ uint64_t psra_stream(const psra_handle *h);
 /* SM count and SM clock (kHz) of the handle's device */
 int  psra_device_info(const psra_handle *h, int32_t *sm_count, int32_t *sm_clock_khz);
 
+/* diagnostics: raw accumulator slots of the last Monte Carlo call (slot 9 = generation waves,
+ * 10 = Philox block jobs, 11 = of which pre-generated ahead, 12 = hour-resolved timeline runs) */
+int  psra_last_counters(const psra_handle *h, uint64_t *out, int32_t n);
+
 /* system data: replaces struct Generator / LoadModel, PSA.jl:20-45 ------------------ */
 /* cap_fp[U] fixed-point MW; mttf_h / mttr_h in hours (lambda = 1/MTTF, mu = 1/MTTR,
  * FOR = lambda/(lambda+mu), PSA.jl:32-37) */

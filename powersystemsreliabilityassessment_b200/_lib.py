@@ -21,7 +21,7 @@ INIT_ALL_UP = 0
 INIT_STATIONARY = 1
 
 EXPORTS = [
-    "psra_create", "psra_destroy", "psra_last_error", "psra_version", "psra_stream", "psra_device_info",
+    "psra_create", "psra_destroy", "psra_last_error", "psra_version", "psra_stream", "psra_device_info", "psra_last_counters",
     "psra_set_system", "psra_set_load", "psra_seq_mc", "psra_seq_eval_injected", "psra_nonseq_mc",
     "psra_nonseq_eval_states", "psra_nonseq_eval_uniforms", "psra_copt", "psra_copt_indices",
     "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail",
@@ -83,6 +83,7 @@ def load():
     L.psra_version.restype = C.c_int; L.psra_version.argtypes = []
     L.psra_stream.restype = u64; L.psra_stream.argtypes = [vp]
     L.psra_device_info.restype = C.c_int; L.psra_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.psra_last_counters.restype = C.c_int; L.psra_last_counters.argtypes = [vp, vp, i32]
     L.psra_set_system.restype = C.c_int; L.psra_set_system.argtypes = [vp, vp, vp, vp, i32]
     L.psra_set_load.restype = C.c_int; L.psra_set_load.argtypes = [vp, vp, i32]
     L.psra_seq_mc.restype = C.c_int

@@ -58,6 +58,13 @@ extern "C" int psra_device_info(const psra_handle *h, int32_t *sm_count, int32_t
     return PSRA_OK;
 }
 
+extern "C" int psra_last_counters(const psra_handle *h, uint64_t *out, int32_t n)
+{
+    if (!h || !out || n < 0) return PSRA_E_INVALID;
+    for (int i = 0; i < n; i++) out[i] = i < ACC_COUNT_MAX ? h->last_acc[i] : 0;
+    return PSRA_OK;
+}
+
 extern "C" int psra_create(psra_handle **out, const psra_config *cfg)
 {
     if (!out) return PSRA_E_INVALID;

@@ -14,6 +14,7 @@
 
 #define PSRA_VERSION 1001
 
+#define ACC_COUNT_MAX 32
 struct psra_handle {
     int device = 0;
     int sm_count = 0;
@@ -52,6 +53,7 @@ struct psra_handle {
     long long *d_group = nullptr; int64_t group_cap = 0;
     void *d_scratch = nullptr; size_t scratch_cap = 0;   // inputs of injected paths, tail keys
     void *d_scratch2 = nullptr; size_t scratch2_cap = 0;
+    unsigned long long last_acc[ACC_COUNT_MAX] = {0};   // accumulators of the last MC call (diagnostics)
 };
 
 int psra_fail(psra_handle *h, int code, const char *fmt, ...);
@@ -155,5 +157,5 @@ __device__ __forceinline__ void atomic_add_u128(unsigned long long *lo, unsigned
 // accumulator slots in d_acc
 enum {
     ACC_LOL = 0, ACC_ENS, ACC_ENT, ACC_YWL, ACC_LOL2, ACC_ENS2_LO, ACC_ENS2_HI, ACC_EVENTS,
-    ACC_OVERFLOW, ACC_COUNT = 32
+    ACC_OVERFLOW, ACC_WAVES, ACC_JOBS, ACC_OPT_JOBS, ACC_FLAGGED, ACC_COUNT = 32
 };

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
     long long acc_ens = 0;
     unsigned int n_events = 0;
+    unsigned int n_waves = 0, n_jobs = 0, n_opt = 0, n_flag = 0;   // warp-uniform diagnostics
 
     const bool unit_valid = lane < a.U;
     const int capu = s_cap[lane];
@@ -162,14 +163,20 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     if (J > 32) {                  // truncate; the remaining demand is served by the next wave
                         n_u = max(0, min(n_u, 32 - off));
                         J = 32;
+                        n_jobs += 32;
                     } else if (J < 32 && !init_wave && pend_cnt <= FAST_PEND_CAP / 2) {
                         // spare lanes: one block ahead for units that run short within the next segment
                         const bool elig = unit_valid && !is_short && tlast <= ahead_t && tlast <= chain_end_t;
                         const uint32_t em = __ballot_sync(0xffffffffu, elig);
                         const int rank = __popc(em & lt_mask);
                         if (elig && rank < 32 - J) { n_u = 1; off = J + rank; }
-                        J = min(32, J + __popc(em));
+                        const int J2 = min(32, J + __popc(em));
+                        n_opt += J2 - J; n_jobs += J2;
+                        J = J2;
+                    } else {
+                        n_jobs += J;
                     }
+                    n_waves++;
 #pragma unroll
                     for (int k = 0; k < FAST_NB_MAX; k++)
                         if (k < n_u) ws->jobmap[off + k] = (unsigned char)lane;
@@ -272,6 +279,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 const int cs_lane = capacity + incl - loc;       // capacity entering the lane's run
                 const bool flagged = (lmin != INT_MAX) && (cs_lane + lmin < 0);
                 uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+                n_flag += __popc(fm);
                 while (fm) {                                     // rare: hour-by-hour, lane = hour
                     const int src = __ffs(fm) - 1;
                     fm &= fm - 1;
@@ -340,6 +348,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         if (acc_lol2) atomicAdd(&a.acc[ACC_LOL2], acc_lol2);
         if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
         if (ev) atomicAdd(&a.acc[ACC_EVENTS], ev);
+        atomicAdd(&a.acc[ACC_WAVES], (unsigned long long)n_waves);
+        atomicAdd(&a.acc[ACC_JOBS], (unsigned long long)n_jobs);
+        atomicAdd(&a.acc[ACC_OPT_JOBS], (unsigned long long)n_opt);
+        atomicAdd(&a.acc[ACC_FLAGGED], (unsigned long long)n_flag);
     }
 }
 

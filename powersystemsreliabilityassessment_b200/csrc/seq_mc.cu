@@ -418,6 +418,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     summary->sum_ens_sq_lo = acc[ACC_ENS2_LO];
     summary->sum_ens_sq_hi = acc[ACC_ENS2_HI];
     summary->events = acc[ACC_EVENTS];
+    memcpy(h->last_acc, acc, sizeof(acc));
     if (want_vec && out->keep_on_device) h->kept_n = nyears;
     if (acc[ACC_OVERFLOW] == 2ull)
         return psra_fail(h, PSRA_E_OVERFLOW, "internal error: pending-event list overflow in the sequential kernel");

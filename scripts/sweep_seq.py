@@ -7,15 +7,15 @@ years = int(float(sys.argv[1])) if len(sys.argv) > 1 else 2_000_000
 cap, mttf, mttr = rts79.units()
 load = rts79.load_curve_int()
 rows = []
-for seg in (8736, 4384, 2944, 2208, 1472, 1120, 576):
-    for wpb in (8, 12, 16, 24):
+for seg in (4384, 2944, 2208, 1760, 1472, 1120):
+    for wpb in (16, 24):
         try:
             with Engine(seg_hours=seg, warps_per_block=wpb) as e:
                 e.set_system(cap, mttf, mttr); e.set_load(load)
                 e.seq_mc(200_000, seed=1)
                 best = min(e.seq_mc(years, seed=2 + i).kernel_ms for i in range(3))
                 r = e.seq_mc(years, seed=2)
-                rows.append(dict(seg=seg, wpb=wpb, ms=best, yps=years / best * 1e3, lole=r.lole, events_per_year=r.events / years))
+                c = e.last_counters(); rows.append(dict(seg=seg, wpb=wpb, ms=round(best, 2), Myps=round(years / best / 1e3, 1), waves=c['waves'] / years, jobs=c['jobs'] / years, ahead=c['ahead_jobs'] / years, runs=c['resolved_runs'] / years))
                 print(rows[-1], flush=True)
         except Exception as ex:
             print("fail", seg, wpb, ex, flush=True)
