@@ -13,10 +13,12 @@
 //    spread over the 32 lanes (lane = job, not lane = unit), each lane turns its block into four
 //    durations and a local prefix, and a segmented warp-shuffle scan chains the blocks of a unit.
 //    Lane utilisation no longer depends on the 6x spread of the units' event rates.
-//  * Events inside the segment are scattered into the warp's shared-memory hour timeline
-//    (atomicAdd of the integer MW delta, atomicOr into the event bitmap); events beyond it wait in
-//    a small pending list.  A wave is one round of <= 32 jobs: mandatory blocks for the units
-//    that are short, spare lanes pre-generate one block for units that run short next segment.
+//  * The warp's shared-memory hour timeline is a ring of two segments.  Events of the current and
+//    of the next segment are scattered directly (atomicAdd of the integer MW delta -- two int16
+//    hours packed per word when the installed capacity allows -- and atomicOr into the event
+//    bitmap); the rare events beyond the ring wait in a small pending list.  A wave is one round
+//    of <= 32 jobs: blocks for the units that are short of the current segment first, the spare
+//    lanes pre-generate blocks towards the end of the next segment.
 //  * Evaluation: lane = run of consecutive 32-hour words.  Gather of the set bits, one shuffle
 //    scan per segment for the capacity entering each lane's run, conservative flag
 //    min-capacity-bound < max-load-of-word; flagged runs (rare) are resolved hour by hour with
@@ -27,52 +29,85 @@
 #include "psra_internal.cuh"
 #include "seq_args.cuh"
 
-#define FAST_NB_MAX 4                  // Philox blocks a unit may request per wave
-#define FAST_PEND_CAP 512              // 32 units x 4 blocks x 4 draws
+#define FAST_NB_MAX 4                  // Philox blocks a unit may get per wave
+#define FAST_PEND_CAP 256              // far-future events (beyond the two-segment ring)
 #define FAST_MAX_THREADS 768
 
-struct FastWarpSmem {                  // per-warp scratch that precedes the timeline
+struct FastWarpSmem {                  // per-warp scratch that precedes the timeline ring
     unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit
     uint32_t pend[FAST_PEND_CAP];      // (hour << 6) | (unit << 1) | (delta > 0)
     unsigned char jobmap[32 * FAST_NB_MAX];
 };
 
-__host__ __device__ inline size_t fast_warp_bytes(int seg_words)
+__host__ __device__ inline size_t fast_warp_bytes(int seg_words, bool packed)
 {
-    size_t b = sizeof(FastWarpSmem) + sizeof(int32_t) * (size_t)seg_words * 32 +
-               sizeof(uint32_t) * (size_t)((seg_words + 3) & ~3);
+    size_t b = sizeof(FastWarpSmem) + 2 * (packed ? 2 : 4) * (size_t)seg_words * 32 +
+               2 * sizeof(uint32_t) * (size_t)((seg_words + 3) & ~3);
     return (b + 15) & ~(size_t)15;
 }
 
-size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block)
+__host__ __device__ inline size_t fast_block_bytes(int Wd, bool load16)
 {
-    size_t b = sizeof(int32_t) * ((size_t)Wd * 32 + (size_t)((Wd + 3) & ~3));   // load curve + word maxima
-    b += 32 * (sizeof(int32_t) + 2 * sizeof(float) + sizeof(uint32_t));       // unit tables
-    return b + (size_t)warps_per_block * fast_warp_bytes(seg_words);
+    size_t b = (load16 ? 2 : 4) * (size_t)Wd * 32 + sizeof(int32_t) * (size_t)((Wd + 3) & ~3);   // load curve + word maxima
+    b += 32 * (sizeof(int32_t) + 2 * sizeof(float) + sizeof(uint32_t));                          // unit tables
+    return (b + 15) & ~(size_t)15;
+}
+
+size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, bool packed, bool load16)
+{
+    return fast_block_bytes(Wd, load16) + (size_t)warps_per_block * fast_warp_bytes(seg_words, packed);
 }
 
 int seq_fast_max_threads() { return FAST_MAX_THREADS; }
 
+// timeline access: int32 per hour, or two int16 hours per 32-bit word.  The packed form adds the
+// (sign-extended) delta of the low hour and delta * 65536 of the high hour with ordinary wrapping
+// integer adds; the word then holds S_lo + 65536 * S_hi (mod 2^32), which decodes exactly as long
+// as both sums stay inside int16 (installed capacity <= 32767 fixed-point units).
+template <bool kPacked>
+__device__ __forceinline__ void tl_add(int32_t *tl, int slot, int delta)
+{
+    if (kPacked) atomicAdd(&tl[slot >> 1], (slot & 1) ? (int)((uint32_t)delta << 16) : delta);
+    else atomicAdd(&tl[slot], delta);
+}
+
+template <bool kPacked>
+__device__ __forceinline__ int tl_get(const int32_t *tl, int slot)
+{
+    if (kPacked) {
+        const int w = tl[slot >> 1];
+        const int lo = (int)(short)(w & 0xffff);
+        return (slot & 1) ? ((w - lo) >> 16) : lo;
+    }
+    return tl[slot];
+}
+
+template <bool kPacked>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int Hpad = a.Wd * 32;
-    int32_t *s_load = reinterpret_cast<int32_t *>(smem_raw);
-    int32_t *s_lmax = s_load + Hpad;
+    const bool load16 = a.load16 != 0;
+    int32_t *s_load32 = reinterpret_cast<int32_t *>(smem_raw);
+    short *s_load16 = reinterpret_cast<short *>(smem_raw);
+    int32_t *s_lmax = reinterpret_cast<int32_t *>(smem_raw + (load16 ? 2 : 4) * (size_t)Hpad);
     int32_t *s_cap = s_lmax + ((a.Wd + 3) & ~3);
     float *s_mup = reinterpret_cast<float *>(s_cap + 32);
     float *s_mdn = s_mup + 32;
     uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_mdn + 32);
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_thr + 32) + (size_t)warp * fast_warp_bytes(a.seg_words);
+    unsigned char *wbase = smem_raw + fast_block_bytes(a.Wd, load16) + (size_t)warp * fast_warp_bytes(a.seg_words, kPacked);
     FastWarpSmem *ws = reinterpret_cast<FastWarpSmem *>(wbase);
-    int32_t *tl = reinterpret_cast<int32_t *>(wbase + sizeof(FastWarpSmem));
+    int32_t *tl = reinterpret_cast<int32_t *>(wbase + sizeof(FastWarpSmem));     // ring: two halves
     const int seg_slots = a.seg_words * 32;
-    uint32_t *bm = reinterpret_cast<uint32_t *>(tl + seg_slots);
-    const int bm_words = (a.seg_words + 3) & ~3;
+    const int half_words32 = kPacked ? seg_slots / 2 : seg_slots;                // 32-bit words per ring half
+    uint32_t *bm = reinterpret_cast<uint32_t *>(tl + 2 * half_words32);
+    const int bm_half = (a.seg_words + 3) & ~3;
 
-    for (int i = threadIdx.x; i < Hpad; i += blockDim.x) s_load[i] = a.load[i];
+    for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
+        if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
+    }
     for (int i = threadIdx.x; i < a.Wd; i += blockDim.x) s_lmax[i] = a.lmax[i];
     if (threadIdx.x < 32) {
         const bool v = threadIdx.x < a.U;
@@ -81,9 +116,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
-    for (int i = lane; i < seg_slots; i += 32) tl[i] = 0;
-    for (int i = lane; i < bm_words; i += 32) bm[i] = 0u;
+    for (int i = lane; i < 2 * half_words32; i += 32) tl[i] = 0;
+    for (int i = lane; i < 2 * bm_half; i += 32) bm[i] = 0u;
     __syncthreads();
+    auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
     unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
     long long acc_ens = 0;
@@ -105,6 +141,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         uint32_t s0mask = 0;          // initial states (bit u = UP)
         int pend_cnt = 0;
         int capacity = 0;
+        int ring = 0;                 // ring half that holds the current segment
         ws->t_run[lane] = 0ull;
         __syncwarp();
         bool init_wave = true;
@@ -112,13 +149,19 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         for (int y = 0; y < a.ypc; y++) {
             unsigned int lolh = 0, entries = 0;
             long long ens_lane = 0;
-            for (int seg = 0; seg < a.nseg; seg++) {
+            for (int seg = 0; seg < a.nseg; seg++, ring ^= 1) {
                 const int seg_h0 = seg * seg_slots;
                 const int seg_h1 = min(a.H, seg_h0 + seg_slots);
                 const int abs0 = y * a.H + seg_h0, abs1 = y * a.H + seg_h1;   // chain-relative hours
+                // the segment after this one (same year or first of the next year) lives in the other half
+                const int nxt_h0 = (seg + 1 < a.nseg) ? seg_h0 + seg_slots : 0;
+                const int abs2 = min(chain_end_h, abs1 + min(seg_slots, a.H - nxt_h0));
                 const unsigned long long seg_end_t = (unsigned long long)abs1 << PSRA_TICK_SHIFT;
+                const unsigned long long nxt_end_t = (unsigned long long)abs2 << PSRA_TICK_SHIFT;
+                int32_t *tl_cur = tl + ring * half_words32, *tl_nxt = tl + (ring ^ 1) * half_words32;
+                uint32_t *bm_cur = bm + ring * bm_half, *bm_nxt = bm + (ring ^ 1) * bm_half;
 
-                // ---- pending events that fall into this segment
+                // ---- far-future events that now fall into the next segment's half
                 if (pend_cnt) {
                     int outc = 0;
                     for (int base = 0; base < pend_cnt; base += 32) {
@@ -126,12 +169,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const bool v = i < pend_cnt;
                         const uint32_t e = v ? ws->pend[i] : 0u;
                         const int hs = (int)(e >> 6);
-                        const bool take = v && hs < abs1;
+                        const bool take = v && hs < abs2;
                         if (take) {
                             const int c = s_cap[(e >> 1) & 31];
-                            const int slot = hs - abs0;
-                            atomicAdd(&tl[slot], (e & 1u) ? c : -c);
-                            atomicOr(&bm[slot >> 5], 1u << (slot & 31));
+                            const int slot = hs - abs1;
+                            tl_add<kPacked>(tl_nxt, slot, (e & 1u) ? c : -c);
+                            atomicOr(&bm_nxt[slot >> 5], 1u << (slot & 31));
                         }
                         const bool keep = v && !take;
                         const uint32_t km = __ballot_sync(0xffffffffu, keep);
@@ -143,39 +186,34 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 }
 
                 // ---- waves: one round of <= 32 (unit, block) jobs each, until every unit covers the segment
-                const unsigned long long ahead_t = seg_end_t + ((unsigned long long)seg_slots << PSRA_TICK_SHIFT);
-                const unsigned long long chain_end_t = (unsigned long long)chain_end_h << PSRA_TICK_SHIFT;
                 while (true) {
                     const unsigned long long tlast = ws->t_run[lane];
                     const bool is_short = unit_valid && tlast <= seg_end_t;
                     if (!__any_sync(0xffffffffu, is_short)) break;
-                    int n_u = 0;
-                    if (is_short) {
-                        if (init_wave) n_u = 1;
-                        else {
-                            const float rem_h = (float)(int)((seg_end_t - tlast) >> PSRA_TICK_SHIFT);
-                            n_u = min(FAST_NB_MAX, 1 + (int)(rem_h * inv_span));
-                        }
+                    int want = 0;                      // blocks towards the end of the NEXT segment
+                    if (init_wave) want = unit_valid ? 1 : 0;
+                    else if (unit_valid && tlast <= nxt_end_t) {
+                        const float rem_h = (float)(int)((nxt_end_t - tlast) >> PSRA_TICK_SHIFT);
+                        want = min(FAST_NB_MAX, 1 + (int)(rem_h * inv_span));
                     }
-                    const int incl = warp_incl_scan(n_u, lane);
-                    int off = incl - n_u;
-                    int J = __shfl_sync(0xffffffffu, incl, 31);
-                    if (J > 32) {                  // truncate; the remaining demand is served by the next wave
-                        n_u = max(0, min(n_u, 32 - off));
-                        J = 32;
-                        n_jobs += 32;
-                    } else if (J < 32 && !init_wave && pend_cnt <= FAST_PEND_CAP / 2) {
-                        // spare lanes: one block ahead for units that run short within the next segment
-                        const bool elig = unit_valid && !is_short && tlast <= ahead_t && tlast <= chain_end_t;
-                        const uint32_t em = __ballot_sync(0xffffffffu, elig);
-                        const int rank = __popc(em & lt_mask);
-                        if (elig && rank < 32 - J) { n_u = 1; off = J + rank; }
-                        const int J2 = min(32, J + __popc(em));
-                        n_opt += J2 - J; n_jobs += J2;
-                        J = J2;
-                    } else {
-                        n_jobs += J;
+                    const int n_m = is_short ? want : 0;             // mandatory: units short of this segment
+                    const int incl_m = warp_incl_scan(n_m, lane);
+                    const int J1 = __shfl_sync(0xffffffffu, incl_m, 31);
+                    int n_u, off, J;
+                    if (J1 >= 32 || init_wave) {       // truncate; the remaining demand is served by the next wave
+                        off = incl_m - n_m;
+                        n_u = max(0, min(n_m, 32 - off));
+                        J = min(J1, 32);
+                    } else {                           // spare lanes pre-generate for the next segment
+                        const int n_o = (!is_short && pend_cnt <= FAST_PEND_CAP / 2) ? want : 0;
+                        const int incl_o = warp_incl_scan(n_o, lane);
+                        const int off_o = J1 + incl_o - n_o;
+                        off = is_short ? incl_m - n_m : off_o;
+                        n_u = is_short ? n_m : max(0, min(n_o, 32 - off_o));
+                        J = min(32, J1 + __shfl_sync(0xffffffffu, incl_o, 31));
+                        n_opt += J - J1;
                     }
+                    n_jobs += J;
                     n_waves++;
 #pragma unroll
                     for (int k = 0; k < FAST_NB_MAX; k++)
@@ -223,13 +261,14 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             const bool inhor = valid && h64 < (unsigned long long)chain_end_h;
                             const int hs = (int)h64;
                             const int delta = (q & 1) ? -delta_a : delta_a;
-                            const bool in_seg = inhor && hs < abs1;
-                            if (in_seg) {
-                                const int slot = hs - abs0;
-                                atomicAdd(&tl[slot], delta);
-                                atomicOr(&bm[slot >> 5], 1u << (slot & 31));
+                            const bool in_ring = inhor && hs < abs2;
+                            if (in_ring) {
+                                const bool cur = hs < abs1;
+                                const int slot = hs - (cur ? abs0 : abs1);
+                                tl_add<kPacked>(cur ? tl_cur : tl_nxt, slot, delta);
+                                atomicOr(&(cur ? bm_cur : bm_nxt)[slot >> 5], 1u << (slot & 31));
                             }
-                            const bool pnd = inhor && !in_seg;
+                            const bool pnd = inhor && !in_ring;
                             const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
                             if (pm) {
                                 const int pos = pend_cnt + __popc(pm & lt_mask);
@@ -257,7 +296,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 }
                 __syncwarp();
 
-                // ---- evaluation: lane = run of `wpl` consecutive words
+                // ---- evaluation of the current half: lane = run of `wpl` consecutive words
                 const int nwords = (seg_h1 - seg_h0 + 31) >> 5;
                 const int wpl = (nwords + 31) >> 5;
                 const int wb = lane * wpl;
@@ -266,8 +305,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     const int w = wb + k;
                     if (w < nwords) {
                         int s = 0, neg = 0;
-                        for (uint32_t mm = bm[w]; mm; mm &= mm - 1) {
-                            const int d = tl[w * 32 + (__ffs(mm) - 1)];
+                        for (uint32_t mm = bm_cur[w]; mm; mm &= mm - 1) {
+                            const int d = tl_get<kPacked>(tl_cur, w * 32 + (__ffs(mm) - 1));
                             s += d;
                             neg += min(d, 0);
                         }
@@ -287,13 +326,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     for (int k = 0; k < wpl; k++) {
                         const int wq = src * wpl + k;
                         if (wq >= nwords) break;
-                        const int c = c_in + warp_incl_scan(tl[wq * 32 + lane], lane);
+                        const int c = c_in + warp_incl_scan(tl_get<kPacked>(tl_cur, wq * 32 + lane), lane);
                         const int hy0 = seg_h0 + wq * 32;
-                        const int L = s_load[hy0 + lane];
+                        const int L = load_at(hy0 + lane);
                         const bool lol = c < L;                  // PSA.jl:253 strict
                         const uint32_t mask = __ballot_sync(0xffffffffu, lol);
                         if (mask) {
-                            const uint32_t prev = (hy0 > 0 && c_in < s_load[hy0 - 1]) ? 1u : 0u;
+                            const uint32_t prev = (hy0 > 0 && c_in < load_at(hy0 - 1)) ? 1u : 0u;
                             lolh += __popc(mask);
                             entries += __popc(mask & ~((mask << 1) | prev));   // calnlc.m:22-34
                             if (lol) {
@@ -306,11 +345,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 }
                 capacity += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
-                {   // clear the segment with 16-byte stores
-                    int4 *t4 = reinterpret_cast<int4 *>(tl);
-                    const int n4 = nwords * 8;
+                {   // clear the evaluated half with 16-byte stores
+                    int4 *t4 = reinterpret_cast<int4 *>(tl_cur);
+                    const int n4 = half_words32 / 4;
                     for (int i = lane; i < n4; i += 32) t4[i] = make_int4(0, 0, 0, 0);
-                    for (int i = lane; i < nwords; i += 32) bm[i] = 0u;
+                    for (int i = lane; i < bm_half; i += 32) bm_cur[i] = 0u;
                 }
                 __syncwarp();
             }
@@ -334,6 +373,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
             acc_e2hi += phi + (nlo < acc_e2lo ? 1ull : 0ull);
             acc_e2lo = nlo;
         }
+        // chain finished: the ring half after the last segment may hold events beyond the chain end
+        // only if abs2 exceeded chain_end_h, which it never does; both halves are clean here.
         __syncwarp();
     }
 
@@ -355,14 +396,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     }
 }
 
-cudaError_t seq_fast_prepare(size_t smem, int threads, int *blocks_per_sm)
+cudaError_t seq_fast_prepare(bool packed, size_t smem, int threads, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(seq_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void *k = packed ? (const void *)seq_fast_kernel<true> : (const void *)seq_fast_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, seq_fast_kernel, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem);
 }
 
-void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
+void seq_fast_launch(bool packed, const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
 {
-    seq_fast_kernel<<<grid, threads, smem, stream>>>(a);
+    if (packed) seq_fast_kernel<true><<<grid, threads, smem, stream>>>(a);
+    else seq_fast_kernel<false><<<grid, threads, smem, stream>>>(a);
 }

@@ -299,6 +299,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (nyears == 0) return PSRA_OK;
 
     const bool one_unit = h->U <= 32;
+    const bool packed = h->total_cap <= 32767, load16 = h->max_load <= 32767;
     const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0];
     SeqArgs a{};
     a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode; a.K = K;
@@ -307,11 +308,12 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
     a.chain_base = chain_base; a.nchains = nchains;
     a.acc = h->d_acc;
+    a.load16 = load16 ? 1 : 0;
 
     // launch geometry: segment length and warps per block under the shared-memory budget
     int seg_words = h->Wd;
     if (one_unit) {
-        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : (fast ? 2208 : 1120);
+        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : (fast ? 1760 : 1120);
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
     a.seg_words = seg_words;
@@ -320,7 +322,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 24 : 16);
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
-        if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w);
+        if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, packed, load16);
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
         if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
@@ -380,7 +382,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     else          kern = one_unit ? seq_mc_kernel<false, true> : seq_mc_kernel<false, false>;
     int bps = 0;
     if (fast) {
-        PSRA_CUDA(h, seq_fast_prepare(smem, wpb * 32, &bps));
+        PSRA_CUDA(h, seq_fast_prepare(packed, smem, wpb * 32, &bps));
     } else {
         PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PSRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
@@ -392,7 +394,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (grid > need) grid = need;
 
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    if (fast) seq_fast_launch(a, (unsigned)grid, wpb * 32, smem, h->stream);
+    if (fast) seq_fast_launch(packed, a, (unsigned)grid, wpb * 32, smem, h->stream);
     else kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
     PSRA_CUDA(h, cudaGetLastError());
     PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));

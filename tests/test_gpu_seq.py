@@ -186,3 +186,18 @@ def test_statistics_match_analytical_rts79(engine, rts):
     assert abs(r.eens - 1176.181257) < 3.0 * r.eens_se + 1e-9
     assert 1.7 < r.lolf < 2.2 and 4.3 < r.lold < 5.4      # BASELINE.md ballparks: 1.90 occ/yr, 4.86 h
     assert 0.50 < r.p_loss_year < 0.60
+
+
+def test_fixed_point_scale_int32_timeline(engine, rts):
+    """fp_scale = 16: installed capacity 54 480 and peak load 45 600 exceed int16, so the sampler kernel
+    takes its int32 timeline / int32 load-curve variant; ENS is then in 1/16 MWh."""
+    load = np.rint(16 * rts["load_mw"]).astype(np.int32)
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"], fp_scale=16.0)
+    engine.set_load(rts["load_mw"])
+    r = engine.seq_mc(96, seed=321, init_mode=1, per_year=True)
+    lol, ens, ent = O.seq_philox(16 * rts["cap"], rts["mttf"], rts["mttr"], load.astype(np.float64), 321, 0, 96, 1, 1)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol)
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    assert np.array_equal(r.entries.astype(np.float64), ent)
+    assert np.allclose(r.ens, ens / 16.0) and lol.sum() > 0
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"], fp_scale=1.0)
