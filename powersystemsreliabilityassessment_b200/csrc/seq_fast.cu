@@ -15,12 +15,13 @@
 //    Lane utilisation no longer depends on the 6x spread of the units' event rates.
 //  * The warp's shared-memory hour timeline is a ring of two segments.  Events of the current and
 //    of the next segment are scattered directly (atomicAdd of the integer MW delta -- two int16
-//    hours packed per word when the installed capacity allows -- and atomicOr into the event
-//    bitmap); the rare events beyond the ring wait in a small pending list.  A wave is one round
+//    hours packed per word when the installed capacity allows -- plus atomicAdd into the per-word
+//    delta sums); the rare events beyond the ring wait in a small pending list.  A wave is one round
 //    of <= 32 jobs: blocks for the units that are short of the current segment first, the spare
 //    lanes pre-generate blocks towards the end of the next segment.
-//  * Evaluation: lane = run of consecutive 32-hour words.  Gather of the set bits, one shuffle
-//    scan per segment for the capacity entering each lane's run, conservative flag
+//  * Evaluation: lane = run of consecutive 32-hour words; the per-word delta sums (and sums of
+//    negative deltas) are accumulated at scatter time.  One shuffle scan per segment gives the
+//    capacity entering each lane's run; conservative flag
 //    min-capacity-bound < max-load-of-word; flagged runs (rare) are resolved hour by hour with
 //    ballot/popc (LOL hours, deficit entries) and per-lane ENS accumulators.  The timeline segment
 //    is then cleared with 16-byte stores.
@@ -42,7 +43,7 @@ struct FastWarpSmem {                  // per-warp scratch that precedes the tim
 __host__ __device__ inline size_t fast_warp_bytes(int seg_words, bool packed)
 {
     size_t b = sizeof(FastWarpSmem) + 2 * (packed ? 2 : 4) * (size_t)seg_words * 32 +
-               2 * sizeof(uint32_t) * (size_t)((seg_words + 3) & ~3);
+               2 * 2 * sizeof(uint32_t) * (size_t)((seg_words + 3) & ~3);   // word sums + word negative sums
     return (b + 15) & ~(size_t)15;
 }
 
@@ -102,8 +103,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     int32_t *tl = reinterpret_cast<int32_t *>(wbase + sizeof(FastWarpSmem));     // ring: two halves
     const int seg_slots = a.seg_words * 32;
     const int half_words32 = kPacked ? seg_slots / 2 : seg_slots;                // 32-bit words per ring half
-    uint32_t *bm = reinterpret_cast<uint32_t *>(tl + 2 * half_words32);
     const int bm_half = (a.seg_words + 3) & ~3;
+    int32_t *wsum = tl + 2 * half_words32;                                      // per 32-hour word: sum of deltas
+    int32_t *wneg = wsum + 2 * bm_half;                                         //                   sum of negative deltas
 
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
         if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
     for (int i = lane; i < 2 * half_words32; i += 32) tl[i] = 0;
-    for (int i = lane; i < 2 * bm_half; i += 32) bm[i] = 0u;
+    for (int i = lane; i < 2 * bm_half; i += 32) { wsum[i] = 0; wneg[i] = 0; }
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
@@ -159,7 +161,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 const unsigned long long seg_end_t = (unsigned long long)abs1 << PSRA_TICK_SHIFT;
                 const unsigned long long nxt_end_t = (unsigned long long)abs2 << PSRA_TICK_SHIFT;
                 int32_t *tl_cur = tl + ring * half_words32, *tl_nxt = tl + (ring ^ 1) * half_words32;
-                uint32_t *bm_cur = bm + ring * bm_half, *bm_nxt = bm + (ring ^ 1) * bm_half;
+                int32_t *ws_cur = wsum + ring * bm_half, *ws_nxt = wsum + (ring ^ 1) * bm_half;
+                int32_t *wn_cur = wneg + ring * bm_half, *wn_nxt = wneg + (ring ^ 1) * bm_half;
 
                 // ---- far-future events that now fall into the next segment's half
                 if (pend_cnt) {
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             const int c = s_cap[(e >> 1) & 31];
                             const int slot = hs - abs1;
                             tl_add<kPacked>(tl_nxt, slot, (e & 1u) ? c : -c);
-                            atomicOr(&bm_nxt[slot >> 5], 1u << (slot & 31));
+                            atomicAdd(&ws_nxt[slot >> 5], (e & 1u) ? c : -c);
+                            if (!(e & 1u)) atomicAdd(&wn_nxt[slot >> 5], -c);
                         }
                         const bool keep = v && !take;
                         const uint32_t km = __ballot_sync(0xffffffffu, keep);
@@ -266,7 +270,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                 const bool cur = hs < abs1;
                                 const int slot = hs - (cur ? abs0 : abs1);
                                 tl_add<kPacked>(cur ? tl_cur : tl_nxt, slot, delta);
-                                atomicOr(&(cur ? bm_cur : bm_nxt)[slot >> 5], 1u << (slot & 31));
+                                atomicAdd(&(cur ? ws_cur : ws_nxt)[slot >> 5], delta);
+                                if (delta < 0) atomicAdd(&(cur ? wn_cur : wn_nxt)[slot >> 5], delta);
                             }
                             const bool pnd = inhor && !in_ring;
                             const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
@@ -304,14 +309,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 for (int k = 0; k < wpl; k++) {
                     const int w = wb + k;
                     if (w < nwords) {
-                        int s = 0, neg = 0;
-                        for (uint32_t mm = bm_cur[w]; mm; mm &= mm - 1) {
-                            const int d = tl_get<kPacked>(tl_cur, w * 32 + (__ffs(mm) - 1));
-                            s += d;
-                            neg += min(d, 0);
-                        }
-                        lmin = min(lmin, loc + neg - s_lmax[seg * a.seg_words + w]);
-                        loc += s;
+                        lmin = min(lmin, loc + wn_cur[w] - s_lmax[seg * a.seg_words + w]);
+                        loc += ws_cur[w];
                     }
                 }
                 const int incl = warp_incl_scan(loc, lane);
@@ -349,7 +348,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     int4 *t4 = reinterpret_cast<int4 *>(tl_cur);
                     const int n4 = half_words32 / 4;
                     for (int i = lane; i < n4; i += 32) t4[i] = make_int4(0, 0, 0, 0);
-                    for (int i = lane; i < bm_half; i += 32) bm_cur[i] = 0u;
+                    for (int i = lane; i < bm_half; i += 32) { ws_cur[i] = 0; wn_cur[i] = 0; }
                 }
                 __syncwarp();
             }
