@@ -43,7 +43,7 @@ struct FastWarpSmem {                  // per-warp scratch that precedes the tim
 __host__ __device__ inline size_t fast_warp_bytes(int seg_words, bool packed)
 {
     size_t b = sizeof(FastWarpSmem) + 2 * (packed ? 2 : 4) * (size_t)seg_words * 32 +
-               2 * 2 * sizeof(uint32_t) * (size_t)((seg_words + 3) & ~3);   // word sums + word negative sums
+               2 * sizeof(uint32_t) * (size_t)((2 * seg_words + 3) & ~3);   // word sums + word negative sums (ring)
     return (b + 15) & ~(size_t)15;
 }
 
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     int32_t *tl = reinterpret_cast<int32_t *>(wbase + sizeof(FastWarpSmem));     // ring: two halves
     const int seg_slots = a.seg_words * 32;
     const int half_words32 = kPacked ? seg_slots / 2 : seg_slots;                // 32-bit words per ring half
-    const int bm_half = (a.seg_words + 3) & ~3;
+    const int ring_words = (2 * a.seg_words + 3) & ~3;
     int32_t *wsum = tl + 2 * half_words32;                                      // per 32-hour word: sum of deltas
-    int32_t *wneg = wsum + 2 * bm_half;                                         //                   sum of negative deltas
+    int32_t *wneg = wsum + ring_words;                                          //                   sum of negative deltas
 
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
         if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
     for (int i = lane; i < 2 * half_words32; i += 32) tl[i] = 0;
-    for (int i = lane; i < 2 * bm_half; i += 32) { wsum[i] = 0; wneg[i] = 0; }
+    for (int i = lane; i < ring_words; i += 32) { wsum[i] = 0; wneg[i] = 0; }
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
@@ -160,9 +160,18 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 const int abs2 = min(chain_end_h, abs1 + min(seg_slots, a.H - nxt_h0));
                 const unsigned long long seg_end_t = (unsigned long long)abs1 << PSRA_TICK_SHIFT;
                 const unsigned long long nxt_end_t = (unsigned long long)abs2 << PSRA_TICK_SHIFT;
-                int32_t *tl_cur = tl + ring * half_words32, *tl_nxt = tl + (ring ^ 1) * half_words32;
-                int32_t *ws_cur = wsum + ring * bm_half, *ws_nxt = wsum + (ring ^ 1) * bm_half;
-                int32_t *wn_cur = wneg + ring * bm_half, *wn_nxt = wneg + (ring ^ 1) * bm_half;
+                // ring geometry: the current segment starts at slot ring*S, the next one at the other half's
+                // base; an event `rel` hours after abs0 lives at slot ring*S + rel (+ pad when it belongs to
+                // the next segment and the current one is shorter than S), modulo 2S
+                const uint32_t len_cur = (uint32_t)(seg_h1 - seg_h0);
+                const uint32_t ring_len = (uint32_t)(abs2 - abs0);
+                const int pad = seg_slots - (int)len_cur;
+                const int ring_base = ring * seg_slots;
+                const int wbase_cur = ring * a.seg_words;                     // word index of the current half
+                auto ring_slot = [&](uint32_t rel) -> int {
+                    int idx = ring_base + (int)rel + (rel >= len_cur ? pad : 0);
+                    return idx >= 2 * seg_slots ? idx - 2 * seg_slots : idx;
+                };
 
                 // ---- far-future events that now fall into the next segment's half
                 if (pend_cnt) {
@@ -175,10 +184,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const bool take = v && hs < abs2;
                         if (take) {
                             const int c = s_cap[(e >> 1) & 31];
-                            const int slot = hs - abs1;
-                            tl_add<kPacked>(tl_nxt, slot, (e & 1u) ? c : -c);
-                            atomicAdd(&ws_nxt[slot >> 5], (e & 1u) ? c : -c);
-                            if (!(e & 1u)) atomicAdd(&wn_nxt[slot >> 5], -c);
+                            const int slot = ring_slot((uint32_t)(hs - abs0));
+                            tl_add<kPacked>(tl, slot, (e & 1u) ? c : -c);
+                            atomicAdd(&wsum[slot >> 5], (e & 1u) ? c : -c);
+                            if (!(e & 1u)) atomicAdd(&wneg[slot >> 5], -c);
                         }
                         const bool keep = v && !take;
                         const uint32_t km = __ballot_sync(0xffffffffu, keep);
@@ -200,21 +209,29 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const float rem_h = (float)(int)((nxt_end_t - tlast) >> PSRA_TICK_SHIFT);
                         want = min(FAST_NB_MAX, 1 + (int)(rem_h * inv_span));
                     }
+                    // exclusive prefix / total of a per-lane count in 0..7 from three ballots
+                    auto count_scan = [&](int n, int &excl, int &total) {
+                        const uint32_t b0 = __ballot_sync(0xffffffffu, n & 1), b1 = __ballot_sync(0xffffffffu, n & 2),
+                                       b2 = __ballot_sync(0xffffffffu, n & 4);
+                        excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+                        total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                    };
                     const int n_m = is_short ? want : 0;             // mandatory: units short of this segment
-                    const int incl_m = warp_incl_scan(n_m, lane);
-                    const int J1 = __shfl_sync(0xffffffffu, incl_m, 31);
+                    int off_m, J1;
+                    count_scan(n_m, off_m, J1);
                     int n_u, off, J;
                     if (J1 >= 32 || init_wave) {       // truncate; the remaining demand is served by the next wave
-                        off = incl_m - n_m;
+                        off = off_m;
                         n_u = max(0, min(n_m, 32 - off));
                         J = min(J1, 32);
                     } else {                           // spare lanes pre-generate for the next segment
                         const int n_o = (!is_short && pend_cnt <= FAST_PEND_CAP / 2) ? want : 0;
-                        const int incl_o = warp_incl_scan(n_o, lane);
-                        const int off_o = J1 + incl_o - n_o;
-                        off = is_short ? incl_m - n_m : off_o;
+                        int off_o, J2;
+                        count_scan(n_o, off_o, J2);
+                        off_o += J1;
+                        off = is_short ? off_m : off_o;
                         n_u = is_short ? n_m : max(0, min(n_o, 32 - off_o));
-                        J = min(32, J1 + __shfl_sync(0xffffffffu, incl_o, 31));
+                        J = min(32, J1 + J2);
                         n_opt += J - J1;
                     }
                     n_jobs += J;
@@ -257,28 +274,29 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const int cu = s_cap[u];
                         const int delta_a = s0u ? cu : -cu;      // draws 0, 2 toggle the unit back to s0
                         if (b == 0u && act) s0mask = s0u ? 1u : 0u;   // init wave (job lane == unit lane), ballot below
+                        // hour of an event at tick T: ceil(T / 2^24) - 1 = (T - 1) >> 24 (fits 32 bits: T < 2^56)
+                        const unsigned long long bm1 = base_t - 1ull;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            const unsigned long long te = base_t + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
+                            const unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
+                            const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
                             const bool valid = act && !(b == 0u && q == 0);
-                            const unsigned long long h64 = (te - 1ull) >> PSRA_TICK_SHIFT;
-                            const bool inhor = valid && h64 < (unsigned long long)chain_end_h;
-                            const int hs = (int)h64;
+                            const uint32_t rel = hs - (uint32_t)abs0;          // >= 0: events are never generated backwards
                             const int delta = (q & 1) ? -delta_a : delta_a;
-                            const bool in_ring = inhor && hs < abs2;
+                            const bool in_ring = valid && rel < ring_len;      // ring_len stops at the chain end
                             if (in_ring) {
-                                const bool cur = hs < abs1;
-                                const int slot = hs - (cur ? abs0 : abs1);
-                                tl_add<kPacked>(cur ? tl_cur : tl_nxt, slot, delta);
-                                atomicAdd(&(cur ? ws_cur : ws_nxt)[slot >> 5], delta);
-                                if (delta < 0) atomicAdd(&(cur ? wn_cur : wn_nxt)[slot >> 5], delta);
+                                const int slot = ring_slot(rel);
+                                tl_add<kPacked>(tl, slot, delta);
+                                atomicAdd(&wsum[slot >> 5], delta);
+                                if (delta < 0) atomicAdd(&wneg[slot >> 5], delta);
                             }
+                            const bool inhor = valid && hs < (uint32_t)chain_end_h;
                             const bool pnd = inhor && !in_ring;
                             const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
                             if (pm) {
                                 const int pos = pend_cnt + __popc(pm & lt_mask);
                                 if (pnd && pos < FAST_PEND_CAP)
-                                    ws->pend[pos] = ((uint32_t)hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
+                                    ws->pend[pos] = (hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
                                 pend_cnt += __popc(pm);
                             }
                             n_events += inhor ? 1u : 0u;
@@ -309,8 +327,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 for (int k = 0; k < wpl; k++) {
                     const int w = wb + k;
                     if (w < nwords) {
-                        lmin = min(lmin, loc + wn_cur[w] - s_lmax[seg * a.seg_words + w]);
-                        loc += ws_cur[w];
+                        lmin = min(lmin, loc + wneg[wbase_cur + w] - s_lmax[seg * a.seg_words + w]);
+                        loc += wsum[wbase_cur + w];
                     }
                 }
                 const int incl = warp_incl_scan(loc, lane);
@@ -325,7 +343,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     for (int k = 0; k < wpl; k++) {
                         const int wq = src * wpl + k;
                         if (wq >= nwords) break;
-                        const int c = c_in + warp_incl_scan(tl_get<kPacked>(tl_cur, wq * 32 + lane), lane);
+                        const int c = c_in + warp_incl_scan(tl_get<kPacked>(tl, ring_base + wq * 32 + lane), lane);
                         const int hy0 = seg_h0 + wq * 32;
                         const int L = load_at(hy0 + lane);
                         const bool lol = c < L;                  // PSA.jl:253 strict
@@ -345,10 +363,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 capacity += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
                 {   // clear the evaluated half with 16-byte stores
-                    int4 *t4 = reinterpret_cast<int4 *>(tl_cur);
+                    int4 *t4 = reinterpret_cast<int4 *>(tl + ring * half_words32);
                     const int n4 = half_words32 / 4;
                     for (int i = lane; i < n4; i += 32) t4[i] = make_int4(0, 0, 0, 0);
-                    for (int i = lane; i < bm_half; i += 32) { ws_cur[i] = 0; wn_cur[i] = 0; }
+                    for (int i = lane; i < a.seg_words; i += 32) { wsum[wbase_cur + i] = 0; wneg[wbase_cur + i] = 0; }
                 }
                 __syncwarp();
             }
