@@ -196,6 +196,29 @@ int psra_tail(psra_handle *h, const int64_t *values, int64_t n, const double *al
               int32_t n_alpha, psra_tail_out *out, int64_t *hist, int32_t n_bins,
               int64_t bin_width);
 
+/* hourly-resampled MC with maintenance / LFU / energy-limited units: replaces run_detailed_mc
+ * (tail_risk.jl:12-91) == run_monte_carlo (MCvsMarkovProcess.jl:210-284) ---------------------- */
+typedef struct psra_detailed_system {
+    const double  *capacity_mw;        /* [n_units] */
+    const double  *for_rate;           /* [n_units] mechanical FOR (tail_risk.jl:44) */
+    const int32_t *maint_start_week;   /* [n_units] scheduled_outage_start, 1-based week (:39) */
+    const int32_t *maint_weeks;        /* [n_units] 0 = no maintenance */
+    const double  *energy_limit_mwh;   /* [n_units] +Inf = not energy limited (:46) */
+    int32_t n_units;                   /* <= 30 */
+    int32_t reserved;
+} psra_detailed_system;
+
+/* years [year0, year0+nyears) of experiment `seed`; year_lole[nyears] = hours with deficit per year
+ * (yearly_lole_distribution), hourly_fail[H] (optional) = years in which hour h had a deficit
+ * (hourly_failure_prob * n_years); lfu_std_mw = maximum(base_load) * lfu_sigma_percent / 100 */
+int psra_detailed_mc(psra_handle *h, const psra_detailed_system *sys, const double *base_load_mw,
+                     int32_t n_hours, double lfu_std_mw, int64_t year0, int64_t nyears, uint64_t seed,
+                     uint32_t *year_lole, uint32_t *hourly_fail, float *kernel_ms);
+/* same loop with injected rand() / randn(): uniforms[(y*H + h)*U + u], normals[y*H + h] */
+int psra_detailed_eval_injected(psra_handle *h, const psra_detailed_system *sys, const double *base_load_mw,
+                                int32_t n_hours, double lfu_std_mw, int64_t nyears, const double *uniforms,
+                                const double *normals, uint32_t *year_lole, uint32_t *hourly_fail);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,8 @@ using Printf
 
 export Generator, LoadModel, ReliabilityResult,
        run_analytical, run_non_sequential_mc, run_sequential_mc, compare_results,
-       SequentialIndices, run_sequential_indices, tail_risk, PSRA_INIT_ALL_UP, PSRA_INIT_STATIONARY
+       SequentialIndices, run_sequential_indices, tail_risk, PSRA_INIT_ALL_UP, PSRA_INIT_STATIONARY,
+       DetailedGenerator, run_detailed_mc
 
 const LIB = get(ENV, "PSRA_B200_LIB", joinpath(@__DIR__, "..", "powersystemsreliabilityassessment_b200", "libpsra_b200.so"))
 const PSRA_INIT_ALL_UP = Int32(0)
@@ -216,6 +217,44 @@ function tail_risk(alphas::Vector{Float64}=[0.95, 0.99]; engine::Engine=default_
     end
     return [(alpha=a, var=o.var / engine.fp_scale, cvar=o.cvar / engine.fp_scale, n_tail=o.n_tail)
             for (a, o) in zip(alphas, outs)]
+end
+
+# ---------------------------------------------------------------- tail_risk.jl / MCvsMarkovProcess.jl engine
+"mutable struct Generator of generating_adequacy_comprehensive.jl:11-24"
+mutable struct DetailedGenerator
+    name::String
+    capacity::Float64
+    for_rate::Float64
+    maintenance_weeks::Int
+    energy_limit::Float64
+    effective_q::Float64
+    scheduled_outage_start::Int
+end
+DetailedGenerator(name, cap, q, maint, elim) = DetailedGenerator(name, cap, q, maint, elim, q, 0)
+
+struct PsraDetailedSystem
+    capacity_mw::Ptr{Float64}; for_rate::Ptr{Float64}; maint_start_week::Ptr{Int32}; maint_weeks::Ptr{Int32}
+    energy_limit_mwh::Ptr{Float64}; n_units::Int32; reserved::Int32
+end
+
+"run_detailed_mc, tail_risk.jl:12-91 -> (yearly_lole_distribution, hourly_failure_prob)"
+function run_detailed_mc(gens::Vector{DetailedGenerator}, base_load::Vector{Float64}, lfu_sigma_percent::Float64,
+                         n_years::Int; seed::Integer=42, engine::Engine=default_engine())
+    cap = [g.capacity for g in gens]; q = [g.for_rate for g in gens]
+    ms = Int32[g.scheduled_outage_start for g in gens]; mw = Int32[g.maintenance_weeks for g in gens]
+    el = [g.energy_limit for g in gens]
+    lfu_std_dev = maximum(base_load) * (lfu_sigma_percent / 100.0)
+    yl = zeros(UInt32, n_years); hf = zeros(UInt32, length(base_load)); ms_k = Ref{Float32}(0f0)
+    GC.@preserve cap q ms mw el base_load yl hf begin
+        sys = Ref(PsraDetailedSystem(pointer(cap), pointer(q), pointer(ms), pointer(mw), pointer(el),
+                                     Int32(length(gens)), Int32(0)))
+        check(engine, ccall((:psra_detailed_mc, LIB), Cint,
+                            (Ptr{Cvoid}, Ref{PsraDetailedSystem}, Ptr{Float64}, Int32, Float64, Int64, Int64, UInt64,
+                             Ptr{UInt32}, Ptr{UInt32}, Ref{Float32}),
+                            engine.h, sys, base_load, Int32(length(base_load)), lfu_std_dev, 0, n_years, UInt64(seed),
+                            yl, hf, ms_k))
+    end
+    return Float64.(yl), Float64.(hf) ./ n_years
 end
 
 "compare_results, PowerSystemAdequacy.jl:275-285 (table only; plotting stays with the caller)"

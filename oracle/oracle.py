@@ -79,6 +79,14 @@ def lib():
         L.oracle_markov2.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp]
         L.oracle_dtmc_capacity.restype = None
         L.oracle_dtmc_capacity.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp]
+        L.oracle_normal_u32x2.restype = C.c_float
+        L.oracle_normal_u32x2.argtypes = [C.c_uint32, C.c_uint32]
+        L.oracle_detailed_mc_injected.restype = C.c_int
+        L.oracle_detailed_mc_injected.argtypes = [C.c_int, _dp, _dp, _i32p, _i32p, _dp, C.c_int, _dp, C.c_double,
+                                                  C.c_int, _dp, _dp, _dp, _dp]
+        L.oracle_detailed_mc_philox.restype = C.c_int
+        L.oracle_detailed_mc_philox.argtypes = [C.c_int, _dp, _u32p, _i32p, _i32p, _dp, C.c_int, _dp, C.c_double,
+                                                C.c_uint64, C.c_int64, C.c_int, _dp, _dp]
         L.oracle_load_factors.restype = None
         L.oracle_load_factors.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
     return _lib
@@ -274,3 +282,55 @@ def cvar(x, alpha):
     v = quantile_type7(x, alpha)
     tail = x[x >= v]
     return v, float(tail.mean())
+
+
+# ------------------------------------------- hourly-resampled MC (tail_risk.jl:12-91), f-1
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def detailed_mc_injected(cap, for_rate, maint_start, maint_weeks, energy_limit, base_load, lfu_std, unif, norm):
+    """unif[n_years, H, U], norm[n_years, H] -> (yearly_lole[n_years], hourly_fail_count[H])."""
+    unif = _d(unif); norm = _d(norm)
+    n, H, U = unif.shape
+    yl = np.zeros(n); hf = np.zeros(H)
+    rc = lib().oracle_detailed_mc_injected(U, _d(cap), _d(for_rate), _i32(maint_start), _i32(maint_weeks),
+                                           _d(energy_limit), H, _d(base_load), float(lfu_std), n, unif, norm, yl, hf)
+    assert rc == 0
+    return yl, hf
+
+
+def detailed_mc_philox(cap, for_rate, maint_start, maint_weeks, energy_limit, base_load, lfu_std, seed, year0, n_years):
+    q = _d(for_rate)
+    thr = np.minimum(np.floor(q * 4294967296.0), 4294967295.0).astype(np.uint32)
+    H = len(base_load)
+    yl = np.zeros(n_years); hf = np.zeros(H)
+    rc = lib().oracle_detailed_mc_philox(len(q), _d(cap), thr, _i32(maint_start), _i32(maint_weeks), _d(energy_limit),
+                                         H, _d(base_load), float(lfu_std), seed, year0, n_years, yl, hf)
+    assert rc == 0
+    return yl, hf
+
+
+def normal_u32x2(x1: int, x2: int) -> float:
+    return float(lib().oracle_normal_u32x2(int(x1), int(x2)))
+
+
+def schedule_maintenance(capacity, maintenance_weeks, weekly_peaks):
+    """generating_adequacy_comprehensive.jl:86-112: units by capacity*weeks descending (stable), each placed
+    at the start week that maximises the minimum reserve over its window (first maximum wins); returns the
+    1-based start weeks (0 = no maintenance)."""
+    cap = _d(capacity); mw = [int(w) for w in maintenance_weeks]; peaks = _d(weekly_peaks)
+    avail = np.full(52, float(cap.sum()))
+    order = sorted(range(len(cap)), key=lambda i: -(cap[i] * mw[i]))
+    start = [0] * len(cap)
+    for i in order:
+        if mw[i] == 0:
+            continue
+        best, best_res = 1, -np.inf
+        for s in range(1, 52 - mw[i] + 2):
+            res = (avail[s - 1:s - 1 + mw[i]] - peaks[s - 1:s - 1 + mw[i]]).min()
+            if res > best_res:
+                best_res, best = res, s
+        start[i] = best
+        avail[best - 1:best - 1 + mw[i]] -= cap[i]
+    return start

@@ -576,3 +576,147 @@ void oracle_load_factors(int total_hours, const double *weekly, const double *da
         factors[h - 1] = weekly[week - 1] * daily[day - 1] * hourly[(hod - 1) * 6 + col];
     }
 }
+
+/* ------------------------------------------------------------------------------------
+ * 9. Hourly-resampled MC with maintenance / LFU / energy-limited units --
+ *    tail_risk.jl:12-91 (run_detailed_mc) == MCvsMarkovProcess.jl:210-284 (run_monte_carlo)
+ *    == generating_adequancy_comparative.jl:15-120.  SURVEY.md section 8 row f-1.
+ *
+ * Literal restatement: per year the ELU energy state is reset (:27); per hour, week =
+ * div(h-1,168)+1 (:31); per unit in order: skipped while on maintenance (:39-42), out iff
+ * rand() < FOR (:44), energy-limited units are unavailable once their state reached the limit
+ * (:46-55); load = base + randn()*sigma (:59); unserved = max(0, load - unlimited capacity)
+ * (:60); full or proportional drain of the available ELUs (:63-76); an hour with deficit > 0
+ * counts once for the year and for the hour (:79-84).
+ *
+ * Injection: unif[(y*H + h)*U + u] stands for the rand() of unit u in hour h (consumed only
+ * when the unit is not on maintenance, like the reference), norm[y*H + h] for randn().
+ * energy_limit[u] = INFINITY for ordinary units.
+ * -------------------------------------------------------------------------------- */
+static void detailed_hour(int U, const double *cap, const double *elim, const unsigned char *avail_flag,
+                          double load, double *energy, int *deficit_flag)
+{
+    /* avail_flag[u]: unit passed the maintenance and outage tests this hour */
+    double cap_unlimited = 0.0, cap_elu = 0.0;
+    int elu_idx[64]; int n_elu = 0;
+    for (int i = 0; i < U; i++) {
+        if (!avail_flag[i]) continue;
+        if (elim[i] < INFINITY) {
+            if (energy[i] >= elim[i]) continue;           /* exhausted */
+            cap_elu += cap[i];
+            elu_idx[n_elu++] = i;
+        } else {
+            cap_unlimited += cap[i];
+        }
+    }
+    double unserved = load - cap_unlimited;
+    if (unserved < 0.0) unserved = 0.0;                   /* max(0.0, ...) */
+    double deficit = 0.0;
+    if (unserved > 0) {
+        if (unserved > cap_elu) {
+            deficit = unserved - cap_elu;
+            for (int k = 0; k < n_elu; k++) energy[elu_idx[k]] += cap[elu_idx[k]];
+        } else {
+            double needed = unserved;
+            for (int k = 0; k < n_elu; k++) {
+                double share = needed * (cap[elu_idx[k]] / cap_elu);
+                energy[elu_idx[k]] += share;
+            }
+        }
+    }
+    *deficit_flag = deficit > 0;
+}
+
+int oracle_detailed_mc_injected(int U, const double *cap, const double *for_rate, const int *maint_start,
+                                const int *maint_weeks, const double *elim, int H, const double *base_load,
+                                double lfu_std, int n_years, const double *unif, const double *norm,
+                                double *year_lole, double *hourly_fail)
+{
+    if (U > 64) return -1;
+    double energy[64]; unsigned char avail[64];
+    for (int h = 0; h < H; h++) hourly_fail[h] = 0.0;
+    for (int y = 0; y < n_years; y++) {
+        for (int i = 0; i < U; i++) energy[i] = 0.0;
+        double count = 0.0;
+        for (int h = 1; h <= H; h++) {
+            int week = (h - 1) / 168 + 1;
+            for (int i = 0; i < U; i++) {
+                avail[i] = 0;
+                if (week >= maint_start[i] && week < maint_start[i] + maint_weeks[i]) continue;
+                if (unif[((size_t)y * H + (h - 1)) * U + i] < for_rate[i]) continue;
+                avail[i] = 1;
+            }
+            double load = base_load[h - 1] + norm[(size_t)y * H + (h - 1)] * lfu_std;
+            int d;
+            detailed_hour(U, cap, elim, avail, load, energy, &d);
+            if (d) { count += 1.0; hourly_fail[h - 1] += 1.0; }
+        }
+        year_lole[y] = count;
+    }
+    return 0;
+}
+
+/* Standard normal from two sampler words, fixed binary32 operation sequence (Box-Muller):
+ *   r = sqrt(2 * E(x1)),  E = oracle_neglog_u32;
+ *   angle = 2 pi (4k + f) / 4 with k = x2 >> 30 and f = (2*((x2 >> 7) & 0x7FFFFF) + 1) / 2^24 in (0,1);
+ *   phi = f * pi/2 folded to [0, pi/4] (swap sin/cos), Taylor polynomials by fma;  z = r * cos(angle). */
+float oracle_normal_u32x2(uint32_t x1, uint32_t x2)
+{
+    float r = sqrtf(2.0f * oracle_neglog_u32(x1));
+    uint32_t k = x2 >> 30;
+    float f = (float)(2u * ((x2 >> 7) & 0x7FFFFFu) + 1u) * 5.9604644775390625e-08f;   /* exact */
+    int swap = f > 0.5f;
+    float g = swap ? 1.0f - f : f;                 /* exact */
+    float x = g * 1.57079637f;
+    float x2f = x * x;
+    float s = fmaf(x2f, 2.75573192e-06f, -1.98412701e-04f);
+    s = fmaf(x2f, s, 8.33333377e-03f);
+    s = fmaf(x2f, s, -1.66666672e-01f);
+    s = fmaf(x * x2f, s, x);                       /* sin x */
+    float c = fmaf(x2f, 2.48015876e-05f, -1.38888892e-03f);
+    c = fmaf(x2f, c, 4.16666679e-02f);
+    c = fmaf(x2f, c, -0.5f);
+    c = fmaf(x2f, c, 1.0f);                        /* cos x */
+    float sn = swap ? c : s, cs = swap ? s : c;    /* sin(phi), cos(phi) */
+    float v = (k == 0) ? cs : (k == 1) ? -sn : (k == 2) ? -cs : sn;
+    return r * v;
+}
+
+/* Sampler-driven version: words of Philox blocks keyed (seed; year, hour, 0x444D0000 | blk):
+ * word u decides unit u (OUT iff word < floor(FOR*2^32)), words U and U+1 give the normal. */
+int oracle_detailed_mc_philox(int U, const double *cap, const uint32_t *for_thr, const int *maint_start,
+                              const int *maint_weeks, const double *elim, int H, const double *base_load,
+                              double lfu_std, uint64_t seed, int64_t year0, int n_years,
+                              double *year_lole, double *hourly_fail)
+{
+    if (U > 62) return -1;
+    double energy[64]; unsigned char avail[64]; uint32_t words[64 + 4];
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    int nblk = (U + 2 + 3) / 4;
+    for (int h = 0; h < H; h++) hourly_fail[h] = 0.0;
+    for (int y = 0; y < n_years; y++) {
+        uint64_t yy = (uint64_t)(year0 + y);
+        for (int i = 0; i < U; i++) energy[i] = 0.0;
+        double count = 0.0;
+        for (int h = 1; h <= H; h++) {
+            for (int b = 0; b < nblk; b++) {
+                uint32_t ctr[4] = { (uint32_t)yy, (uint32_t)(yy >> 32), (uint32_t)(h - 1), 0x444D0000u | (uint32_t)b };
+                oracle_philox4x32_10(ctr, key, &words[4 * b]);
+            }
+            int week = (h - 1) / 168 + 1;
+            for (int i = 0; i < U; i++) {
+                avail[i] = 0;
+                if (week >= maint_start[i] && week < maint_start[i] + maint_weeks[i]) continue;
+                if (words[i] < for_thr[i]) continue;
+                avail[i] = 1;
+            }
+            double z = (double)oracle_normal_u32x2(words[U], words[U + 1]);
+            double load = base_load[h - 1] + z * lfu_std;
+            int d;
+            detailed_hour(U, cap, elim, avail, load, energy, &d);
+            if (d) { count += 1.0; hourly_fail[h - 1] += 1.0; }
+        }
+        year_lole[y] = count;
+    }
+    return 0;
+}

@@ -24,7 +24,7 @@ EXPORTS = [
     "psra_create", "psra_destroy", "psra_last_error", "psra_version", "psra_stream", "psra_device_info", "psra_last_counters",
     "psra_set_system", "psra_set_load", "psra_seq_mc", "psra_seq_eval_injected", "psra_nonseq_mc",
     "psra_nonseq_eval_states", "psra_nonseq_eval_uniforms", "psra_copt", "psra_copt_indices",
-    "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail",
+    "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail", "psra_detailed_mc", "psra_detailed_eval_injected",
 ]
 
 
@@ -55,6 +55,12 @@ class NonseqSummary(C.Structure):
 class NonseqOutputs(C.Structure):
     _fields_ = [("lol_hours", C.c_void_p), ("ens_fp", C.c_void_p), ("cap_avail", C.c_void_p),
                 ("states", C.c_void_p), ("group_lol", C.c_void_p), ("group", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class DetailedSystem(C.Structure):
+    _fields_ = [("capacity_mw", C.c_void_p), ("for_rate", C.c_void_p), ("maint_start_week", C.c_void_p),
+                ("maint_weeks", C.c_void_p), ("energy_limit_mwh", C.c_void_p), ("n_units", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -107,5 +113,9 @@ def load():
     L.psra_dtmc_capacity.restype = C.c_int; L.psra_dtmc_capacity.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp]
     L.psra_tail.restype = C.c_int
     L.psra_tail.argtypes = [vp, vp, i64, vp, i32, C.POINTER(TailOut), vp, i32, i64]
+    L.psra_detailed_mc.restype = C.c_int
+    L.psra_detailed_mc.argtypes = [vp, C.POINTER(DetailedSystem), vp, i32, dbl, i64, i64, u64, vp, vp, C.POINTER(C.c_float)]
+    L.psra_detailed_eval_injected.restype = C.c_int
+    L.psra_detailed_eval_injected.argtypes = [vp, C.POINTER(DetailedSystem), vp, i32, dbl, i64, vp, vp, vp, vp]
     _lib = L
     return L

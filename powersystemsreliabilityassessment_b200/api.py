@@ -355,6 +355,35 @@ class Engine:
         self._check(self._L.psra_dtmc_capacity(self._h, _ptr(a), _ptr(b), _ptr(c), U, _ptr(r), T, _ptr(out)))
         return out
 
+    # ---- hourly-resampled MC with maintenance / LFU / ELU (tail_risk.jl:12-91)
+    def _detailed_sys(self, gens):
+        cap = np.ascontiguousarray([g.capacity for g in gens], dtype=np.float64)
+        q = np.ascontiguousarray([g.for_rate for g in gens], dtype=np.float64)
+        ms = np.ascontiguousarray([g.scheduled_outage_start for g in gens], dtype=np.int32)
+        mw = np.ascontiguousarray([g.maintenance_weeks for g in gens], dtype=np.int32)
+        el = np.ascontiguousarray([g.energy_limit for g in gens], dtype=np.float64)
+        sys = _lib.DetailedSystem(_ptr(cap), _ptr(q), _ptr(ms), _ptr(mw), _ptr(el), len(gens), 0)
+        return sys, (cap, q, ms, mw, el)
+
+    def detailed_mc(self, gens, base_load, lfu_std: float, n_years: int, seed: int = 42, year0: int = 0):
+        sys, keep = self._detailed_sys(gens)
+        bl = np.ascontiguousarray(base_load, dtype=np.float64)
+        yl = np.zeros(n_years, dtype=np.uint32); hf = np.zeros(len(bl), dtype=np.uint32)
+        ms = C.c_float()
+        self._check(self._L.psra_detailed_mc(self._h, C.byref(sys), _ptr(bl), len(bl), float(lfu_std), year0,
+                                             n_years, seed, _ptr(yl), _ptr(hf), C.byref(ms)))
+        return yl, hf, ms.value
+
+    def detailed_eval_injected(self, gens, base_load, lfu_std: float, uniforms, normals):
+        sys, keep = self._detailed_sys(gens)
+        bl = np.ascontiguousarray(base_load, dtype=np.float64)
+        un = np.ascontiguousarray(uniforms, dtype=np.float64); no = np.ascontiguousarray(normals, dtype=np.float64)
+        n = un.shape[0]
+        yl = np.zeros(n, dtype=np.uint32); hf = np.zeros(len(bl), dtype=np.uint32)
+        self._check(self._L.psra_detailed_eval_injected(self._h, C.byref(sys), _ptr(bl), len(bl), float(lfu_std), n,
+                                                        _ptr(un), _ptr(no), _ptr(yl), _ptr(hf)))
+        return yl, hf
+
     # ---- tail risk
     def tail(self, values_fp=None, alphas=(0.95, 0.99), n_bins: int = 0, bin_width: int = 1):
         """VaR / CVaR (type-7 quantile, mean of values >= VaR) of integer per-year ENS.
@@ -469,3 +498,64 @@ def evaluate_risk(cum_prob, cum_freq, peak_load: float, installed_cap: float):
             lolf = cum_freq[i]
             return lole_h, lolf, (lole_h / lolf if lolf > 0 else 0.0)
     return 0.0, 0.0, 0.0
+
+
+# ------------------------------------------------ tail_risk.jl / MCvsMarkovProcess.jl entry points
+@dataclasses.dataclass
+class DetailedGenerator:
+    """mutable struct Generator of generating_adequacy_comprehensive.jl:11-24 (the one tail_risk.jl includes)."""
+    name: str
+    capacity: float
+    for_rate: float
+    maintenance_weeks: int
+    energy_limit: float = math.inf
+    effective_q: float = None
+    scheduled_outage_start: int = 0
+
+    def __post_init__(self):
+        if self.effective_q is None:
+            self.effective_q = self.for_rate
+
+
+def schedule_maintenance(gens: Sequence[DetailedGenerator], weekly_peaks) -> None:
+    """schedule_maintenance!, generating_adequacy_comprehensive.jl:86-112 (greedy levelised reserve);
+    sets g.scheduled_outage_start in place.  Host-side planning, O(52 * U)."""
+    peaks = np.asarray(weekly_peaks, dtype=np.float64)
+    total_installed = sum(g.capacity for g in gens)
+    weekly_available = np.full(52, float(total_installed))
+    for g in sorted(gens, key=lambda g: g.capacity * g.maintenance_weeks, reverse=True):
+        if g.maintenance_weeks == 0:
+            continue
+        best_start, max_min_reserve = 1, -math.inf
+        for start_w in range(1, 52 - g.maintenance_weeks + 2):
+            w = slice(start_w - 1, start_w - 1 + g.maintenance_weeks)
+            min_res = float((weekly_available[w] - peaks[w]).min())
+            if min_res > max_min_reserve:
+                max_min_reserve, best_start = min_res, start_w
+        g.scheduled_outage_start = best_start
+        weekly_available[best_start - 1:best_start - 1 + g.maintenance_weeks] -= g.capacity
+
+
+def run_detailed_mc(gens: Sequence[DetailedGenerator], base_load, lfu_sigma_percent: float, n_years: int,
+                    seed: int = 42, engine: Optional[Engine] = None):
+    """tail_risk.jl:12-91 -> (yearly_lole_distribution, hourly_failure_prob)."""
+    eng = engine or default_engine()
+    base_load = np.asarray(base_load, dtype=np.float64)
+    lfu_std_dev = float(base_load.max()) * (lfu_sigma_percent / 100.0)       # tail_risk.jl:22
+    yl, hf, _ = eng.detailed_mc(gens, base_load, lfu_std_dev, n_years, seed=seed)
+    return yl.astype(np.float64), hf.astype(np.float64) / n_years
+
+
+@dataclasses.dataclass
+class SystemParams:
+    """MCvsMarkovProcess.jl:34-38."""
+    step_size: float
+    lfu_sigma_percent: float
+    mc_years: int
+
+
+def run_monte_carlo(gens: Sequence[DetailedGenerator], base_load, params: SystemParams, seed: int = 42,
+                    engine: Optional[Engine] = None):
+    """MCvsMarkovProcess.jl:210-284 -> (mean(yearly_lole), hourly_failures / years, yearly_lole)."""
+    yl, prof = run_detailed_mc(gens, base_load, params.lfu_sigma_percent, params.mc_years, seed=seed, engine=engine)
+    return float(yl.mean()), prof, yl

@@ -32,7 +32,9 @@
 
 #define FAST_NB_MAX 4                  // Philox blocks a unit may get per wave
 #define FAST_PEND_CAP 256              // far-future events (beyond the two-segment ring)
+#ifndef FAST_MAX_THREADS
 #define FAST_MAX_THREADS 768
+#endif
 
 struct FastWarpSmem {                  // per-warp scratch that precedes the timeline ring
     unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit

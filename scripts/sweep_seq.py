@@ -6,9 +6,11 @@ from powersystemsreliabilityassessment_b200 import Engine, rts79
 years = int(float(sys.argv[1])) if len(sys.argv) > 1 else 2_000_000
 cap, mttf, mttr = rts79.units()
 load = rts79.load_curve_int()
+SEGS = [int(x) for x in os.environ.get('SEGS', '2944,2208,1760,1472,1120').split(',')]
+WPBS = [int(x) for x in os.environ.get('WPBS', '16,24').split(',')]
 rows = []
-for seg in (4384, 2944, 2208, 1760, 1472, 1120):
-    for wpb in (16, 24):
+for seg in SEGS:
+    for wpb in WPBS:
         try:
             with Engine(seg_hours=seg, warps_per_block=wpb) as e:
                 e.set_system(cap, mttf, mttr); e.set_load(load)
