@@ -39,6 +39,10 @@ extern "C" {
 
 #define PSRA_INIT_ALL_UP      0  /* PSA.jl:223-224: every unit UP at hour 0 */
 #define PSRA_INIT_STATIONARY  1  /* state ~ Bernoulli(FOR), residual ~ Exp (memoryless) */
+/* OR-ed into init_mode: MATLAB next-event discretisation of Montecarlo_seq/seq_mcsampling.m:48-67
+ * (time to failure rounded to the nearest hour, time to repair rounded up, DOWN from the hour after
+ * the failure time); seqMain.m restarts all-up every year: use PSRA_INIT_ALL_UP, years_per_chain = 1 */
+#define PSRA_DISC_MATLAB      0x100
 
 typedef struct psra_handle psra_handle;
 

@@ -79,6 +79,9 @@ def lib():
         L.oracle_markov2.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp]
         L.oracle_dtmc_capacity.restype = None
         L.oracle_dtmc_capacity.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp]
+        L.oracle_seq_matlab_philox.restype = C.c_int
+        L.oracle_seq_matlab_philox.argtypes = [C.c_int, _dp, _fp, _fp, C.c_int, _dp, C.c_uint64, C.c_int64, C.c_int64,
+                                               _dp, _dp, _dp]
         L.oracle_normal_u32x2.restype = C.c_float
         L.oracle_normal_u32x2.argtypes = [C.c_uint32, C.c_uint32]
         L.oracle_detailed_mc_injected.restype = C.c_int
@@ -131,6 +134,15 @@ def seq_philox(cap, mttf, mttr, load, seed, chain0, nchains, years_per_chain=1, 
     lol = np.zeros(n); eue = np.zeros(n); ent = np.zeros(n)
     lib().oracle_seq_philox(len(cap), cap, mf, mr, thr, len(load), load, seed, chain0, nchains,
                             years_per_chain, init_mode, lol, eue, ent)
+    return lol, eue, ent
+
+
+def seq_matlab_philox(cap, mttf, mttr, load, seed, year0, nyears):
+    """Montecarlo_seq/seq_mcsampling.m:40-74 discretisation (round / ceil, all UP every year) at HL1."""
+    cap = _d(cap); load = _d(load)
+    mf = np.ascontiguousarray(mttf, dtype=np.float32); mr = np.ascontiguousarray(mttr, dtype=np.float32)
+    lol = np.zeros(nyears); eue = np.zeros(nyears); ent = np.zeros(nyears)
+    lib().oracle_seq_matlab_philox(len(cap), cap, mf, mr, len(load), load, seed, year0, nyears, lol, eue, ent)
     return lol, eue, ent
 
 

@@ -720,3 +720,57 @@ int oracle_detailed_mc_philox(int U, const double *cap, const uint32_t *for_thr,
     }
     return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------
+ * 10. MATLAB next-event discretisation -- Montecarlo_seq/seq_mcsampling.m:40-74 (SURVEY a-8),
+ *     evaluated at HL1 (capacity vs load, no network): every year all components start UP at
+ *     time 0 (:40-41, seqMain.m:91); time to failure = round(-MTTF ln u) (:52-53, MATLAB round =
+ *     half away from zero), time to repair = ceil(-MTTR ln u) (:59-60); the DOWN hours are
+ *     start = round(t)+1 ... min(start+dur-1, H) (:63-67).  Durations come from the sampler
+ *     streams of section 2 (draw 0 of a unit is consumed and ignored, as in ALL_UP mode).
+ * -------------------------------------------------------------------------------- */
+int oracle_seq_matlab_philox(int U, const double *cap, const float *mttf_f, const float *mttr_f, int H,
+                             const double *load, uint64_t seed, int64_t year0, int64_t nyears,
+                             double *year_lol, double *year_eue, double *year_entries)
+{
+    unsigned char *down = (unsigned char *)malloc((size_t)U * (size_t)H);
+    draw_stream st;
+    for (int64_t y = 0; y < nyears; y++) {
+        memset(down, 0, (size_t)U * (size_t)H);
+        for (int i = 0; i < U; i++) {
+            stream_init(&st, seed, (uint64_t)(year0 + y), (uint32_t)i);
+            (void)stream_next(&st);
+            double current_time = 0; int is_up = 1;
+            while (current_time < H) {
+                if (is_up) {
+                    double duration = duration_hours(mttf_f[i], stream_next(&st));
+                    double duration_int = round(duration);
+                    current_time = current_time + duration_int;
+                } else {
+                    double duration = duration_hours(mttr_f[i], stream_next(&st));
+                    double duration_int = ceil(duration);
+                    long start_idx = (long)round(current_time) + 1;
+                    long end_idx = start_idx + (long)duration_int - 1;
+                    if (end_idx > H) end_idx = H;
+                    if (start_idx <= H)
+                        for (long h = start_idx; h <= end_idx; h++) down[(size_t)i * H + (h - 1)] = 1;
+                    current_time = current_time + duration_int;
+                }
+                is_up = !is_up;
+            }
+        }
+        double lole = 0.0, eue = 0.0, entries = 0.0; int prev = 0;
+        for (int h = 0; h < H; h++) {
+            double cap_avail = 0.0;
+            for (int i = 0; i < U; i++) if (!down[(size_t)i * H + h]) cap_avail += cap[i];
+            int flag = 0;
+            if (cap_avail < load[h]) { lole += 1.0; eue += load[h] - cap_avail; flag = 1; }
+            if (flag && !prev) entries += 1.0;
+            prev = flag;
+        }
+        year_lol[y] = lole; year_eue[y] = eue; year_entries[y] = entries;
+    }
+    free(down);
+    return 0;
+}

@@ -19,6 +19,7 @@ PSRA_E_OVERFLOW = -3
 PSRA_E_NCCL = -4
 INIT_ALL_UP = 0
 INIT_STATIONARY = 1
+DISC_MATLAB = 0x100
 
 EXPORTS = [
     "psra_create", "psra_destroy", "psra_last_error", "psra_version", "psra_stream", "psra_device_info", "psra_last_counters",

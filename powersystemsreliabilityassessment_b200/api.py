@@ -559,3 +559,49 @@ def run_monte_carlo(gens: Sequence[DetailedGenerator], base_load, params: System
     """MCvsMarkovProcess.jl:210-284 -> (mean(yearly_lole), hourly_failures / years, yearly_lole)."""
     yl, prof = run_detailed_mc(gens, base_load, params.lfu_sigma_percent, params.mc_years, seed=seed, engine=engine)
     return float(yl.mean()), prof, yl
+
+
+# ------------------------------------------------------------------ adaptive stopping (SURVEY f-2)
+def run_sequential_until_cov(engine: Engine, cov_threshold: float = 0.05, batch_years: int = 1000,
+                             max_years: int = 10_000_000, seed: int = 42, init_mode: int = INIT_STATIONARY,
+                             years_per_chain: int = 1) -> SequentialIndices:
+    """Montecarlo_seq/seqMain.m:183-197 stop rule: simulate until CoV = std(ENS_1..n)/(mean*sqrt(n)) drops below
+    the threshold (and is > 0).  The reference tests the rule after every year; here after every batch of
+    years (one kernel launch each), so the stop year is rounded up to a batch boundary."""
+    tot = None
+    done = 0
+    while done < max_years:
+        n = min(batch_years, max_years - done)
+        r = engine.seq_mc(n, seed=seed, year0=done, init_mode=init_mode, years_per_chain=years_per_chain)
+        tot = dict(r.raw) if tot is None else {k: tot[k] + r.raw[k] for k in tot}
+        done += n
+        idx = indices_from_raw(tot, engine.fp_scale)
+        if 0 < idx.cov_eens < cov_threshold:
+            break
+    return indices_from_raw(tot, engine.fp_scale)
+
+
+def run_nonseq_until_beta(engine: Engine, beta_threshold: float = 0.0017, batch: int = 100, max_samples: int = 100_000,
+                          seed: int = 42):
+    """Montecarlo_nsq_single/nsqMain.m:60-62,285-301 stop rule for the state sampler: beta =
+    sqrt(sum (dns - EDNS)^2) / N / EDNS on the samples so far (peak-load mode: set_load([peak]) so that the
+    per-sample ENS is the DNS); stops at beta < threshold or max_samples.  Returns (result dict, beta history)."""
+    tot = None
+    done = 0
+    history = []
+    while done < max_samples:
+        n = min(batch, max_samples - done)
+        r = engine.nonseq_mc(n, seed=seed, sample0=done)
+        tot = dict(r["raw"]) if tot is None else {k: tot[k] + r["raw"][k] for k in tot}
+        done += n
+        N = tot["samples"]
+        mean = tot["sum_ens_fp"] / N
+        ss = tot["sum_ens_sq"] - N * mean * mean            # sum (dns - EDNS)^2
+        beta = math.sqrt(max(ss, 0.0)) / N / mean if mean > 0 else math.inf
+        history.append(beta)
+        if beta < beta_threshold:
+            break
+    N = tot["samples"]
+    out = dict(samples=N, plc=tot["samples_with_loss"] / N, lole=tot["sum_lol_hours"] / N,
+               edns=tot["sum_ens_fp"] / N / engine.fp_scale, beta=history[-1], raw=tot)
+    return out, np.array(history)

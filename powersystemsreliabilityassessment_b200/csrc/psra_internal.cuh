@@ -126,6 +126,15 @@ __device__ __forceinline__ unsigned long long dur_ticks(float mean_ticks, uint32
     return (unsigned long long)__float2ll_rn(fmaxf(__fmul_rn(mean_ticks, neglog_u32(x)), 1.0f));
 }
 
+// MATLAB next-event discretisation (Montecarlo_seq/seq_mcsampling.m:52-60): time to failure rounded to
+// the nearest hour (half up), time to repair rounded up; result again in ticks
+__device__ __forceinline__ unsigned long long dur_ticks_disc(float mean_ticks, uint32_t x, bool up_state, int disc)
+{
+    unsigned long long t = dur_ticks(mean_ticks, x);
+    if (disc) t = ((t + (up_state ? (1ull << 23) : ((1ull << 24) - 1ull))) >> 24) << 24;
+    return t;
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 {
 #pragma unroll

@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 struct SeqArgs {
-    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16;
+    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc;
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
     const int32_t *load; const int32_t *lmax;
     uint32_t k0, k1;

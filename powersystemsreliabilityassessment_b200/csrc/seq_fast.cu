@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         int pend_cnt = 0;
         int capacity = 0;
         int ring = 0;                 // ring half that holds the current segment
-        ws->t_run[lane] = 0ull;
+        // MATLAB discretisation: a unit that fails after d whole hours is DOWN from hour d+1 (seq_mcsampling.m:63)
+        ws->t_run[lane] = a.disc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
         __syncwarp();
         bool init_wave = true;
 
@@ -258,10 +259,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const float mup = s_mup[u], mdn = s_mdn[u];
                         const float m_a = s0u ? mdn : mup;      // draws 0, 2 of a block: state s0^1
                         const float m_b = s0u ? mup : mdn;      // draws 1, 3: state s0
-                        const unsigned long long p1 = (b == 0u) ? 0ull : dur_ticks(m_a, x[0]);
-                        const unsigned long long p2 = p1 + dur_ticks(m_b, x[1]);
-                        const unsigned long long p3 = p2 + dur_ticks(m_a, x[2]);
-                        const unsigned long long p4 = p3 + dur_ticks(m_b, x[3]);
+                        const unsigned long long p1 = (b == 0u) ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, a.disc);
+                        const unsigned long long p2 = p1 + dur_ticks_disc(m_b, x[1], s0u, a.disc);
+                        const unsigned long long p3 = p2 + dur_ticks_disc(m_a, x[2], !s0u, a.disc);
+                        const unsigned long long p4 = p3 + dur_ticks_disc(m_b, x[3], s0u, a.disc);
                         const unsigned long long tot = act ? p4 : 0ull;
                         unsigned long long inc2 = tot;
 #pragma unroll

@@ -72,7 +72,7 @@ __device__ __forceinline__ double next_duration(const SeqArgs &a, long long chai
         const uint32_t x = next_word<false>(a, chain, u, s);
         // tick-quantised duration (2^-24 h), same definition as seq_fast.cu / DESIGN.md "Sampler"
         const float mt = __fmul_rn(s.status ? mf : mr, 16777216.0f);
-        return (double)dur_ticks(mt, x) * 5.9604644775390625e-08;
+        return (double)dur_ticks_disc(mt, x, s.status != 0, a.disc) * 5.9604644775390625e-08;
     }
 }
 
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
                             if (a.init_mode == PSRA_INIT_STATIONARY && x0 < thr) st.status = 0;
                         }
                         const double d0 = next_duration<kInjected>(a, cl, chain, u, st, mf, mr);
-                        schedule(st, d0, -1);
+                        schedule(st, (!kInjected && a.disc) ? d0 + 1.0 : d0, -1);   // MATLAB: DOWN from hour d+1
                         cap_part += st.status ? capu : 0;
                     } else if constexpr (!kOneUnit) {
                         st.r = st_r[u]; st.next = st_next[u];
@@ -302,7 +302,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     const bool packed = h->total_cap <= 32767, load16 = h->max_load <= 32767;
     const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0];
     SeqArgs a{};
-    a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode; a.K = K;
+    a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode & ~PSRA_DISC_MATLAB; a.K = K;
+    a.disc = (!injected && (init_mode & PSRA_DISC_MATLAB)) ? 1 : 0;
     a.cap = h->d_cap; a.mttf = h->d_mttf; a.mttr = h->d_mttr; a.for_thr = h->d_for_thr;
     a.load = h->d_load; a.lmax = h->d_lmax;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
@@ -437,7 +438,8 @@ extern "C" int psra_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64
     PSRA_REQUIRE(h, year0 >= 0 && nyears >= 0, "negative year range");
     PSRA_REQUIRE(h, year0 % years_per_chain == 0 && nyears % years_per_chain == 0,
                  "year0 and nyears must be multiples of years_per_chain");
-    PSRA_REQUIRE(h, init_mode == PSRA_INIT_ALL_UP || init_mode == PSRA_INIT_STATIONARY, "unknown init_mode");
+    PSRA_REQUIRE(h, (init_mode & ~PSRA_DISC_MATLAB) == PSRA_INIT_ALL_UP || (init_mode & ~PSRA_DISC_MATLAB) == PSRA_INIT_STATIONARY,
+                 "unknown init_mode");
     return run_seq(h, false, nullptr, 0, year0 / years_per_chain, nyears / years_per_chain, years_per_chain,
                    init_mode, seed, out, summary);
 }

@@ -82,3 +82,17 @@ def test_config1_statistics_hourly_and_peak(engine, rts):
     plc = p["lole"]                       # H = 1: LOL "hours" per sample = loss indicator
     assert abs(plc - 0.084578060826) < 3 * p["lole_se"]
     assert 13.0 < p["eue"] < 16.0         # EDNS ballpark 14.51 MW
+
+
+def test_adaptive_stop_rules(engine, rts):
+    """f-2: CoV stop of seqMain.m:183-197 and beta stop of nsqMain.m:299-301 on top of batched launches."""
+    import powersystemsreliabilityassessment_b200 as P
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(rts["load_int"])
+    r = P.run_sequential_until_cov(engine, cov_threshold=0.05, batch_years=200, seed=3)
+    assert 0 < r.cov_eens < 0.05 and r.years % 200 == 0 and 800 <= r.years <= 4000     # HL2 run stopped at 1245
+    again = engine.seq_mc(r.years, seed=3)
+    assert again.raw["sum_ens_fp"] == r.raw["sum_ens_fp"]        # batches are shards of one experiment
+    engine.set_load(np.array([2850], dtype=np.int32))
+    out, hist = P.run_nonseq_until_beta(engine, beta_threshold=0.02, batch=1000, max_samples=200_000, seed=9)
+    assert out["beta"] < 0.02 and len(hist) == out["samples"] // 1000
+    assert abs(out["plc"] - 0.0846) < 0.01 and 12 < out["edns"] < 17

@@ -201,3 +201,28 @@ def test_fixed_point_scale_int32_timeline(engine, rts):
     assert np.array_equal(r.entries.astype(np.float64), ent)
     assert np.allclose(r.ens, ens / 16.0) and lol.sum() > 0
     engine.set_system(rts["cap"], rts["mttf"], rts["mttr"], fp_scale=1.0)
+
+
+def test_matlab_discretisation_mode(engine, rts):
+    """SURVEY a-8: round(TTF) / ceil(TTR), all UP each year (Montecarlo_seq/seq_mcsampling.m:40-74), both
+    kernels vs the oracle's literal restatement of the MATLAB sampler evaluated at HL1."""
+    from powersystemsreliabilityassessment_b200 import DISC_MATLAB, INIT_ALL_UP, Engine
+    load = rts["load_int"]
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(load)
+    r = engine.seq_mc(96, seed=77, year0=32, init_mode=INIT_ALL_UP | DISC_MATLAB, per_year=True)
+    lol, ens, ent = O.seq_matlab_philox(rts["cap"], rts["mttf"], rts["mttr"], load.astype(np.float64), 77, 32, 96)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol)
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    assert np.array_equal(r.entries.astype(np.float64), ent) and lol.sum() > 0
+    with Engine(force_generic=True) as g:
+        g.set_system(rts["cap"], rts["mttf"], rts["mttr"]); g.set_load(load)
+        r2 = g.seq_mc(96, seed=77, year0=32, init_mode=INIT_ALL_UP | DISC_MATLAB, per_year=True)
+    assert np.array_equal(r.lol_hours, r2.lol_hours) and np.array_equal(r.raw["ens_fp_vector"], r2.raw["ens_fp_vector"])
+    # short cycles: zero-hour up times and same-hour double toggles
+    cap = np.array([10.0, 5.0, 7.0]); mttf = np.array([3.0, 0.4, 30.0]); mttr = np.array([1.5, 2.0, 0.2])
+    ld = np.full(500, 14, dtype=np.int32)
+    engine.set_system(cap, mttf, mttr); engine.set_load(ld)
+    r3 = engine.seq_mc(64, seed=5, init_mode=INIT_ALL_UP | DISC_MATLAB, per_year=True)
+    lol, ens, ent = O.seq_matlab_philox(cap, mttf, mttr, ld.astype(np.float64), 5, 0, 64)
+    assert np.array_equal(r3.lol_hours.astype(np.float64), lol) and np.array_equal(r3.entries.astype(np.float64), ent)
+    assert np.array_equal(r3.raw["ens_fp_vector"].astype(np.float64), ens)
