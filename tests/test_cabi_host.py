@@ -30,6 +30,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.NonseqSummary) == 64
     assert ctypes.sizeof(_lib.NonseqOutputs) == 48
     assert ctypes.sizeof(_lib.TailOut) == 40
+    assert ctypes.sizeof(_lib.DetailedSystem) == 48
 
 
 def test_no_cpu_fallback():
