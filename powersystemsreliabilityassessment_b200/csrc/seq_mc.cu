@@ -301,6 +301,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     const bool one_unit = h->U <= 32;
     const bool packed = h->total_cap <= 32767, load16 = h->max_load <= 32767;
     const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0];
+    const bool team = !injected && !one_unit && h->U <= seq_team_max_units() && (long long)ypc * h->H < (1ll << 20) &&
+                      !h->cfg.reserved[0];
     SeqArgs a{};
     a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode & ~PSRA_DISC_MATLAB; a.K = K;
     a.disc = (!injected && (init_mode & PSRA_DISC_MATLAB)) ? 1 : 0;
@@ -313,22 +315,29 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
 
     // launch geometry: segment length and warps per block under the shared-memory budget
     int seg_words = h->Wd;
+    if (team) {
+        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : 1760;
+        seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
+    }
     if (one_unit) {
         int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : (fast ? 1760 : 1120);
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
     a.seg_words = seg_words;
     a.nseg = (h->Wd + seg_words - 1) / seg_words;
-    a.persist = (!one_unit && (ypc > 1 || a.nseg > 1)) ? 1 : 0;
+    a.persist = (!one_unit && !team && (ypc > 1 || a.nseg > 1)) ? 1 : 0;
+    a.pend_cap = seq_team_pend_cap(h->U);
     int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 24 : 16);
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
         if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, packed, load16);
+        if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words);
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
         if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
         return b;
     };
+    if (team) wpb = SEQ_TEAM_WARPS;
     while (wpb > 1 && smem_for(wpb) > h->smem_optin) wpb--;
     const size_t smem = smem_for(wpb);
     if (smem > h->smem_optin)
@@ -384,6 +393,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     int bps = 0;
     if (fast) {
         PSRA_CUDA(h, seq_fast_prepare(packed, smem, wpb * 32, &bps));
+    } else if (team) {
+        PSRA_CUDA(h, seq_team_prepare(smem, &bps));
     } else {
         PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PSRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
@@ -391,11 +402,12 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (bps < 1) return psra_fail(h, PSRA_E_CUDA, "sequential kernel does not fit on an SM (smem %zu B)", smem);
     if (h->cfg.blocks_per_sm > 0) bps = std::min(bps, h->cfg.blocks_per_sm);
     long long grid = (long long)h->sm_count * bps;
-    const long long need = (nchains + wpb - 1) / wpb;
+    const long long need = team ? nchains : (nchains + wpb - 1) / wpb;
     if (grid > need) grid = need;
 
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (fast) seq_fast_launch(packed, a, (unsigned)grid, wpb * 32, smem, h->stream);
+    else if (team) seq_team_launch(a, (unsigned)grid, smem, h->stream);
     else kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
     PSRA_CUDA(h, cudaGetLastError());
     PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));

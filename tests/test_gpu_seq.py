@@ -226,3 +226,34 @@ def test_matlab_discretisation_mode(engine, rts):
     lol, ens, ent = O.seq_matlab_philox(cap, mttf, mttr, ld.astype(np.float64), 5, 0, 64)
     assert np.array_equal(r3.lol_hours.astype(np.float64), lol) and np.array_equal(r3.entries.astype(np.float64), ent)
     assert np.array_equal(r3.raw["ens_fp_vector"].astype(np.float64), ens)
+
+
+def test_team_kernel_large_systems(engine, rts):
+    """seq_team.cu (block per chain, > 32 units): bit-exact vs the oracle's literal loop and vs the generic
+    kernel, incl. a unit count that is not a multiple of 32, multi-year chains and BASELINE config 5 (1024 units)."""
+    from powersystemsreliabilityassessment_b200 import DISC_MATLAB, INIT_ALL_UP, Engine, rts79
+    cap = np.tile(rts["cap"], 3)[:70]; mttf = np.tile(rts["mttf"], 3)[:70]; mttr = np.tile(rts["mttr"], 3)[:70]
+    load = np.rint(2.2 * rts["load_mw"]).astype(np.int32)
+    engine.set_system(cap, mttf, mttr); engine.set_load(load)
+    for ypc, init in ((1, 1), (4, 0)):
+        r = engine.seq_mc(24 * ypc, seed=31, init_mode=init, years_per_chain=ypc, per_year=True, fail_count=True)
+        lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 31, 0, 24, ypc, init)
+        assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(r.entries.astype(np.float64), ent)
+        assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens) and lol.sum() > 0
+        with Engine(force_generic=True) as g:
+            g.set_system(cap, mttf, mttr); g.set_load(load)
+            r2 = g.seq_mc(24 * ypc, seed=31, init_mode=init, years_per_chain=ypc, per_year=True, fail_count=True)
+        assert np.array_equal(r.lol_hours, r2.lol_hours) and np.array_equal(r.fail_count, r2.fail_count)
+        assert r.raw["events"] == r2.raw["events"]
+    r = engine.seq_mc(16, seed=8, init_mode=INIT_ALL_UP | DISC_MATLAB, per_year=True)
+    lol, ens, ent = O.seq_matlab_philox(cap, mttf, mttr, load.astype(np.float64), 8, 0, 16)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    # config 5: 1024 units, load x 37
+    cap, mttf, mttr, load = rts79.synthetic_system(32, 37.0)
+    engine.set_system(cap, mttf, mttr); engine.set_load(load)
+    r = engine.seq_mc(12, seed=2024, year0=100, per_year=True)
+    lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 2024, 100, 12, 1, 1)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(r.entries.astype(np.float64), ent)
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+    big = engine.seq_mc(20000, seed=1)
+    assert abs(big.lole - 8.033131) < 4 * big.lole_se          # analytical COPT value (BASELINE.md section 3)
