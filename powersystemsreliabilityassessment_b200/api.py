@@ -160,7 +160,7 @@ class Engine:
         out = (C.c_uint64 * 16)()
         self._check(self._L.psra_last_counters(self._h, out, 16))
         v = list(out)
-        return dict(waves=v[9], jobs=v[10], ahead_jobs=v[11], resolved_runs=v[12], events=v[7])
+        return dict(waves=v[9], jobs=v[10], ahead_jobs=v[11], resolved_runs=v[12], pend_max=v[13], events=v[7])
 
     # ---- system data
     def set_system(self, capacity_mw, mttf_h, mttr_h, fp_scale: float = 1.0, strict: bool = True):

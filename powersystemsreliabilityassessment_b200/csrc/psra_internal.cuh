@@ -166,5 +166,5 @@ __device__ __forceinline__ void atomic_add_u128(unsigned long long *lo, unsigned
 // accumulator slots in d_acc
 enum {
     ACC_LOL = 0, ACC_ENS, ACC_ENT, ACC_YWL, ACC_LOL2, ACC_ENS2_LO, ACC_ENS2_HI, ACC_EVENTS,
-    ACC_OVERFLOW, ACC_WAVES, ACC_JOBS, ACC_OPT_JOBS, ACC_FLAGGED, ACC_COUNT = 32
+    ACC_OVERFLOW, ACC_WAVES, ACC_JOBS, ACC_OPT_JOBS, ACC_FLAGGED, ACC_PEND_MAX, ACC_COUNT = 32
 };

@@ -85,7 +85,7 @@ __device__ __forceinline__ int tl_get(const int32_t *tl, int slot)
     return tl[slot];
 }
 
-template <bool kPacked>
+template <bool kPacked, bool kDisc>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
     long long acc_ens = 0;
     unsigned int n_events = 0;
-    unsigned int n_waves = 0, n_jobs = 0, n_opt = 0, n_flag = 0;   // warp-uniform diagnostics
+    unsigned int n_waves = 0, n_jobs = 0, n_opt = 0, n_flag = 0, pend_max = 0;   // warp-uniform diagnostics
 
     const bool unit_valid = lane < a.U;
     const int capu = s_cap[lane];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         int capacity = 0;
         int ring = 0;                 // ring half that holds the current segment
         // MATLAB discretisation: a unit that fails after d whole hours is DOWN from hour d+1 (seq_mcsampling.m:63)
-        ws->t_run[lane] = a.disc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
+        ws->t_run[lane] = kDisc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
         __syncwarp();
         bool init_wave = true;
 
@@ -259,10 +259,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const float mup = s_mup[u], mdn = s_mdn[u];
                         const float m_a = s0u ? mdn : mup;      // draws 0, 2 of a block: state s0^1
                         const float m_b = s0u ? mup : mdn;      // draws 1, 3: state s0
-                        const unsigned long long p1 = (b == 0u) ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, a.disc);
-                        const unsigned long long p2 = p1 + dur_ticks_disc(m_b, x[1], s0u, a.disc);
-                        const unsigned long long p3 = p2 + dur_ticks_disc(m_a, x[2], !s0u, a.disc);
-                        const unsigned long long p4 = p3 + dur_ticks_disc(m_b, x[3], s0u, a.disc);
+                        const unsigned long long p1 = (b == 0u) ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, kDisc);
+                        const unsigned long long p2 = p1 + dur_ticks_disc(m_b, x[1], s0u, kDisc);
+                        const unsigned long long p3 = p2 + dur_ticks_disc(m_a, x[2], !s0u, kDisc);
+                        const unsigned long long p4 = p3 + dur_ticks_disc(m_b, x[3], s0u, kDisc);
                         const unsigned long long tot = act ? p4 : 0ull;
                         unsigned long long inc2 = tot;
 #pragma unroll
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         init_wave = false;
                     }
                 }
+                pend_max = max(pend_max, (unsigned int)pend_cnt);
                 if (pend_cnt > FAST_PEND_CAP) {                  // reported as PSRA_E_OVERFLOW (never seen in practice)
                     if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 2ull);
                     pend_cnt = FAST_PEND_CAP;
@@ -413,12 +414,19 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         atomicAdd(&a.acc[ACC_JOBS], (unsigned long long)n_jobs);
         atomicAdd(&a.acc[ACC_OPT_JOBS], (unsigned long long)n_opt);
         atomicAdd(&a.acc[ACC_FLAGGED], (unsigned long long)n_flag);
+        atomicMax(&a.acc[ACC_PEND_MAX], (unsigned long long)pend_max);
     }
 }
 
-cudaError_t seq_fast_prepare(bool packed, size_t smem, int threads, int *blocks_per_sm)
+static const void *fast_kernel_ptr(bool packed, bool disc)
 {
-    const void *k = packed ? (const void *)seq_fast_kernel<true> : (const void *)seq_fast_kernel<false>;
+    if (packed) return disc ? (const void *)seq_fast_kernel<true, true> : (const void *)seq_fast_kernel<true, false>;
+    return disc ? (const void *)seq_fast_kernel<false, true> : (const void *)seq_fast_kernel<false, false>;
+}
+
+cudaError_t seq_fast_prepare(bool packed, bool disc, size_t smem, int threads, int *blocks_per_sm)
+{
+    const void *k = fast_kernel_ptr(packed, disc);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem);
@@ -426,6 +434,6 @@ cudaError_t seq_fast_prepare(bool packed, size_t smem, int threads, int *blocks_
 
 void seq_fast_launch(bool packed, const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
 {
-    if (packed) seq_fast_kernel<true><<<grid, threads, smem, stream>>>(a);
-    else seq_fast_kernel<false><<<grid, threads, smem, stream>>>(a);
+    void *args[] = {(void *)&a};
+    cudaLaunchKernel(fast_kernel_ptr(packed, a.disc != 0), dim3(grid), dim3(threads), args, smem, stream);
 }

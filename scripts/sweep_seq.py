@@ -17,7 +17,7 @@ for seg in SEGS:
                 e.seq_mc(200_000, seed=1)
                 best = min(e.seq_mc(years, seed=2 + i).kernel_ms for i in range(3))
                 r = e.seq_mc(years, seed=2)
-                c = e.last_counters(); rows.append(dict(seg=seg, wpb=wpb, ms=round(best, 2), Myps=round(years / best / 1e3, 1), waves=c['waves'] / years, jobs=c['jobs'] / years, ahead=c['ahead_jobs'] / years, runs=c['resolved_runs'] / years))
+                c = e.last_counters(); rows.append(dict(seg=seg, wpb=wpb, ms=round(best, 2), Myps=round(years / best / 1e3, 1), waves=c['waves'] / years, jobs=c['jobs'] / years, ahead=c['ahead_jobs'] / years, runs=c['resolved_runs'] / years, pend_max=c['pend_max']))
                 print(rows[-1], flush=True)
         except Exception as ex:
             print("fail", seg, wpb, ex, flush=True)
