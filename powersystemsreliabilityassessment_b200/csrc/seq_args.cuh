@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 struct SeqArgs {
-    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap;
+    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves;
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
     const int32_t *load; const int32_t *lmax;
     uint32_t k0, k1;
@@ -20,10 +20,10 @@ struct SeqArgs {
 #define PSRA_TICK_SHIFT 24
 
 // seq_fast.cu
-size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, bool packed, bool load16);
+size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_cap, bool two_halves, bool load16);
 int seq_fast_max_threads();
-cudaError_t seq_fast_prepare(bool packed, bool disc, size_t smem, int threads, int *blocks_per_sm);
-void seq_fast_launch(bool packed, const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);
+cudaError_t seq_fast_prepare(bool disc, size_t smem, int threads, int *blocks_per_sm);
+void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);
 
 // seq_team.cu
 size_t seq_team_smem_bytes(int U, int Wd, int seg_words);

@@ -13,18 +13,21 @@
 //    spread over the 32 lanes (lane = job, not lane = unit), each lane turns its block into four
 //    durations and a local prefix, and a segmented warp-shuffle scan chains the blocks of a unit.
 //    Lane utilisation no longer depends on the 6x spread of the units' event rates.
-//  * The warp's shared-memory hour timeline is a ring of two segments.  Events of the current and
-//    of the next segment are scattered directly (atomicAdd of the integer MW delta -- two int16
-//    hours packed per word when the installed capacity allows -- plus atomicAdd into the per-word
-//    delta sums); the rare events beyond the ring wait in a small pending list.  A wave is one round
-//    of <= 32 jobs: blocks for the units that are short of the current segment first, the spare
-//    lanes pre-generate blocks towards the end of the next segment.
-//  * Evaluation: lane = run of consecutive 32-hour words; the per-word delta sums (and sums of
-//    negative deltas) are accumulated at scatter time.  One shuffle scan per segment gives the
-//    capacity entering each lane's run; conservative flag
-//    min-capacity-bound < max-load-of-word; flagged runs (rare) are resolved hour by hour with
-//    ballot/popc (LOL hours, deficit entries) and per-lane ENS accumulators.  The timeline segment
-//    is then cleared with 16-byte stores.
+//  * The warp's shared-memory timeline is a ring of two segments kept at two resolutions: per
+//    32-hour word the sum of the integer MW deltas and the sum of the negative deltas (atomicAdd at
+//    scatter time), and a compact event list (hour, unit, sign) per ring half.  Hour resolution is
+//    rebuilt from the event list only for the few words that can contain loss of load.  The rare
+//    events beyond the ring wait in a small pending list.  A wave is one round of <= 32 jobs:
+//    blocks for the units that are short of the current segment first, the spare lanes
+//    pre-generate blocks towards the end of the next segment.  For RTS-79 the whole year is one
+//    segment (no ring switch, no pending traffic).
+//  * Evaluation: lane = run of consecutive words.  One shuffle scan per segment over the word
+//    sums gives the capacity entering each run; conservative flag
+//    capacity + (negative deltas of the word) < max load of the word (table staged in shared
+//    memory).  Flagged words (about 3 per RTS-79 year) are resolved hour by hour, lane = hour:
+//    the word's deltas are gathered from the event list, a shuffle scan turns them into the 32
+//    capacities, which are compared with the load curve staged once per block in shared memory;
+//    __ballot_sync/__popc give LOL hours and deficit entries, per-lane int64 accumulators the ENS.
 #include <limits.h>
 
 #include "psra_internal.cuh"
@@ -36,16 +39,19 @@
 #define FAST_MAX_THREADS 768
 #endif
 
-struct FastWarpSmem {                  // per-warp scratch that precedes the timeline ring
+struct FastWarpSmem {                  // per-warp scratch that precedes the event lists
     unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit
-    uint32_t pend[FAST_PEND_CAP];      // (hour << 6) | (unit << 1) | (delta > 0)
-    unsigned char jobmap[32 * FAST_NB_MAX];
+    int32_t hour_delta[32];            // hour-resolved deltas of the word being resolved
+    unsigned char jobmap[32];
 };
 
-__host__ __device__ inline size_t fast_warp_bytes(int seg_words, bool packed)
+// two_halves: the ring needs its second half (several segments per year, or multi-year chains)
+__host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, bool two_halves)
 {
-    size_t b = sizeof(FastWarpSmem) + 2 * (packed ? 2 : 4) * (size_t)seg_words * 32 +
-               2 * sizeof(uint32_t) * (size_t)((2 * seg_words + 3) & ~3);   // word sums + word negative sums (ring)
+    const int halves = two_halves ? 2 : 1;
+    size_t b = sizeof(FastWarpSmem) + (two_halves ? sizeof(uint32_t) * FAST_PEND_CAP : 0) +
+               sizeof(uint32_t) * (size_t)halves * ev_cap +                          // event lists
+               2 * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);        // word sums + negative sums
     return (b + 15) & ~(size_t)15;
 }
 
@@ -56,36 +62,14 @@ __host__ __device__ inline size_t fast_block_bytes(int Wd, bool load16)
     return (b + 15) & ~(size_t)15;
 }
 
-size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, bool packed, bool load16)
+size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_cap, bool two_halves, bool load16)
 {
-    return fast_block_bytes(Wd, load16) + (size_t)warps_per_block * fast_warp_bytes(seg_words, packed);
+    return fast_block_bytes(Wd, load16) + (size_t)warps_per_block * fast_warp_bytes(seg_words, ev_cap, two_halves);
 }
 
 int seq_fast_max_threads() { return FAST_MAX_THREADS; }
 
-// timeline access: int32 per hour, or two int16 hours per 32-bit word.  The packed form adds the
-// (sign-extended) delta of the low hour and delta * 65536 of the high hour with ordinary wrapping
-// integer adds; the word then holds S_lo + 65536 * S_hi (mod 2^32), which decodes exactly as long
-// as both sums stay inside int16 (installed capacity <= 32767 fixed-point units).
-template <bool kPacked>
-__device__ __forceinline__ void tl_add(int32_t *tl, int slot, int delta)
-{
-    if (kPacked) atomicAdd(&tl[slot >> 1], (slot & 1) ? (int)((uint32_t)delta << 16) : delta);
-    else atomicAdd(&tl[slot], delta);
-}
-
-template <bool kPacked>
-__device__ __forceinline__ int tl_get(const int32_t *tl, int slot)
-{
-    if (kPacked) {
-        const int w = tl[slot >> 1];
-        const int lo = (int)(short)(w & 0xffff);
-        return (slot & 1) ? ((w - lo) >> 16) : lo;
-    }
-    return tl[slot];
-}
-
-template <bool kPacked, bool kDisc>
+template <bool kDisc>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -100,13 +84,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     float *s_mup = reinterpret_cast<float *>(s_cap + 32);
     float *s_mdn = s_mup + 32;
     uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_mdn + 32);
-    unsigned char *wbase = smem_raw + fast_block_bytes(a.Wd, load16) + (size_t)warp * fast_warp_bytes(a.seg_words, kPacked);
+    const bool two_halves = a.two_halves != 0;
+    const int halves = two_halves ? 2 : 1;
+    const int ev_cap = a.ev_cap;
+    unsigned char *wbase = smem_raw + fast_block_bytes(a.Wd, load16) + (size_t)warp * fast_warp_bytes(a.seg_words, ev_cap, two_halves);
     FastWarpSmem *ws = reinterpret_cast<FastWarpSmem *>(wbase);
-    int32_t *tl = reinterpret_cast<int32_t *>(wbase + sizeof(FastWarpSmem));     // ring: two halves
+    uint32_t *pend = reinterpret_cast<uint32_t *>(wbase + sizeof(FastWarpSmem));  // (hour << 6) | (unit << 1) | (delta > 0)
+    uint32_t *evl = pend + (two_halves ? FAST_PEND_CAP : 0);                      // [halves][ev_cap]: (hour in segment << 6) | (unit << 1) | sign
     const int seg_slots = a.seg_words * 32;
-    const int half_words32 = kPacked ? seg_slots / 2 : seg_slots;                // 32-bit words per ring half
-    const int ring_words = (2 * a.seg_words + 3) & ~3;
-    int32_t *wsum = tl + 2 * half_words32;                                      // per 32-hour word: sum of deltas
+    const int ring_words = (halves * a.seg_words + 3) & ~3;
+    int32_t *wsum = reinterpret_cast<int32_t *>(evl + (size_t)halves * ev_cap);  // per 32-hour word: sum of deltas
     int32_t *wneg = wsum + ring_words;                                          //                   sum of negative deltas
 
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
@@ -120,7 +107,6 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
-    for (int i = lane; i < 2 * half_words32; i += 32) tl[i] = 0;
     for (int i = lane; i < ring_words; i += 32) { wsum[i] = 0; wneg[i] = 0; }
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
@@ -146,6 +132,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         int pend_cnt = 0;
         int capacity = 0;
         int ring = 0;                 // ring half that holds the current segment
+        int ev_cnt0 = 0, ev_cnt1 = 0; // events in the list of ring half 0 / 1 (warp-uniform)
         // MATLAB discretisation: a unit that fails after d whole hours is DOWN from hour d+1 (seq_mcsampling.m:63)
         ws->t_run[lane] = kDisc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
         __syncwarp();
@@ -163,18 +150,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 const int abs2 = min(chain_end_h, abs1 + min(seg_slots, a.H - nxt_h0));
                 const unsigned long long seg_end_t = (unsigned long long)abs1 << PSRA_TICK_SHIFT;
                 const unsigned long long nxt_end_t = (unsigned long long)abs2 << PSRA_TICK_SHIFT;
-                // ring geometry: the current segment starts at slot ring*S, the next one at the other half's
-                // base; an event `rel` hours after abs0 lives at slot ring*S + rel (+ pad when it belongs to
-                // the next segment and the current one is shorter than S), modulo 2S
+                // ring geometry: an event `rel` hours after abs0 belongs to the current half when rel < len_cur,
+                // otherwise to the other half (which holds the next segment from its hour 0)
                 const uint32_t len_cur = (uint32_t)(seg_h1 - seg_h0);
                 const uint32_t ring_len = (uint32_t)(abs2 - abs0);
-                const int pad = seg_slots - (int)len_cur;
-                const int ring_base = ring * seg_slots;
-                const int wbase_cur = ring * a.seg_words;                     // word index of the current half
-                auto ring_slot = [&](uint32_t rel) -> int {
-                    int idx = ring_base + (int)rel + (rel >= len_cur ? pad : 0);
-                    return idx >= 2 * seg_slots ? idx - 2 * seg_slots : idx;
-                };
+                const int wbase_cur = ring * a.seg_words, wbase_nxt = (ring ^ 1) * a.seg_words;
+                uint32_t *ev_cur = evl + (size_t)ring * ev_cap, *ev_nxt = evl + (size_t)(ring ^ 1) * ev_cap;
+                int cnt_cur = ring ? ev_cnt1 : ev_cnt0, cnt_nxt = ring ? ev_cnt0 : ev_cnt1;
 
                 // ---- far-future events that now fall into the next segment's half
                 if (pend_cnt) {
@@ -182,20 +164,23 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     for (int base = 0; base < pend_cnt; base += 32) {
                         const int i = base + lane;
                         const bool v = i < pend_cnt;
-                        const uint32_t e = v ? ws->pend[i] : 0u;
+                        const uint32_t e = v ? pend[i] : 0u;
                         const int hs = (int)(e >> 6);
                         const bool take = v && hs < abs2;
-                        if (take) {
+                        const uint32_t tm = __ballot_sync(0xffffffffu, take);
+                        if (take) {                       // pending events are beyond abs1: next half
                             const int c = s_cap[(e >> 1) & 31];
-                            const int slot = ring_slot((uint32_t)(hs - abs0));
-                            tl_add<kPacked>(tl, slot, (e & 1u) ? c : -c);
-                            atomicAdd(&wsum[slot >> 5], (e & 1u) ? c : -c);
-                            if (!(e & 1u)) atomicAdd(&wneg[slot >> 5], -c);
+                            const uint32_t hseg = (uint32_t)(hs - abs1);
+                            atomicAdd(&wsum[wbase_nxt + (hseg >> 5)], (e & 1u) ? c : -c);
+                            if (!(e & 1u)) atomicAdd(&wneg[wbase_nxt + (hseg >> 5)], -c);
+                            const int pos = cnt_nxt + __popc(tm & lt_mask);
+                            if (pos < ev_cap) ev_nxt[pos] = (hseg << 6) | (e & 63u);
                         }
+                        cnt_nxt += __popc(tm);
                         const bool keep = v && !take;
                         const uint32_t km = __ballot_sync(0xffffffffu, keep);
                         __syncwarp();
-                        if (keep) ws->pend[outc + __popc(km & lt_mask)] = e;
+                        if (keep) pend[outc + __popc(km & lt_mask)] = e;
                         outc += __popc(km);
                     }
                     pend_cnt = outc;
@@ -241,7 +226,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     n_waves++;
 #pragma unroll
                     for (int k = 0; k < FAST_NB_MAX; k++)
-                        if (k < n_u) ws->jobmap[off + k] = (unsigned char)lane;
+                        if (k < n_u) ws->jobmap[off + k] = (unsigned char)lane;   // off + n_u <= 32
                     __syncwarp();
                     {
                         const bool act = lane < J;               // lane = job
@@ -287,11 +272,30 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             const uint32_t rel = hs - (uint32_t)abs0;          // >= 0: events are never generated backwards
                             const int delta = (q & 1) ? -delta_a : delta_a;
                             const bool in_ring = valid && rel < ring_len;      // ring_len stops at the chain end
+                            const bool in_cur = in_ring && rel < len_cur;
+                            const bool in_nxt = in_ring && !in_cur;
+                            const uint32_t hseg = in_cur ? rel : rel - len_cur;  // hour within its segment
                             if (in_ring) {
-                                const int slot = ring_slot(rel);
-                                tl_add<kPacked>(tl, slot, delta);
-                                atomicAdd(&wsum[slot >> 5], delta);
-                                if (delta < 0) atomicAdd(&wneg[slot >> 5], delta);
+                                const int w = (in_cur ? wbase_cur : wbase_nxt) + (int)(hseg >> 5);
+                                atomicAdd(&wsum[w], delta);
+                                if (delta < 0) atomicAdd(&wneg[w], delta);
+                            }
+                            const uint32_t ent = (hseg << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
+                            const uint32_t mc = __ballot_sync(0xffffffffu, in_cur);
+                            if (in_cur) {
+                                const int pos = cnt_cur + __popc(mc & lt_mask);
+                                if (pos < ev_cap) ev_cur[pos] = ent;
+                            }
+                            cnt_cur += __popc(mc);
+                            if (two_halves) {
+                                const uint32_t mn = __ballot_sync(0xffffffffu, in_nxt);
+                                if (mn) {
+                                    if (in_nxt) {
+                                        const int pos = cnt_nxt + __popc(mn & lt_mask);
+                                        if (pos < ev_cap) ev_nxt[pos] = ent;
+                                    }
+                                    cnt_nxt += __popc(mn);
+                                }
                             }
                             const bool inhor = valid && hs < (uint32_t)chain_end_h;
                             const bool pnd = inhor && !in_ring;
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             if (pm) {
                                 const int pos = pend_cnt + __popc(pm & lt_mask);
                                 if (pnd && pos < FAST_PEND_CAP)
-                                    ws->pend[pos] = (hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
+                                    pend[pos] = (hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
                                 pend_cnt += __popc(pm);
                             }
                             n_events += inhor ? 1u : 0u;
@@ -316,7 +320,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         init_wave = false;
                     }
                 }
-                pend_max = max(pend_max, (unsigned int)pend_cnt);
+                pend_max = max(pend_max, (unsigned int)max(cnt_cur, cnt_nxt));
+                if (cnt_cur > ev_cap || cnt_nxt > ev_cap) {      // reported as PSRA_E_OVERFLOW: choose a shorter segment
+                    if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 3ull);
+                    cnt_cur = min(cnt_cur, ev_cap); cnt_nxt = min(cnt_nxt, ev_cap);
+                }
                 if (pend_cnt > FAST_PEND_CAP) {                  // reported as PSRA_E_OVERFLOW (never seen in practice)
                     if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 2ull);
                     pend_cnt = FAST_PEND_CAP;
@@ -340,14 +348,37 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 const bool flagged = (lmin != INT_MAX) && (cs_lane + lmin < 0);
                 uint32_t fm = __ballot_sync(0xffffffffu, flagged);
                 n_flag += __popc(fm);
-                while (fm) {                                     // rare: hour-by-hour, lane = hour
+                while (fm) {                                     // rare: a run that may contain loss of load
                     const int src = __ffs(fm) - 1;
                     fm &= fm - 1;
-                    int c_in = __shfl_sync(0xffffffffu, cs_lane, src);
-                    for (int k = 0; k < wpl; k++) {
+                    const int c_run = __shfl_sync(0xffffffffu, cs_lane, src);
+                    // lane k < wpl looks at word k of the run: capacity entering it and the per-word flag
+                    int c_word = c_run;
+                    bool wflag = false;
+                    {
+                        const int wq = src * wpl + lane;
+                        if (lane < wpl && wq < nwords) {
+                            for (int j = 0; j < lane; j++) c_word += wsum[wbase_cur + src * wpl + j];
+                            wflag = c_word + wneg[wbase_cur + wq] < s_lmax[seg * a.seg_words + wq];
+                        }
+                    }
+                    uint32_t wm = __ballot_sync(0xffffffffu, wflag);
+                    while (wm) {                                 // resolve the word hour by hour, lane = hour
+                        const int k = __ffs(wm) - 1;
+                        wm &= wm - 1;
                         const int wq = src * wpl + k;
-                        if (wq >= nwords) break;
-                        const int c = c_in + warp_incl_scan(tl_get<kPacked>(tl, ring_base + wq * 32 + lane), lane);
+                        const int c_in = __shfl_sync(0xffffffffu, c_word, k);
+                        ws->hour_delta[lane] = 0;
+                        __syncwarp();
+                        for (int i = lane; i < cnt_cur; i += 32) {       // gather the word's events
+                            const uint32_t e = ev_cur[i];
+                            if ((int)(e >> 11) == wq) {
+                                const int c = s_cap[(e >> 1) & 31];
+                                atomicAdd(&ws->hour_delta[(e >> 6) & 31], (e & 1u) ? c : -c);
+                            }
+                        }
+                        __syncwarp();
+                        const int c = c_in + warp_incl_scan(ws->hour_delta[lane], lane);
                         const int hy0 = seg_h0 + wq * 32;
                         const int L = load_at(hy0 + lane);
                         const bool lol = c < L;                  // PSA.jl:253 strict
@@ -361,18 +392,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                 if (a.fail) atomicAdd(&a.fail[hy0 + lane], 1u);
                             }
                         }
-                        c_in = __shfl_sync(0xffffffffu, c, 31);
+                        __syncwarp();
                     }
                 }
                 capacity += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
-                {   // clear the evaluated half with 16-byte stores
-                    int4 *t4 = reinterpret_cast<int4 *>(tl + ring * half_words32);
-                    const int n4 = half_words32 / 4;
-                    for (int i = lane; i < n4; i += 32) t4[i] = make_int4(0, 0, 0, 0);
-                    for (int i = lane; i < a.seg_words; i += 32) { wsum[wbase_cur + i] = 0; wneg[wbase_cur + i] = 0; }
-                }
+                // clear the evaluated half: word sums to zero, event list empty
+                for (int i = lane; i < nwords; i += 32) { wsum[wbase_cur + i] = 0; wneg[wbase_cur + i] = 0; }
+                if (ring) { ev_cnt1 = 0; ev_cnt0 = cnt_nxt; } else { ev_cnt0 = 0; ev_cnt1 = cnt_nxt; }
                 __syncwarp();
+                if (!two_halves) ring ^= 1;                      // single half: undo the toggle of the loop header
             }
 
             // ---- per-year indices
@@ -418,22 +447,21 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     }
 }
 
-static const void *fast_kernel_ptr(bool packed, bool disc)
+static const void *fast_kernel_ptr(bool disc)
 {
-    if (packed) return disc ? (const void *)seq_fast_kernel<true, true> : (const void *)seq_fast_kernel<true, false>;
-    return disc ? (const void *)seq_fast_kernel<false, true> : (const void *)seq_fast_kernel<false, false>;
+    return disc ? (const void *)seq_fast_kernel<true> : (const void *)seq_fast_kernel<false>;
 }
 
-cudaError_t seq_fast_prepare(bool packed, bool disc, size_t smem, int threads, int *blocks_per_sm)
+cudaError_t seq_fast_prepare(bool disc, size_t smem, int threads, int *blocks_per_sm)
 {
-    const void *k = fast_kernel_ptr(packed, disc);
+    const void *k = fast_kernel_ptr(disc);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem);
 }
 
-void seq_fast_launch(bool packed, const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
+void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
 {
     void *args[] = {(void *)&a};
-    cudaLaunchKernel(fast_kernel_ptr(packed, a.disc != 0), dim3(grid), dim3(threads), args, smem, stream);
+    cudaLaunchKernel(fast_kernel_ptr(a.disc != 0), dim3(grid), dim3(threads), args, smem, stream);
 }

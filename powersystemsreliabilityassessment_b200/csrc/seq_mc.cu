@@ -299,7 +299,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (nyears == 0) return PSRA_OK;
 
     const bool one_unit = h->U <= 32;
-    const bool packed = h->total_cap <= 32767, load16 = h->max_load <= 32767;
+    const bool load16 = h->max_load <= 32767;
     const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0];
     const bool team = !injected && !one_unit && h->U <= seq_team_max_units() && (long long)ypc * h->H < (1ll << 20) &&
                       !h->cfg.reserved[0];
@@ -319,18 +319,28 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : 1760;
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
+    // seq_fast.cu: event lists sized 2x the expected transitions of a segment (+ initial draws + slack);
+    // by default the whole year is one segment unless that list would exceed 2048 entries
+    auto ev_cap_for = [&](int sw) -> int {
+        const double e = h->events_per_hour * sw * 32.0 + h->U;
+        const long long c = (long long)(2.0 * e) + 128;
+        return (int)((c + 31) & ~31ll);
+    };
     if (one_unit) {
-        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : (fast ? 1760 : 1120);
-        seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
+        if (h->cfg.seg_hours > 0) seg_words = std::max(1, std::min(h->Wd, (h->cfg.seg_hours + 31) / 32));
+        else if (fast) { while (seg_words > 1 && ev_cap_for(seg_words) > 2048) seg_words = (seg_words + 1) / 2; }
+        else seg_words = std::max(1, std::min(h->Wd, (1120 + 31) / 32));
     }
     a.seg_words = seg_words;
     a.nseg = (h->Wd + seg_words - 1) / seg_words;
     a.persist = (!one_unit && !team && (ypc > 1 || a.nseg > 1)) ? 1 : 0;
     a.pend_cap = seq_team_pend_cap(h->U);
+    a.two_halves = (a.nseg > 1 || ypc > 1) ? 1 : 0;
+    a.ev_cap = ev_cap_for(seg_words);
     int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 24 : 16);
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
-        if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, packed, load16);
+        if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16);
         if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words);
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
@@ -392,7 +402,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     else          kern = one_unit ? seq_mc_kernel<false, true> : seq_mc_kernel<false, false>;
     int bps = 0;
     if (fast) {
-        PSRA_CUDA(h, seq_fast_prepare(packed, a.disc != 0, smem, wpb * 32, &bps));
+        PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, smem, wpb * 32, &bps));
     } else if (team) {
         PSRA_CUDA(h, seq_team_prepare(smem, &bps));
     } else {
@@ -406,7 +416,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (grid > need) grid = need;
 
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    if (fast) seq_fast_launch(packed, a, (unsigned)grid, wpb * 32, smem, h->stream);
+    if (fast) seq_fast_launch(a, (unsigned)grid, wpb * 32, smem, h->stream);
     else if (team) seq_team_launch(a, (unsigned)grid, smem, h->stream);
     else kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
     PSRA_CUDA(h, cudaGetLastError());
@@ -435,6 +445,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     summary->events = acc[ACC_EVENTS];
     memcpy(h->last_acc, acc, sizeof(acc));
     if (want_vec && out->keep_on_device) h->kept_n = nyears;
+    if (acc[ACC_OVERFLOW] == 3ull)
+        return psra_fail(h, PSRA_E_OVERFLOW, "event list of a timeline segment overflowed (%d entries): set a shorter psra_config.seg_hours", a.ev_cap);
     if (acc[ACC_OVERFLOW] == 2ull)
         return psra_fail(h, PSRA_E_OVERFLOW, "internal error: pending-event list overflow in the sequential kernel");
     if (acc[ACC_OVERFLOW])
