@@ -204,11 +204,17 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
                         total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
                     };
-                    const int n_m = is_short ? want : 0;             // mandatory: units short of this segment
+                    int n_m = is_short ? want : 0;                   // mandatory: units short of this segment
                     int off_m, J1;
                     count_scan(n_m, off_m, J1);
+                    if (J1 < 32 && !init_wave) {       // spare lanes: one more block of slack for the short units
+                        const int n_x = is_short ? min(FAST_NB_MAX, want + 1) : 0;
+                        int off_x, Jx;
+                        count_scan(n_x, off_x, Jx);
+                        if (Jx <= 32) { n_m = n_x; off_m = off_x; J1 = Jx; }
+                    }
                     int n_u, off, J;
-                    if (J1 >= 32 || init_wave) {       // truncate; the remaining demand is served by the next wave
+                    if (J1 >= 32 || init_wave || !two_halves) {     // truncate; the remaining demand is served by the next wave
                         off = off_m;
                         n_u = max(0, min(n_m, 32 - off));
                         J = min(J1, 32);
