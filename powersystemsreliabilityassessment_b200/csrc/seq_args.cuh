@@ -22,7 +22,7 @@ struct SeqArgs {
 // seq_fast.cu
 size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_cap, bool two_halves, bool load16);
 int seq_fast_max_threads();
-cudaError_t seq_fast_prepare(bool disc, size_t smem, int threads, int *blocks_per_sm);
+cudaError_t seq_fast_prepare(bool disc, bool two, size_t smem, int threads, int *blocks_per_sm);
 void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);
 
 // seq_team.cu

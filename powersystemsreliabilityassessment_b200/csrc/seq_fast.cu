@@ -69,7 +69,7 @@ size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_ca
 
 int seq_fast_max_threads() { return FAST_MAX_THREADS; }
 
-template <bool kDisc>
+template <bool kDisc, bool kTwo>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     float *s_mup = reinterpret_cast<float *>(s_cap + 32);
     float *s_mdn = s_mup + 32;
     uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_mdn + 32);
-    const bool two_halves = a.two_halves != 0;
+    constexpr bool two_halves = kTwo;     // the ring needs its second half (several segments per year or multi-year chains)
     const int halves = two_halves ? 2 : 1;
     const int ev_cap = a.ev_cap;
     unsigned char *wbase = smem_raw + fast_block_bytes(a.Wd, load16) + (size_t)warp * fast_warp_bytes(a.seg_words, ev_cap, two_halves);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 int cnt_cur = ring ? ev_cnt1 : ev_cnt0, cnt_nxt = ring ? ev_cnt0 : ev_cnt1;
 
                 // ---- far-future events that now fall into the next segment's half
-                if (pend_cnt) {
+                if (two_halves && pend_cnt) {
                     int outc = 0;
                     for (int base = 0; base < pend_cnt; base += 32) {
                         const int i = base + lane;
@@ -304,13 +304,15 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                 }
                             }
                             const bool inhor = valid && hs < (uint32_t)chain_end_h;
-                            const bool pnd = inhor && !in_ring;
-                            const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
-                            if (pm) {
-                                const int pos = pend_cnt + __popc(pm & lt_mask);
-                                if (pnd && pos < FAST_PEND_CAP)
-                                    pend[pos] = (hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
-                                pend_cnt += __popc(pm);
+                            if (two_halves) {                              // events beyond the ring (a single segment has none)
+                                const bool pnd = inhor && !in_ring;
+                                const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
+                                if (pm) {
+                                    const int pos = pend_cnt + __popc(pm & lt_mask);
+                                    if (pnd && pos < FAST_PEND_CAP)
+                                        pend[pos] = (hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
+                                    pend_cnt += __popc(pm);
+                                }
                             }
                             n_events += inhor ? 1u : 0u;
                         }
@@ -453,14 +455,15 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     }
 }
 
-static const void *fast_kernel_ptr(bool disc)
+static const void *fast_kernel_ptr(bool disc, bool two)
 {
-    return disc ? (const void *)seq_fast_kernel<true> : (const void *)seq_fast_kernel<false>;
+    if (two) return disc ? (const void *)seq_fast_kernel<true, true> : (const void *)seq_fast_kernel<false, true>;
+    return disc ? (const void *)seq_fast_kernel<true, false> : (const void *)seq_fast_kernel<false, false>;
 }
 
-cudaError_t seq_fast_prepare(bool disc, size_t smem, int threads, int *blocks_per_sm)
+cudaError_t seq_fast_prepare(bool disc, bool two, size_t smem, int threads, int *blocks_per_sm)
 {
-    const void *k = fast_kernel_ptr(disc);
+    const void *k = fast_kernel_ptr(disc, two);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem);
@@ -469,5 +472,5 @@ cudaError_t seq_fast_prepare(bool disc, size_t smem, int threads, int *blocks_pe
 void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
 {
     void *args[] = {(void *)&a};
-    cudaLaunchKernel(fast_kernel_ptr(a.disc != 0), dim3(grid), dim3(threads), args, smem, stream);
+    cudaLaunchKernel(fast_kernel_ptr(a.disc != 0, a.two_halves != 0), dim3(grid), dim3(threads), args, smem, stream);
 }

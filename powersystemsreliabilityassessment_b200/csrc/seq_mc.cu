@@ -402,7 +402,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     else          kern = one_unit ? seq_mc_kernel<false, true> : seq_mc_kernel<false, false>;
     int bps = 0;
     if (fast) {
-        PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, smem, wpb * 32, &bps));
+        PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, a.two_halves != 0, smem, wpb * 32, &bps));
     } else if (team) {
         PSRA_CUDA(h, seq_team_prepare(smem, &bps));
     } else {
