@@ -25,7 +25,7 @@
 //    sums gives the capacity entering each run; conservative flag
 //    capacity + (negative deltas of the word) < max load of the word (table staged in shared
 //    memory).  Flagged words (about 3 per RTS-79 year) are resolved hour by hour, lane = hour:
-//    the word's deltas are gathered from the event list, a shuffle scan turns them into the 32
+//    the word's deltas are gathered by walking the word's linked event list, a shuffle scan turns them into the 32
 //    capacities, which are compared with the load curve staged once per block in shared memory;
 //    __ballot_sync/__popc give LOL hours and deficit entries, per-lane int64 accumulators the ENS.
 #include <limits.h>
@@ -41,7 +41,6 @@
 
 struct FastWarpSmem {                  // per-warp scratch that precedes the event lists
     unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit
-    int32_t hour_delta[32];            // hour-resolved deltas of the word being resolved
     unsigned char jobmap[32];
 };
 
@@ -51,7 +50,7 @@ __host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, boo
     const int halves = two_halves ? 2 : 1;
     size_t b = sizeof(FastWarpSmem) + (two_halves ? sizeof(uint32_t) * FAST_PEND_CAP : 0) +
                sizeof(uint32_t) * (size_t)halves * ev_cap +                          // event lists
-               2 * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);        // word sums + negative sums
+               3 * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);        // word sums, negative sums, list heads
     return (b + 15) & ~(size_t)15;
 }
 
@@ -90,11 +89,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     unsigned char *wbase = smem_raw + fast_block_bytes(a.Wd, load16) + (size_t)warp * fast_warp_bytes(a.seg_words, ev_cap, two_halves);
     FastWarpSmem *ws = reinterpret_cast<FastWarpSmem *>(wbase);
     uint32_t *pend = reinterpret_cast<uint32_t *>(wbase + sizeof(FastWarpSmem));  // (hour << 6) | (unit << 1) | (delta > 0)
-    uint32_t *evl = pend + (two_halves ? FAST_PEND_CAP : 0);                      // [halves][ev_cap]: (hour in segment << 6) | (unit << 1) | sign
+    uint32_t *evl = pend + (two_halves ? FAST_PEND_CAP : 0);                      // [halves][ev_cap]: (next << 20) | (hour in segment << 6) | (unit << 1) | sign; the events of a
+                                                                                  // 32-hour word form a linked list (next = 1 + index, 0 = end)
     const int seg_slots = a.seg_words * 32;
     const int ring_words = (halves * a.seg_words + 3) & ~3;
     int32_t *wsum = reinterpret_cast<int32_t *>(evl + (size_t)halves * ev_cap);  // per 32-hour word: sum of deltas
     int32_t *wneg = wsum + ring_words;                                          //                   sum of negative deltas
+    uint32_t *whead = reinterpret_cast<uint32_t *>(wneg + ring_words);          //                   1 + index of its newest event (0 = none)
 
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
         if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
-    for (int i = lane; i < ring_words; i += 32) { wsum[i] = 0; wneg[i] = 0; }
+    for (int i = lane; i < ring_words; i += 32) { wsum[i] = 0; wneg[i] = 0; whead[i] = 0u; }
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
@@ -174,7 +175,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             atomicAdd(&wsum[wbase_nxt + (hseg >> 5)], (e & 1u) ? c : -c);
                             if (!(e & 1u)) atomicAdd(&wneg[wbase_nxt + (hseg >> 5)], -c);
                             const int pos = cnt_nxt + __popc(tm & lt_mask);
-                            if (pos < ev_cap) ev_nxt[pos] = (hseg << 6) | (e & 63u);
+                            if (pos < ev_cap) {
+                                const uint32_t nx = atomicExch(&whead[wbase_nxt + (hseg >> 5)], (uint32_t)(pos + 1));
+                                ev_nxt[pos] = (nx << 20) | (hseg << 6) | (e & 63u);
+                            }
                         }
                         cnt_nxt += __popc(tm);
                         const bool keep = v && !take;
@@ -290,7 +294,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             const uint32_t mc = __ballot_sync(0xffffffffu, in_cur);
                             if (in_cur) {
                                 const int pos = cnt_cur + __popc(mc & lt_mask);
-                                if (pos < ev_cap) ev_cur[pos] = ent;
+                                if (pos < ev_cap) {
+                                    const uint32_t nx = atomicExch(&whead[wbase_cur + (int)(hseg >> 5)], (uint32_t)(pos + 1));
+                                    ev_cur[pos] = (nx << 20) | ent;
+                                }
                             }
                             cnt_cur += __popc(mc);
                             if (two_halves) {
@@ -298,7 +305,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                 if (mn) {
                                     if (in_nxt) {
                                         const int pos = cnt_nxt + __popc(mn & lt_mask);
-                                        if (pos < ev_cap) ev_nxt[pos] = ent;
+                                        if (pos < ev_cap) {
+                                            const uint32_t nx = atomicExch(&whead[wbase_nxt + (int)(hseg >> 5)], (uint32_t)(pos + 1));
+                                            ev_nxt[pos] = (nx << 20) | ent;
+                                        }
                                     }
                                     cnt_nxt += __popc(mn);
                                 }
@@ -376,17 +386,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         wm &= wm - 1;
                         const int wq = src * wpl + k;
                         const int c_in = __shfl_sync(0xffffffffu, c_word, k);
-                        ws->hour_delta[lane] = 0;
-                        __syncwarp();
-                        for (int i = lane; i < cnt_cur; i += 32) {       // gather the word's events
-                            const uint32_t e = ev_cur[i];
-                            if ((int)(e >> 11) == wq) {
+                        int d = 0;                               // delta of hour `lane` of the word: walk its event list
+                        for (uint32_t i = whead[wbase_cur + wq]; i; ) {
+                            const uint32_t e = ev_cur[i - 1];
+                            if (((e >> 6) & 31u) == (uint32_t)lane) {
                                 const int c = s_cap[(e >> 1) & 31];
-                                atomicAdd(&ws->hour_delta[(e >> 6) & 31], (e & 1u) ? c : -c);
+                                d += (e & 1u) ? c : -c;
                             }
+                            i = e >> 20;
                         }
-                        __syncwarp();
-                        const int c = c_in + warp_incl_scan(ws->hour_delta[lane], lane);
+                        const int c = c_in + warp_incl_scan(d, lane);
                         const int hy0 = seg_h0 + wq * 32;
                         const int L = load_at(hy0 + lane);
                         const bool lol = c < L;                  // PSA.jl:253 strict
@@ -400,13 +409,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                 if (a.fail) atomicAdd(&a.fail[hy0 + lane], 1u);
                             }
                         }
-                        __syncwarp();
                     }
                 }
                 capacity += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
                 // clear the evaluated half: word sums to zero, event list empty
-                for (int i = lane; i < nwords; i += 32) { wsum[wbase_cur + i] = 0; wneg[wbase_cur + i] = 0; }
+                for (int i = lane; i < nwords; i += 32) { wsum[wbase_cur + i] = 0; wneg[wbase_cur + i] = 0; whead[wbase_cur + i] = 0u; }
                 if (ring) { ev_cnt1 = 0; ev_cnt0 = cnt_nxt; } else { ev_cnt0 = 0; ev_cnt1 = cnt_nxt; }
                 __syncwarp();
                 if (!two_halves) ring ^= 1;                      // single half: undo the toggle of the loop header

@@ -328,8 +328,9 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     };
     if (one_unit) {
         if (h->cfg.seg_hours > 0) seg_words = std::max(1, std::min(h->Wd, (h->cfg.seg_hours + 31) / 32));
-        else if (fast) { while (seg_words > 1 && ev_cap_for(seg_words) > 2048) seg_words = (seg_words + 1) / 2; }
-        else seg_words = std::max(1, std::min(h->Wd, (1120 + 31) / 32));
+        else if (!fast) seg_words = std::max(1, std::min(h->Wd, (1120 + 31) / 32));
+        // event entries hold an 11-bit list link and a 14-bit hour: bound the list and the segment length
+        if (fast) { while (seg_words > 1 && (ev_cap_for(seg_words) > 2016 || seg_words > 512)) seg_words = (seg_words + 1) / 2; }
     }
     a.seg_words = seg_words;
     a.nseg = (h->Wd + seg_words - 1) / seg_words;
@@ -337,6 +338,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     a.pend_cap = seq_team_pend_cap(h->U);
     a.two_halves = (a.nseg > 1 || ypc > 1) ? 1 : 0;
     a.ev_cap = ev_cap_for(seg_words);
+    if (fast && a.ev_cap > 2016)
+        return psra_fail(h, PSRA_E_INVALID, "unit transition rate too high for the sampler kernel (%d events per 32-hour word)", a.ev_cap);
     int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 24 : 16);
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
