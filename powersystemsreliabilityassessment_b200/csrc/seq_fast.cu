@@ -4,7 +4,7 @@
 // GeneratingAdequacy/PowerSystemAdequacy.jl:214-269; indices per Montecarlo_seq/seqMain.m:160-176,
 // Montecarlo_seq/calnlc.m:22-34), reorganised so that lanes are busy:
 //
-//  * Time is kept in integer ticks of 2^-24 h.  A sampler duration is D = max(1, RN(mean*2^24*E))
+//  * Time is kept in integer ticks of 2^-24 h.  A sampler duration is D = RN(max(mean*2^24*E, 1))
 //    ticks, so every residual of the reference's `ttf -= 1.0` / `ttf += D` recurrence
 //    (PSA.jl:239-246) is an exact FP64 number and the event times are plain prefix sums
 //    T_k = D_0 + ... + D_k; event k toggles the unit in hour ceil(T_k / 2^24).
@@ -15,8 +15,9 @@
 //    Lane utilisation no longer depends on the 6x spread of the units' event rates.
 //  * The warp's shared-memory timeline is a ring of two segments kept at two resolutions: per
 //    32-hour word the sum of the integer MW deltas and the sum of the negative deltas (atomicAdd at
-//    scatter time), and a compact event list (hour, unit, sign) per ring half.  Hour resolution is
-//    rebuilt from the event list only for the few words that can contain loss of load.  The rare
+//    scatter time), and a compact event list (hour, unit, sign) per ring half in which the events
+//    of one word are linked (atomicExch on the word's list head).  Hour resolution is rebuilt from
+//    that list only for the few words that can contain loss of load.  The rare
 //    events beyond the ring wait in a small pending list.  A wave is one round of <= 32 jobs:
 //    blocks for the units that are short of the current segment first, the spare lanes
 //    pre-generate blocks towards the end of the next segment.  For RTS-79 the whole year is one
@@ -25,8 +26,8 @@
 //    sums gives the capacity entering each run; conservative flag
 //    capacity + (negative deltas of the word) < max load of the word (table staged in shared
 //    memory).  Flagged words (about 3 per RTS-79 year) are resolved hour by hour, lane = hour:
-//    the word's deltas are gathered by walking the word's linked event list, a shuffle scan turns them into the 32
-//    capacities, which are compared with the load curve staged once per block in shared memory;
+//    the word's deltas are gathered by walking its linked event list, a shuffle scan turns them
+//    into the 32 capacities, which are compared with the load curve staged once per block in shared memory;
 //    __ballot_sync/__popc give LOL hours and deficit entries, per-lane int64 accumulators the ENS.
 #include <limits.h>
 
