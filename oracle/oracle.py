@@ -90,6 +90,10 @@ def lib():
         L.oracle_detailed_mc_philox.restype = C.c_int
         L.oracle_detailed_mc_philox.argtypes = [C.c_int, _dp, _u32p, _i32p, _i32p, _dp, C.c_int, _dp, C.c_double,
                                                 C.c_uint64, C.c_int64, C.c_int, _dp, _dp]
+        L.oracle_expected_generation.restype = C.c_double
+        L.oracle_expected_generation.argtypes = [_dp, C.c_int, C.c_double, C.c_double, _dp, C.c_int, C.c_double]
+        L.oracle_lfu_hourly_risk.restype = None
+        L.oracle_lfu_hourly_risk.argtypes = [_dp, C.c_int, C.c_double, _dp, C.c_int, C.c_double, _dp]
         L.oracle_load_factors.restype = None
         L.oracle_load_factors.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
     return _lib
@@ -346,3 +350,17 @@ def schedule_maintenance(capacity, maintenance_weeks, weekly_peaks):
         start[i] = best
         avail[best - 1:best - 1 + mw[i]] -= cap[i]
     return start
+
+
+def expected_generation(probs, step, unit_cap, loads, lfu_sigma):
+    """calculate_expected_generation, generating_adequacy_comprehensive.jl:118-142 (literal loops)."""
+    p = _d(probs); ld = _d(loads)
+    return float(lib().oracle_expected_generation(p, len(p), float(step), float(unit_cap), ld, len(ld), float(lfu_sigma)))
+
+
+def lfu_hourly_risk(probs, step, loads, lfu_mw):
+    """tail_risk.jl:124-136 hourly risk with the 7-step LFU table (literal loops)."""
+    p = _d(probs); ld = _d(loads)
+    out = np.zeros(len(ld))
+    lib().oracle_lfu_hourly_risk(p, len(p), float(step), ld, len(ld), float(lfu_mw), out)
+    return out

@@ -774,3 +774,52 @@ int oracle_seq_matlab_philox(int U, const double *cap, const float *mttf_f, cons
     free(down);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------
+ * 11. Analytical side of tail_risk.jl / generating_adequacy_comprehensive.jl (host-side planning):
+ *     calculate_expected_generation (comprehensive.jl:118-142) and the hourly LFU risk loop
+ *     (tail_risk.jl:124-136 == comprehensive.jl:251-265), literal loops over the 7-step LFU table
+ *     (comprehensive.jl:76-80).  `installed` / `cap_rest` are the LAST GRID STATE of the table.
+ * -------------------------------------------------------------------------------- */
+static const double LFU_Z[7] = { -3.0, -2.0, -1.0, 0.0, 1.0, 2.0, 3.0 };
+static const double LFU_P[7] = { 0.006, 0.061, 0.242, 0.382, 0.242, 0.061, 0.006 };
+
+double oracle_expected_generation(const double *probs, int n, double step, double unit_cap,
+                                  const double *loads, int H, double lfu_sigma)
+{
+    double total_energy = 0.0;
+    double cap_rest = (double)(n - 1) * step;
+    for (int h = 0; h < H; h++) {
+        double hourly_e = 0.0;
+        for (int k = 0; k < 7; k++) {
+            double actual_load = loads[h] + (LFU_Z[k] * lfu_sigma);
+            double reserve_thresh = cap_rest - actual_load;
+            double term_e = 0.0;
+            for (int i = 0; i < n; i++) {
+                double outage = (double)i * step;
+                if (outage > reserve_thresh) {
+                    double deficit = outage - reserve_thresh;
+                    term_e += (unit_cap < deficit ? unit_cap : deficit) * probs[i];
+                }
+            }
+            hourly_e += term_e * LFU_P[k];
+        }
+        total_energy += hourly_e;
+    }
+    return total_energy;
+}
+
+void oracle_lfu_hourly_risk(const double *probs, int n, double step, const double *loads, int H,
+                            double lfu_mw, double *risk)
+{
+    double installed = (double)(n - 1) * step;
+    for (int h = 0; h < H; h++) {
+        double risk_h = 0.0;
+        for (int k = 0; k < 7; k++) {
+            double res = installed - (loads[h] + LFU_Z[k] * lfu_mw);
+            for (int i = 0; i < n; i++)
+                if ((double)i * step > res) risk_h += probs[i] * LFU_P[k];
+        }
+        risk[h] = risk_h;
+    }
+}

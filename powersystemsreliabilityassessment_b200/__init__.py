@@ -7,7 +7,8 @@ include/psra_b200.h); this package is the thin host mirror of the reference's Ju
 from . import rts79  # noqa: F401
 from ._lib import DISC_MATLAB, INIT_ALL_UP, INIT_STATIONARY, LIB_PATH  # noqa: F401
 from .api import (DetailedGenerator, SystemParams, run_detailed_mc, run_monte_carlo, schedule_maintenance,  # noqa: F401
-                  run_nonseq_until_beta, run_sequential_until_cov,
+                  run_nonseq_until_beta, run_sequential_until_cov, run_detailed_analytical, update_elu,
+                  calculate_expected_generation, get_lfu_distribution,
                   Engine, Generator, LoadModel, PsraError, ReliabilityResult, SequentialIndices,  # noqa: F401
                   compare_results, evaluate_risk, indices_from_raw, run_analytical,
                   run_non_sequential_mc, run_sequential_mc)

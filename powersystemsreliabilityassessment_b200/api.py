@@ -605,3 +605,87 @@ def run_nonseq_until_beta(engine: Engine, beta_threshold: float = 0.0017, batch:
     out = dict(samples=N, plc=tot["samples_with_loss"] / N, lole=tot["sum_lol_hours"] / N,
                edns=tot["sum_ens_fp"] / N / engine.fp_scale, beta=history[-1], raw=tot)
     return out, np.array(history)
+
+
+# ------------------------------ analytical side of tail_risk.jl (host-side planning; COPT tables on the GPU)
+LFU_DISTRIBUTION = ((-3.0, 0.006), (-2.0, 0.061), (-1.0, 0.242), (0.0, 0.382), (1.0, 0.242), (2.0, 0.061), (3.0, 0.006))
+
+
+def get_lfu_distribution():
+    """7-step normal approximation, generating_adequacy_comprehensive.jl:76-80."""
+    return list(LFU_DISTRIBUTION)
+
+
+def _tail_weights(probs, step, thresholds):
+    """For each threshold t: (sum of p_i with outage_i > t, sum of outage_i * p_i over the same states)."""
+    n = len(probs)
+    outages = np.arange(n) * step
+    sp = np.concatenate([np.cumsum(probs[::-1])[::-1], [0.0]])
+    sxp = np.concatenate([np.cumsum((outages * probs)[::-1])[::-1], [0.0]])
+    first = np.searchsorted(outages, thresholds, side="right")        # first state with outage > t
+    return sp[first], sxp[first], first
+
+
+def calculate_expected_generation(probs, step: float, unit_cap: float, loads, lfu_sigma: float) -> float:
+    """generating_adequacy_comprehensive.jl:118-142: expected energy an energy-limited unit of `unit_cap` MW must
+    deliver on top of the rest of the system (COPT `probs` on the grid i*step), with the 7-step LFU.
+    sum_i min(cap, outage_i - t) p_i over outage_i > t  =  [E(t) - E(t + cap)] with E(t) = sum (outage_i - t)+ p_i."""
+    probs = np.asarray(probs, dtype=np.float64)
+    loads = np.asarray(loads, dtype=np.float64)
+    cap_rest = (len(probs) - 1) * step
+    total = 0.0
+    for z, pz in LFU_DISTRIBUTION:
+        t = cap_rest - (loads + z * lfu_sigma)
+        sp1, sxp1, _ = _tail_weights(probs, step, t)
+        sp2, sxp2, _ = _tail_weights(probs, step, t + unit_cap)
+        e1 = sxp1 - t * sp1                      # sum (outage - t)+ p
+        e2 = sxp2 - (t + unit_cap) * sp2         # sum (outage - t - cap)+ p
+        total += pz * float((e1 - e2).sum())
+    return total
+
+
+def update_elu(gens: Sequence[DetailedGenerator], loads, step_size: float, lfu_sigma: float,
+               engine: Optional[Engine] = None) -> bool:
+    """update_elu!, generating_adequacy_comprehensive.jl:144-175: effective FOR of the energy-limited units."""
+    eng = engine or default_engine()
+    changed = False
+    for g in gens:
+        if g.energy_limit == math.inf:
+            continue
+        rest = [og for og in gens if og is not g]
+        probs = eng.copt([og.capacity for og in rest], [og.effective_q for og in rest], step_size)
+        req_energy = calculate_expected_generation(probs, step_size, g.capacity, loads, lfu_sigma)
+        new_q = g.for_rate
+        if req_energy > g.energy_limit:
+            deficit = req_energy - g.energy_limit
+            new_q += deficit / (g.capacity * len(loads))
+        new_q = min(new_q, 1.0)
+        if abs(new_q - g.effective_q) > 1e-5:
+            g.effective_q = new_q
+            changed = True
+    return changed
+
+
+def run_detailed_analytical(gens: Sequence[DetailedGenerator], base_load, lfu_sigma_percent: float,
+                            engine: Optional[Engine] = None):
+    """tail_risk.jl:96-141 -> (sum(hourly_risk_profile), hourly_risk_profile): 5 ELU updates, 52 weekly COPTs
+    (20 MW grid, units on maintenance left out), hourly risk with the 7-step LFU."""
+    eng = engine or default_engine()
+    base_load = np.asarray(base_load, dtype=np.float64)
+    profile = np.zeros(len(base_load))
+    step_size = 20.0
+    lfu_mw = float(base_load.max()) * (lfu_sigma_percent / 100.0)
+    for _ in range(5):
+        update_elu(gens, base_load, step_size, lfu_mw, eng)
+    for w in range(1, 53):
+        week = [g for g in gens if not (w >= g.scheduled_outage_start and w < g.scheduled_outage_start + g.maintenance_weeks)]
+        probs = eng.copt([g.capacity for g in week], [g.effective_q for g in week], step_size)
+        installed = (len(probs) - 1) * step_size
+        h0, h1 = (w - 1) * 168, min(w * 168, 8760)
+        load = base_load[h0:h1]
+        risk = np.zeros(len(load))
+        for z, pz in LFU_DISTRIBUTION:
+            sp, _, _ = _tail_weights(probs, step_size, installed - (load + z * lfu_mw))
+            risk += sp * pz
+        profile[h0:h1] = risk
+    return float(profile.sum()), profile

@@ -104,7 +104,7 @@ extern "C" void psra_destroy(psra_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     void *bufs[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_load, h->d_lmax,
-                    h->d_tab_lol, h->d_tab_ens, h->d_acc, h->d_lol, h->d_ens, h->d_ent, h->d_fail,
+                    h->d_load_sorted, h->d_load_suffix, h->d_acc, h->d_lol, h->d_ens, h->d_ent, h->d_fail,
                     h->d_group, h->d_scratch, h->d_scratch2};
     for (void *p : bufs)
         if (p) cudaFree(p);

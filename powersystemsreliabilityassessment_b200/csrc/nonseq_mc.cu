@@ -136,13 +136,13 @@ static int prepare_sorted(psra_handle *h)
     std::sort(ld.begin(), ld.end());
     std::vector<long long> suf((size_t)h->H + 1, 0);
     for (int i = h->H - 1; i >= 0; i--) suf[i] = suf[i + 1] + ld[i];
-    if (h->d_tab_lol) cudaFree(h->d_tab_lol);
-    if (h->d_tab_ens) cudaFree(h->d_tab_ens);
-    h->d_tab_lol = nullptr; h->d_tab_ens = nullptr;
-    PSRA_CUDA(h, cudaMalloc(&h->d_tab_lol, sizeof(int32_t) * (size_t)h->H));
-    PSRA_CUDA(h, cudaMalloc(&h->d_tab_ens, sizeof(long long) * ((size_t)h->H + 1)));
-    PSRA_CUDA(h, cudaMemcpy(h->d_tab_lol, ld.data(), sizeof(int32_t) * (size_t)h->H, cudaMemcpyHostToDevice));
-    PSRA_CUDA(h, cudaMemcpy(h->d_tab_ens, suf.data(), sizeof(long long) * suf.size(), cudaMemcpyHostToDevice));
+    if (h->d_load_sorted) cudaFree(h->d_load_sorted);
+    if (h->d_load_suffix) cudaFree(h->d_load_suffix);
+    h->d_load_sorted = nullptr; h->d_load_suffix = nullptr;
+    PSRA_CUDA(h, cudaMalloc(&h->d_load_sorted, sizeof(int32_t) * (size_t)h->H));
+    PSRA_CUDA(h, cudaMalloc(&h->d_load_suffix, sizeof(long long) * ((size_t)h->H + 1)));
+    PSRA_CUDA(h, cudaMemcpy(h->d_load_sorted, ld.data(), sizeof(int32_t) * (size_t)h->H, cudaMemcpyHostToDevice));
+    PSRA_CUDA(h, cudaMemcpy(h->d_load_suffix, suf.data(), sizeof(long long) * suf.size(), cudaMemcpyHostToDevice));
     h->tab_valid = true;
     return PSRA_OK;
 }
@@ -164,7 +164,7 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
     NsArgs a{};
     a.U = h->U; a.H = h->H; a.W = (h->U + 31) / 32;
     a.cap = h->d_cap; a.for_thr = h->d_for_thr; a.for_rate = h->d_for;
-    a.sorted = (const int32_t *)h->d_tab_lol; a.suffix = (const long long *)h->d_tab_ens;
+    a.sorted = h->d_load_sorted; a.suffix = (const long long *)h->d_load_suffix;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
     a.i0 = i0; a.n = n; a.acc = h->d_acc; a.group = 1;
 

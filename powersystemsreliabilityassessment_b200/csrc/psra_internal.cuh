@@ -40,10 +40,10 @@ struct psra_handle {
     int32_t max_load = 0;
     int32_t *d_load = nullptr;       // [Wd*32] zero padded
     int32_t *d_lmax = nullptr;       // [Wd] max load of each 32-hour word
-    // non-sequential lookup tables over capacity c = 0..total_cap (built lazily)
+    // non-sequential evaluation tables (built lazily at the first psra_nonseq_* call after psra_set_load)
     bool tab_valid = false;
-    uint32_t *d_tab_lol = nullptr;   // #{h : load[h] > c}
-    int64_t *d_tab_ens = nullptr;    // sum_h max(load[h]-c, 0)
+    int32_t *d_load_sorted = nullptr;   // [H] load curve sorted ascending
+    int64_t *d_load_suffix = nullptr;   // [H+1] suffix sums of the sorted curve
     // accumulators / scratch
     unsigned long long *d_acc = nullptr;  // [32]
     // per-run outputs kept on the device (grown on demand)

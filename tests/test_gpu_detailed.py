@@ -74,3 +74,27 @@ def test_run_detailed_mc_entry_point(engine):
     lole, _, _ = O.analytical([g.capacity for g in plain], [g.for_rate for g in plain], base, 1.0)
     se = d0.std(ddof=1) / math.sqrt(len(d0))
     assert abs(d0.mean() - lole) < 4 * se + 0.05
+
+
+def test_detailed_analytical_vs_literal_loops(engine):
+    """tail_risk.jl:96-141: ELU effective-FOR fixed point + weekly COPT risk with 7-step LFU; the numeric cores
+    (comprehensive.jl:118-142, tail_risk.jl:124-136) against the oracle's literal loops."""
+    gens, base, _ = _system()
+    lfu_mw = base.max() * 0.05
+    rest = [g for g in gens if g.name != "Hydro_ELU"]
+    probs = engine.copt([g.capacity for g in rest], [g.effective_q for g in rest], 20.0)
+    e_fast = P.calculate_expected_generation(probs, 20.0, 200.0, base, lfu_mw)
+    e_ref = O.expected_generation(probs, 20.0, 200.0, base, lfu_mw)
+    assert abs(e_fast - e_ref) <= 1e-9 * e_ref and e_ref > 200.0 * 50.0        # the limit binds (comprehensive.jl:194-197)
+    total, profile = P.run_detailed_analytical(gens, base, 5.0, engine=engine)
+    hydro = [g for g in gens if g.name == "Hydro_ELU"][0]
+    assert hydro.effective_q > hydro.for_rate + 1e-3                           # ELU raised the effective FOR
+    assert abs(total - profile.sum()) < 1e-12 and (profile[8736:] == 0).all()
+    for w in (1, 20, 52):                                                       # spot-check weeks against literal loops
+        week = [g for g in gens if not (w >= g.scheduled_outage_start and w < g.scheduled_outage_start + g.maintenance_weeks)]
+        pw = engine.copt([g.capacity for g in week], [g.effective_q for g in week], 20.0)
+        ref = O.lfu_hourly_risk(pw, 20.0, base[(w - 1) * 168:w * 168], lfu_mw)
+        assert np.allclose(profile[(w - 1) * 168:w * 168], ref, rtol=1e-9, atol=1e-15)
+    # the MC mean sits above the analytical prediction (the point of tail_risk.jl plot 1)
+    dist, _ = P.run_detailed_mc(gens, base, 5.0, 2000, seed=4, engine=engine)
+    assert dist.mean() > 0.5 * total
