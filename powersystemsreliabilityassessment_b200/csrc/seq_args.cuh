@@ -26,7 +26,7 @@ cudaError_t seq_fast_prepare(bool disc, bool two, size_t smem, int threads, int 
 void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);
 
 // seq_team.cu
-size_t seq_team_smem_bytes(int U, int Wd, int seg_words);
+size_t seq_team_smem_bytes(int U, int Wd, int seg_words, bool two_halves);
 int seq_team_pend_cap(int U);
 int seq_team_max_units();
 cudaError_t seq_team_prepare(size_t smem, int *blocks_per_sm);

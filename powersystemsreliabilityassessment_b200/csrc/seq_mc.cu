@@ -316,7 +316,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     // launch geometry: segment length and warps per block under the shared-memory budget
     int seg_words = h->Wd;
     if (team) {
-        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : 1760;
+        // whole year in one segment when its int32 timeline stays below 40 KB, else 1760-hour segments
+        int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : (h->Wd * 32 <= 10240 ? h->Wd * 32 : 1760);
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
     // seq_fast.cu: event lists sized 2x the expected transitions of a segment (+ initial draws + slack);
@@ -344,7 +345,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
         if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16);
-        if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words);
+        if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words, a.two_halves != 0);
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
         if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));

@@ -32,15 +32,16 @@ struct TeamShared {                   // scalars shared by the block
 
 int seq_team_pend_cap(int U) { const int c = 4 * ((U + 31) & ~31); return c < 1024 ? 1024 : c; }
 
-size_t seq_team_smem_bytes(int U, int Wd, int seg_words)
+size_t seq_team_smem_bytes(int U, int Wd, int seg_words, bool two_halves)
 {
+    const int halves = two_halves ? 2 : 1;
     const size_t Upad = (size_t)((U + 31) & ~31);
     size_t b = sizeof(int32_t) * (size_t)((Wd + 3) & ~3);                                  // word maxima of the load
     b += Upad * (sizeof(unsigned long long) + sizeof(int32_t) + 2 * sizeof(float) + 2 * sizeof(uint32_t));  // t_run, cap, means, thr, nb
     b += sizeof(uint32_t) * (size_t)(((Upad / 32) + 3) & ~3);                             // initial-state masks
-    b += sizeof(int32_t) * 2 * (size_t)seg_words * 32;                                    // ring timeline
-    b += 2 * sizeof(int32_t) * (size_t)((2 * seg_words + 3) & ~3);                         // word sums
-    b += 2 * sizeof(uint32_t) * (size_t)seq_team_pend_cap(U);                              // pending lists
+    b += sizeof(int32_t) * halves * (size_t)seg_words * 32;                               // ring timeline
+    b += 2 * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);                    // word sums
+    b += two_halves ? 2 * sizeof(uint32_t) * (size_t)seq_team_pend_cap(U) : 0;             // pending lists
     b += TEAM_WARPS * 32 * TEAM_NB_MAX;                                                   // job maps
     b += sizeof(TeamShared) + 64;
     return (b + 15) & ~(size_t)15;
@@ -54,9 +55,11 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int Upad = (a.U + 31) & ~31, G = Upad >> 5;
-    const int PEND_CAP = a.pend_cap;
+    const bool two_halves = a.two_halves != 0;
+    const int halves = two_halves ? 2 : 1;
+    const int PEND_CAP = two_halves ? a.pend_cap : 0;
     const int seg_slots = a.seg_words * 32;
-    const int ring_words = (2 * a.seg_words + 3) & ~3;
+    const int ring_words = (halves * a.seg_words + 3) & ~3;
     // ---- shared-memory carve-up (8-byte items first)
     unsigned long long *t_run = reinterpret_cast<unsigned long long *>(smem_raw);          // [Upad]
     int32_t *s_lmax = reinterpret_cast<int32_t *>(t_run + Upad);                            // [pad4(Wd)]
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqA
     uint32_t *s_nb = s_thr + Upad;                                                          // next Philox block per unit
     uint32_t *s_s0 = s_nb + Upad;                                                           // [G] initial-state masks
     int32_t *tl = reinterpret_cast<int32_t *>(s_s0 + ((G + 3) & ~3));                       // [2*seg_slots]
-    int32_t *wsum = tl + 2 * seg_slots;
+    int32_t *wsum = tl + halves * seg_slots;
     int32_t *wneg = wsum + ring_words;
     uint32_t *pend = reinterpret_cast<uint32_t *>(wneg + ring_words);                       // [2][CAP]
     unsigned char *jobmap = reinterpret_cast<unsigned char *>(pend + 2 * PEND_CAP) + warp * 32 * TEAM_NB_MAX;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqA
         s_mdn[i] = v ? __fmul_rn(a.mttr[i], 16777216.0f) : 1.0f;
         s_thr[i] = v ? a.for_thr[i] : 0u;
     }
-    for (int i = threadIdx.x; i < 2 * seg_slots; i += blockDim.x) tl[i] = 0;
+    for (int i = threadIdx.x; i < halves * seg_slots; i += blockDim.x) tl[i] = 0;
     for (int i = threadIdx.x; i < ring_words; i += blockDim.x) { wsum[i] = 0; wneg[i] = 0; }
     if (threadIdx.x == 0) { sh->pend_cnt[0] = sh->pend_cnt[1] = 0; sh->capacity = 0; sh->overflow = 0; }
     __syncthreads();
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqA
         for (int y = 0; y < a.ypc; y++) {
             unsigned int lolh = 0, entries = 0;      // meaningful in warp 0
             long long ens_lane = 0;
-            for (int seg = 0; seg < a.nseg; seg++, ring ^= 1) {
+            for (int seg = 0; seg < a.nseg; seg++, ring = two_halves ? ring ^ 1 : 0) {
                 const int seg_h0 = seg * seg_slots;
                 const int seg_h1 = min(a.H, seg_h0 + seg_slots);
                 const int abs0 = y * a.H + seg_h0, abs1 = y * a.H + seg_h1;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqA
                 uint32_t *pend_in = pend + pb * PEND_CAP, *pend_out = pend + (pb ^ 1) * PEND_CAP;
 
                 // ---- pending events: scatter those that now fall into the ring, keep the rest (other buffer)
-                const int n_in = sh->pend_cnt[pb];
+                const int n_in = two_halves ? sh->pend_cnt[pb] : 0;
                 if (n_in) {
                     for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
                         const uint32_t e = pend_in[i];
@@ -175,11 +178,17 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqA
                             excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
                             total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
                         };
-                        const int n_m = is_short ? want : 0;
+                        int n_m = is_short ? want : 0;
                         int off_m, J1;
                         count_scan(n_m, off_m, J1);
+                        if (J1 < 32 && !first) {       // spare lanes: one more block of slack for the short units
+                            const int n_x = is_short ? min(TEAM_NB_MAX, want + 1) : 0;
+                            int off_x, Jx;
+                            count_scan(n_x, off_x, Jx);
+                            if (Jx <= 32) { n_m = n_x; off_m = off_x; J1 = Jx; }
+                        }
                         int n_u, off, J;
-                        if (J1 >= 32 || first) {
+                        if (J1 >= 32 || first || !two_halves) {
                             off = off_m;
                             n_u = max(0, min(n_m, 32 - off));
                             J = min(J1, 32);
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqA
                                     if (delta < 0) atomicAdd(&wneg[slot >> 5], delta);
                                 }
                                 const bool inhor = valid && hs < (uint32_t)chain_end_h;
-                                const bool pnd = inhor && !in_ring;
+                                const bool pnd = two_halves && inhor && !in_ring;
                                 const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
                                 if (pm) {
                                     int basep = 0;
