@@ -49,7 +49,7 @@ size_t seq_team_smem_bytes(int U, int Wd, int seg_words, bool two_halves)
 
 int seq_team_max_units() { return TEAM_MAX_UNITS; }
 
-__global__ void __launch_bounds__(TEAM_WARPS * 32, 2) seq_team_kernel(const SeqArgs a)
+__global__ void __launch_bounds__(TEAM_WARPS * 32, 3) seq_team_kernel(const SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -257,3 +257,19 @@ def test_team_kernel_large_systems(engine, rts):
     assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
     big = engine.seq_mc(20000, seed=1)
     assert abs(big.lole - 8.033131) < 4 * big.lole_se          # analytical COPT value
+
+
+def test_high_transition_rate_short_segments(engine):
+    """Units that toggle every few hours force the sampler kernel into many short ring segments (event lists
+    are bounded); results stay bit-identical to the literal loop."""
+    cap = np.array([40.0, 30.0, 30.0, 20.0, 20.0, 10.0, 10.0, 5.0])
+    mttf = np.array([2.0, 3.0, 2.5, 4.0, 1.5, 6.0, 2.0, 1.0]); mttr = np.array([1.0, 0.5, 2.0, 1.0, 0.7, 3.0, 0.2, 1.0])
+    rng = np.random.default_rng(3)
+    load = rng.integers(60, 130, 8736).astype(np.int32)
+    engine.set_system(cap, mttf, mttr); engine.set_load(load)
+    for ypc, init in ((1, 1), (3, 0)):
+        r = engine.seq_mc(12 * ypc, seed=55, init_mode=init, years_per_chain=ypc, per_year=True)
+        lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 55, 0, 12, ypc, init)
+        assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(r.entries.astype(np.float64), ent)
+        assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+        assert r.raw["events"] > 30000 * 12 * ypc and lol.sum() > 100
