@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
                             }
                         }
                     }
+                    __syncwarp();   // every lane has read the words it helped to resolve before they are cleared
                     for (uint32_t mm = m; mm; mm &= mm - 1) tl[w * 32 + (__ffs(mm) - 1)] = 0;
                     if (valid) bm[w] = 0u;
                     capacity += __shfl_sync(0xffffffffu, incl, 31);

@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 3) seq_team_kernel(const SeqA
                         }
                     }
                     capacity += __shfl_sync(0xffffffffu, incl, 31);
+                    __syncwarp();
                     if (lane == 0) sh->capacity = capacity;
                 }
                 __syncthreads();
