@@ -69,6 +69,21 @@ size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_ca
 
 int seq_fast_max_threads() { return FAST_MAX_THREADS; }
 
+// predicated shared-memory updates (inline PTX keeps them branch-free in SASS)
+__device__ __forceinline__ void red_add_shared_if(uint32_t saddr, int v, bool p)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p red.shared.add.s32 [%0], %1;\n}\n"
+                 :: "r"(saddr), "r"(v), "r"((int)p) : "memory");
+}
+
+// push event `ent` (list link filled in) onto the list of its word: head <- idx1, entry.next <- old head
+__device__ __forceinline__ void list_push_shared_if(uint32_t head_saddr, uint32_t ev_saddr, uint32_t idx1, uint32_t ent, bool p)
+{
+    asm volatile("{\n .reg .pred p;\n .reg .b32 nx;\n setp.ne.b32 p, %4, 0;\n @p atom.shared.exch.b32 nx, [%0], %2;\n"
+                 " @p shl.b32 nx, nx, 20;\n @p or.b32 nx, nx, %3;\n @p st.shared.b32 [%1], nx;\n}\n"
+                 :: "r"(head_saddr), "r"(ev_saddr), "r"(idx1), "r"(ent), "r"((int)p) : "memory");
+}
+
 template <bool kDisc, bool kTwo>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
 {
@@ -110,6 +125,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
     for (int i = lane; i < ring_words; i += 32) { wsum[i] = 0; wneg[i] = 0; whead[i] = 0u; }
+    const uint32_t wsum_s = (uint32_t)__cvta_generic_to_shared(wsum), wneg_s = (uint32_t)__cvta_generic_to_shared(wneg),
+                   whead_s = (uint32_t)__cvta_generic_to_shared(whead);
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
@@ -159,6 +176,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 const int wbase_cur = ring * a.seg_words, wbase_nxt = (ring ^ 1) * a.seg_words;
                 uint32_t *ev_cur = evl + (size_t)ring * ev_cap, *ev_nxt = evl + (size_t)(ring ^ 1) * ev_cap;
                 int cnt_cur = ring ? ev_cnt1 : ev_cnt0, cnt_nxt = ring ? ev_cnt0 : ev_cnt1;
+                const uint32_t evcur_s = (uint32_t)__cvta_generic_to_shared(ev_cur), evnxt_s = (uint32_t)__cvta_generic_to_shared(ev_nxt);
 
                 // ---- far-future events that now fall into the next segment's half
                 if (two_halves && pend_cnt) {
@@ -286,33 +304,21 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             const bool in_cur = in_ring && rel < len_cur;
                             const bool in_nxt = in_ring && !in_cur;
                             const uint32_t hseg = in_cur ? rel : rel - len_cur;  // hour within its segment
-                            if (in_ring) {
-                                const int w = (in_cur ? wbase_cur : wbase_nxt) + (int)(hseg >> 5);
-                                atomicAdd(&wsum[w], delta);
-                                if (delta < 0) atomicAdd(&wneg[w], delta);
-                            }
+                            const uint32_t w4 = 4u * ((in_cur ? (uint32_t)wbase_cur : (uint32_t)wbase_nxt) + (hseg >> 5));
+                            red_add_shared_if(wsum_s + w4, delta, in_ring);
+                            red_add_shared_if(wneg_s + w4, delta, in_ring && delta < 0);
                             const uint32_t ent = (hseg << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
                             const uint32_t mc = __ballot_sync(0xffffffffu, in_cur);
-                            if (in_cur) {
-                                const int pos = cnt_cur + __popc(mc & lt_mask);
-                                if (pos < ev_cap) {
-                                    const uint32_t nx = atomicExch(&whead[wbase_cur + (int)(hseg >> 5)], (uint32_t)(pos + 1));
-                                    ev_cur[pos] = (nx << 20) | ent;
-                                }
+                            {
+                                const uint32_t pos = (uint32_t)cnt_cur + __popc(mc & lt_mask);
+                                list_push_shared_if(whead_s + w4, evcur_s + 4u * pos, pos + 1u, ent, in_cur && pos < (uint32_t)ev_cap);
                             }
                             cnt_cur += __popc(mc);
                             if (two_halves) {
                                 const uint32_t mn = __ballot_sync(0xffffffffu, in_nxt);
-                                if (mn) {
-                                    if (in_nxt) {
-                                        const int pos = cnt_nxt + __popc(mn & lt_mask);
-                                        if (pos < ev_cap) {
-                                            const uint32_t nx = atomicExch(&whead[wbase_nxt + (int)(hseg >> 5)], (uint32_t)(pos + 1));
-                                            ev_nxt[pos] = (nx << 20) | ent;
-                                        }
-                                    }
-                                    cnt_nxt += __popc(mn);
-                                }
+                                const uint32_t pos = (uint32_t)cnt_nxt + __popc(mn & lt_mask);
+                                list_push_shared_if(whead_s + w4, evnxt_s + 4u * pos, pos + 1u, ent, in_nxt && pos < (uint32_t)ev_cap);
+                                cnt_nxt += __popc(mn);
                             }
                             const bool inhor = valid && hs < (uint32_t)chain_end_h;
                             if (two_halves) {                              // events beyond the ring (a single segment has none)
