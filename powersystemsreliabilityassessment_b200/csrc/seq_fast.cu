@@ -37,11 +37,13 @@
 #define FAST_NB_MAX 4                  // Philox blocks a unit may get per wave
 #define FAST_PEND_CAP 256              // far-future events (beyond the two-segment ring)
 #ifndef FAST_MAX_THREADS
-#define FAST_MAX_THREADS 768
+#define FAST_MAX_THREADS 896
 #endif
 
 struct FastWarpSmem {                  // per-warp scratch that precedes the event lists
     unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit
+    unsigned long long acc[8];         // per-warp accumulators (lane 0): lol, ens, entries, years with loss, lol^2, ens^2 lo/hi
+    unsigned int diag[8];              // waves, jobs, ahead jobs, flagged runs, max list depth
     unsigned char jobmap[32];
 };
 
@@ -130,10 +132,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
-    unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
-    long long acc_ens = 0;
+    // long-lived per-warp sums live in shared memory (registers are what limits the resident warps)
+    if (lane < 8) { ws->acc[lane] = 0ull; ws->diag[lane] = 0u; }
+    __syncwarp();
     unsigned int n_events = 0;
-    unsigned int n_waves = 0, n_jobs = 0, n_opt = 0, n_flag = 0, pend_max = 0;   // warp-uniform diagnostics
 
     const bool unit_valid = lane < a.U;
     const int capu = s_cap[lane];
@@ -249,10 +251,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         off = is_short ? off_m : off_o;
                         n_u = is_short ? n_m : max(0, min(n_o, 32 - off_o));
                         J = min(32, J1 + J2);
-                        n_opt += J - J1;
+                        if (lane == 0) ws->diag[2] += (unsigned int)(J - J1);
                     }
-                    n_jobs += J;
-                    n_waves++;
+                    if (lane == 0) { ws->diag[1] += (unsigned int)J; ws->diag[0]++; }
 #pragma unroll
                     for (int k = 0; k < FAST_NB_MAX; k++)
                         if (k < n_u) ws->jobmap[off + k] = (unsigned char)lane;   // off + n_u <= 32
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         init_wave = false;
                     }
                 }
-                pend_max = max(pend_max, (unsigned int)max(cnt_cur, cnt_nxt));
+                if (lane == 0) ws->diag[4] = max(ws->diag[4], (unsigned int)max(cnt_cur, cnt_nxt));
                 if (cnt_cur > ev_cap || cnt_nxt > ev_cap) {      // reported as PSRA_E_OVERFLOW: choose a shorter segment
                     if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 3ull);
                     cnt_cur = min(cnt_cur, ev_cap); cnt_nxt = min(cnt_nxt, ev_cap);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 const int cs_lane = capacity + incl - loc;       // capacity entering the lane's run
                 const bool flagged = (lmin != INT_MAX) && (cs_lane + lmin < 0);
                 uint32_t fm = __ballot_sync(0xffffffffu, flagged);
-                n_flag += __popc(fm);
+                if (lane == 0) ws->diag[3] += (unsigned int)__popc(fm);
                 while (fm) {                                     // rare: a run that may contain loss of load
                     const int src = __ffs(fm) - 1;
                     fm &= fm - 1;
@@ -437,17 +438,17 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 if (a.ent) a.ent[yi] = entries;
                 if (a.group_lol && lolh) atomicAdd(&a.group_lol[yi / a.group], (unsigned long long)lolh);
             }
-            acc_lol += lolh; acc_ens += ens; acc_ent += entries;
-            acc_ywl += lolh ? 1 : 0;
-            acc_lol2 += (unsigned long long)lolh * lolh;
-            const unsigned long long e = (unsigned long long)ens;
-            const unsigned long long plo = e * e, phi = __umul64hi(e, e);
-            const unsigned long long nlo = acc_e2lo + plo;
-            acc_e2hi += phi + (nlo < acc_e2lo ? 1ull : 0ull);
-            acc_e2lo = nlo;
+            if (lane == 0) {
+                ws->acc[0] += lolh; ws->acc[1] += (unsigned long long)ens; ws->acc[2] += entries;
+                ws->acc[3] += lolh ? 1ull : 0ull;
+                ws->acc[4] += (unsigned long long)lolh * lolh;
+                const unsigned long long e = (unsigned long long)ens;
+                const unsigned long long plo = e * e, phi = __umul64hi(e, e);
+                const unsigned long long nlo = ws->acc[5] + plo;
+                ws->acc[6] += phi + (nlo < ws->acc[5] ? 1ull : 0ull);
+                ws->acc[5] = nlo;
+            }
         }
-        // chain finished: the ring half after the last segment may hold events beyond the chain end
-        // only if abs2 exceeded chain_end_h, which it never does; both halves are clean here.
         __syncwarp();
     }
 
@@ -455,18 +456,18 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ev += __shfl_xor_sync(0xffffffffu, ev, d);
     if (lane == 0) {
-        if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
-        if (acc_ens) atomicAdd(&a.acc[ACC_ENS], (unsigned long long)acc_ens);
-        if (acc_ent) atomicAdd(&a.acc[ACC_ENT], acc_ent);
-        if (acc_ywl) atomicAdd(&a.acc[ACC_YWL], acc_ywl);
-        if (acc_lol2) atomicAdd(&a.acc[ACC_LOL2], acc_lol2);
-        if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
+        if (ws->acc[0]) atomicAdd(&a.acc[ACC_LOL], ws->acc[0]);
+        if (ws->acc[1]) atomicAdd(&a.acc[ACC_ENS], ws->acc[1]);
+        if (ws->acc[2]) atomicAdd(&a.acc[ACC_ENT], ws->acc[2]);
+        if (ws->acc[3]) atomicAdd(&a.acc[ACC_YWL], ws->acc[3]);
+        if (ws->acc[4]) atomicAdd(&a.acc[ACC_LOL2], ws->acc[4]);
+        if (ws->acc[5] | ws->acc[6]) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], ws->acc[5], ws->acc[6]);
         if (ev) atomicAdd(&a.acc[ACC_EVENTS], ev);
-        atomicAdd(&a.acc[ACC_WAVES], (unsigned long long)n_waves);
-        atomicAdd(&a.acc[ACC_JOBS], (unsigned long long)n_jobs);
-        atomicAdd(&a.acc[ACC_OPT_JOBS], (unsigned long long)n_opt);
-        atomicAdd(&a.acc[ACC_FLAGGED], (unsigned long long)n_flag);
-        atomicMax(&a.acc[ACC_PEND_MAX], (unsigned long long)pend_max);
+        atomicAdd(&a.acc[ACC_WAVES], (unsigned long long)ws->diag[0]);
+        atomicAdd(&a.acc[ACC_JOBS], (unsigned long long)ws->diag[1]);
+        atomicAdd(&a.acc[ACC_OPT_JOBS], (unsigned long long)ws->diag[2]);
+        atomicAdd(&a.acc[ACC_FLAGGED], (unsigned long long)ws->diag[3]);
+        atomicMax(&a.acc[ACC_PEND_MAX], (unsigned long long)ws->diag[4]);
     }
 }
 

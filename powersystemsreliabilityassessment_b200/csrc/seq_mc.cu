@@ -321,11 +321,12 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         int seg_hours = h->cfg.seg_hours > 0 ? h->cfg.seg_hours : (h->Wd * 32 <= 10240 ? h->Wd * 32 : 1760);
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
-    // seq_fast.cu: event lists sized 2x the expected transitions of a segment (+ initial draws + slack);
+    // seq_fast.cu: event lists sized 1.75x the expected transitions of a segment (+ initial draws + slack:
+    // > 15 standard deviations for RTS-79; an overflow is reported as PSRA_E_OVERFLOW, never silent);
     // by default the whole year is one segment unless that list would exceed 2048 entries
     auto ev_cap_for = [&](int sw) -> int {
         const double e = h->events_per_hour * sw * 32.0 + h->U;
-        const long long c = (long long)(2.0 * e) + 128;
+        const long long c = (long long)(1.75 * e) + 64;
         return (int)((c + 31) & ~31ll);
     };
     if (one_unit) {
@@ -342,7 +343,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     a.ev_cap = ev_cap_for(seg_words);
     if (fast && a.ev_cap > 2016)
         return psra_fail(h, PSRA_E_INVALID, "unit transition rate too high for the sampler kernel (%d events per 32-hour word)", a.ev_cap);
-    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 24 : 16);
+    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 28 : 16);
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
         if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16);
