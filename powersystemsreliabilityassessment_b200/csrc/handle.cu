@@ -141,15 +141,18 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
         thr[u] = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
     }
     PSRA_REQUIRE(h, total <= 0x3fffffff, "installed capacity exceeds the int32 fixed-point range");
-    void *old[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for};
-    for (void *p : old)
-        if (p) cudaFree(p);
-    h->d_cap = nullptr; h->d_mttf = nullptr; h->d_mttr = nullptr; h->d_for_thr = nullptr; h->d_for = nullptr;
-    PSRA_CUDA(h, cudaMalloc(&h->d_cap, sizeof(int32_t) * U));
-    PSRA_CUDA(h, cudaMalloc(&h->d_mttf, sizeof(float) * U));
-    PSRA_CUDA(h, cudaMalloc(&h->d_mttr, sizeof(float) * U));
-    PSRA_CUDA(h, cudaMalloc(&h->d_for_thr, sizeof(uint32_t) * U));
-    PSRA_CUDA(h, cudaMalloc(&h->d_for, sizeof(double) * U));
+    if (U != h->U || !h->d_cap) {      // (re)allocate only when the unit count changes
+        void *old[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for};
+        for (void *p : old)
+            if (p) cudaFree(p);
+        h->d_cap = nullptr; h->d_mttf = nullptr; h->d_mttr = nullptr; h->d_for_thr = nullptr; h->d_for = nullptr;
+        h->U = 0;
+        PSRA_CUDA(h, cudaMalloc(&h->d_cap, sizeof(int32_t) * U));
+        PSRA_CUDA(h, cudaMalloc(&h->d_mttf, sizeof(float) * U));
+        PSRA_CUDA(h, cudaMalloc(&h->d_mttr, sizeof(float) * U));
+        PSRA_CUDA(h, cudaMalloc(&h->d_for_thr, sizeof(uint32_t) * U));
+        PSRA_CUDA(h, cudaMalloc(&h->d_for, sizeof(double) * U));
+    }
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_cap, cap_fp, sizeof(int32_t) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_mttf, mf.data(), sizeof(float) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_mttr, mr.data(), sizeof(float) * U, cudaMemcpyHostToDevice, h->stream));
@@ -178,11 +181,13 @@ extern "C" int psra_set_load(psra_handle *h, const int32_t *load_fp, int32_t n_h
         if (load_fp[i] > lmax[i >> 5]) lmax[i >> 5] = load_fp[i];
         if (load_fp[i] > mx) mx = load_fp[i];
     }
-    if (h->d_load) cudaFree(h->d_load);
-    if (h->d_lmax) cudaFree(h->d_lmax);
-    h->d_load = nullptr; h->d_lmax = nullptr;
-    PSRA_CUDA(h, cudaMalloc(&h->d_load, sizeof(int32_t) * pad.size()));
-    PSRA_CUDA(h, cudaMalloc(&h->d_lmax, sizeof(int32_t) * Wd));
+    if (Wd != h->Wd || !h->d_load) {   // (re)allocate only when the padded length changes
+        if (h->d_load) cudaFree(h->d_load);
+        if (h->d_lmax) cudaFree(h->d_lmax);
+        h->d_load = nullptr; h->d_lmax = nullptr; h->H = 0; h->Wd = 0;
+        PSRA_CUDA(h, cudaMalloc(&h->d_load, sizeof(int32_t) * pad.size()));
+        PSRA_CUDA(h, cudaMalloc(&h->d_lmax, sizeof(int32_t) * Wd));
+    }
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_load, pad.data(), sizeof(int32_t) * pad.size(), cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_lmax, lmax.data(), sizeof(int32_t) * Wd, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
