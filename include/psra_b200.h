@@ -105,6 +105,8 @@ typedef struct psra_seq_outputs {       /* all optional (NULL = not wanted) */
                                cumsum/(group*k) = convergence_history, PSA.jl:263-265 */
     int32_t   group;        /* 10 for PSA.jl:263 */
     int32_t   keep_on_device; /* !=0: keep the per-year ENS / LOL vectors on the device for psra_tail */
+    double   *history;      /* [nyears/group] running mean of LOL hours after every `group` years, i.e.
+                               convergence_history of PSA.jl:263-265, computed on the device */
 } psra_seq_outputs;
 
 /* Years [year0, year0+nyears) of the experiment `seed`.  Years are grouped in chains of
@@ -143,6 +145,7 @@ typedef struct psra_nonseq_outputs {    /* all optional */
     int64_t  *group_lol;    /* [ceil(n/group)], group = 100 for PSA.jl:202-204 */
     int32_t   group;
     int32_t   reserved;
+    double   *history;      /* [n/group] running mean of LOL hours every `group` samples (PSA.jl:202-204) */
 } psra_nonseq_outputs;
 
 /* samples [sample0, sample0+n): unit u of sample i UP iff x >= floor(FOR_u * 2^32), x the

@@ -68,7 +68,7 @@ mutable struct PsraSeqSummary
 end
 struct PsraSeqOutputs
     lol_hours::Ptr{UInt32}; ens_fp::Ptr{Int64}; entries::Ptr{UInt32}; fail_count::Ptr{UInt32}
-    group_lol::Ptr{Int64}; group::Int32; keep_on_device::Int32
+    group_lol::Ptr{Int64}; group::Int32; keep_on_device::Int32; history::Ptr{Float64}
 end
 mutable struct PsraNonseqSummary
     samples::Int64; sum_lol_hours::Int64; sum_ens_fp::Int64; samples_with_loss::Int64
@@ -78,7 +78,7 @@ mutable struct PsraNonseqSummary
 end
 struct PsraNonseqOutputs
     lol_hours::Ptr{UInt32}; ens_fp::Ptr{Int64}; cap_avail::Ptr{Int32}; states::Ptr{UInt32}
-    group_lol::Ptr{Int64}; group::Int32; reserved::Int32
+    group_lol::Ptr{Int64}; group::Int32; reserved::Int32; history::Ptr{Float64}
 end
 struct PsraTailOut
     var::Float64; cvar::Float64; n_tail::Int64; x_lo::Int64; x_hi::Int64
@@ -157,16 +157,14 @@ function run_non_sequential_mc(gens::Vector{Generator}, load::LoadModel, iterati
                                seed::Integer=42, fp_scale::Float64=1.0, engine::Engine=default_engine())
     t_start = time()
     set_system!(engine, gens, load; fp_scale=fp_scale)
-    groups = zeros(Int64, cld(iterations, 100))
+    history = zeros(Float64, div(iterations, 100))
     s = PsraNonseqSummary()
-    GC.@preserve groups begin
-        out = Ref(PsraNonseqOutputs(C_NULL, C_NULL, C_NULL, C_NULL, pointer(groups), Int32(100), Int32(0)))
+    GC.@preserve history begin
+        out = Ref(PsraNonseqOutputs(C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, Int32(100), Int32(0), pointer(history)))
         check(engine, ccall((:psra_nonseq_mc, LIB), Cint,
                             (Ptr{Cvoid}, Int64, Int64, UInt64, Ref{PsraNonseqOutputs}, Ref{PsraNonseqSummary}),
                             engine.h, 0, iterations, UInt64(seed), out, s))
     end
-    k = div(iterations, 100)
-    history = cumsum(groups[1:k]) ./ (100.0 .* (1:k))
     return ReliabilityResult("Non-Sequential MC", s.sum_lol_hours / iterations,
                              s.sum_ens_fp / iterations / fp_scale, time() - t_start, history)
 end
@@ -184,16 +182,14 @@ function run_sequential_indices(gens::Vector{Generator}, load::LoadModel, years:
                                 years_per_chain::Integer=1, keep_on_device::Bool=false,
                                 engine::Engine=default_engine())
     set_system!(engine, gens, load; fp_scale=fp_scale)
-    groups = zeros(Int64, cld(years, 10))
+    history = zeros(Float64, div(years, 10))          # running mean every 10 years, computed on the device
     s = PsraSeqSummary()
-    GC.@preserve groups begin
-        out = Ref(PsraSeqOutputs(C_NULL, C_NULL, C_NULL, C_NULL, pointer(groups), Int32(10), Int32(keep_on_device)))
+    GC.@preserve history begin
+        out = Ref(PsraSeqOutputs(C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, Int32(10), Int32(keep_on_device), pointer(history)))
         check(engine, ccall((:psra_seq_mc, LIB), Cint,
                             (Ptr{Cvoid}, Int64, Int64, UInt64, Int32, Int32, Ref{PsraSeqOutputs}, Ref{PsraSeqSummary}),
                             engine.h, year0, years, UInt64(seed), init_mode, Int32(years_per_chain), out, s))
     end
-    k = div(years, 10)
-    history = cumsum(groups[1:k]) ./ (10.0 .* (1:k))
     n = max(s.years, 1)
     return SequentialIndices(s.years, s.sum_lol_hours / n, s.sum_ens_fp / n / fp_scale, s.sum_entries / n,
                              s.sum_entries > 0 ? s.sum_lol_hours / s.sum_entries : 0.0,

@@ -44,7 +44,7 @@ class SeqSummary(C.Structure):
 class SeqOutputs(C.Structure):
     _fields_ = [("lol_hours", C.c_void_p), ("ens_fp", C.c_void_p), ("entries", C.c_void_p),
                 ("fail_count", C.c_void_p), ("group_lol", C.c_void_p), ("group", C.c_int32),
-                ("keep_on_device", C.c_int32)]
+                ("keep_on_device", C.c_int32), ("history", C.c_void_p)]
 
 
 class NonseqSummary(C.Structure):
@@ -56,7 +56,7 @@ class NonseqSummary(C.Structure):
 class NonseqOutputs(C.Structure):
     _fields_ = [("lol_hours", C.c_void_p), ("ens_fp", C.c_void_p), ("cap_avail", C.c_void_p),
                 ("states", C.c_void_p), ("group_lol", C.c_void_p), ("group", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("history", C.c_void_p)]
 
 
 class DetailedSystem(C.Structure):

@@ -85,6 +85,7 @@ class SequentialIndices:
     entries: Optional[np.ndarray] = None
     fail_count: Optional[np.ndarray] = None
     group_lol: Optional[np.ndarray] = None
+    history: Optional[np.ndarray] = None       # running mean of LOL hours every `history` years (device-computed)
     raw: Optional[dict] = None                 # exact integer accumulators (shardable)
 
 
@@ -184,9 +185,12 @@ class Engine:
         return self.set_load(load.hourly_load, strict=False)
 
     # ---- sequential MC
-    def _seq_outputs(self, n, per_year, fail_count, group, keep):
+    def _seq_outputs(self, n, per_year, fail_count, group, keep, history=False):
         o = _lib.SeqOutputs()
         bufs = {}
+        if history:
+            bufs["history"] = np.zeros(n // history, dtype=np.float64)
+            o.history = _ptr(bufs["history"]); o.group = history
         if per_year:
             bufs["lol_hours"] = np.zeros(n, dtype=np.uint32)
             bufs["ens"] = np.zeros(n, dtype=np.int64)
@@ -213,14 +217,17 @@ class Engine:
         r.entries = bufs.get("entries")
         r.fail_count = bufs.get("fail_count")
         r.group_lol = bufs.get("group_lol")
+        r.history = bufs.get("history")
         if "ens" in bufs:
             raw["ens_fp_vector"] = bufs["ens"]
         return r
 
     def seq_mc(self, years: int, seed: int = 42, year0: int = 0, init_mode: int = INIT_STATIONARY,
                years_per_chain: int = 1, per_year: bool = False, fail_count: bool = False,
-               group: int = 0, keep_on_device: bool = False) -> SequentialIndices:
-        o, bufs = self._seq_outputs(years, per_year, fail_count, group, keep_on_device)
+               group: int = 0, keep_on_device: bool = False, history: int = 0) -> SequentialIndices:
+        if history and group and history != group:
+            raise ValueError("history and group must use the same cadence")
+        o, bufs = self._seq_outputs(years, per_year, fail_count, group, keep_on_device, history)
         s = _lib.SeqSummary()
         self._check(self._L.psra_seq_mc(self._h, year0, years, seed, init_mode, years_per_chain,
                                         C.byref(o), C.byref(s)))
@@ -243,9 +250,12 @@ class Engine:
         return self._seq_result(s, bufs)
 
     # ---- non-sequential MC
-    def _ns_outputs(self, n, per_sample, states, group):
+    def _ns_outputs(self, n, per_sample, states, group, history=0):
         o = _lib.NonseqOutputs()
         bufs = {}
+        if history:
+            bufs["history"] = np.zeros(n // history, dtype=np.float64)
+            o.history = _ptr(bufs["history"]); o.group = history
         if per_sample:
             bufs["lol_hours"] = np.zeros(n, dtype=np.uint32)
             bufs["ens"] = np.zeros(n, dtype=np.int64)
@@ -276,8 +286,8 @@ class Engine:
         return out
 
     def nonseq_mc(self, samples: int, seed: int = 42, sample0: int = 0, per_sample: bool = False,
-                  states: bool = False, group: int = 0):
-        o, bufs = self._ns_outputs(samples, per_sample, states, group)
+                  states: bool = False, group: int = 0, history: int = 0):
+        o, bufs = self._ns_outputs(samples, per_sample, states, group, history)
         s = _lib.NonseqSummary()
         self._check(self._L.psra_nonseq_mc(self._h, sample0, samples, seed, C.byref(o), C.byref(s)))
         return self._ns_result(s, bufs)
@@ -453,10 +463,8 @@ def run_non_sequential_mc(gens: Sequence[Generator], load: LoadModel, iterations
     eng = engine or default_engine()
     t0 = time.time()
     eng.set_generators(gens, load, fp_scale)
-    r = eng.nonseq_mc(iterations, seed=seed, group=100)
-    g = r["group_lol"][: iterations // 100]
-    hist = np.cumsum(g) / (100.0 * np.arange(1, len(g) + 1))
-    return ReliabilityResult("Non-Sequential MC", r["lole"], r["eue"], time.time() - t0, hist)
+    r = eng.nonseq_mc(iterations, seed=seed, history=100)
+    return ReliabilityResult("Non-Sequential MC", r["lole"], r["eue"], time.time() - t0, r["history"])
 
 
 def run_sequential_mc(gens: Sequence[Generator], load: LoadModel, years: int, seed: int = 42,
@@ -468,10 +476,8 @@ def run_sequential_mc(gens: Sequence[Generator], load: LoadModel, years: int, se
     eng = engine or default_engine()
     t0 = time.time()
     eng.set_generators(gens, load, fp_scale)
-    r = eng.seq_mc(years, seed=seed, year0=year0, init_mode=init_mode, years_per_chain=years_per_chain, group=10)
-    g = r.group_lol[: years // 10]
-    hist = np.cumsum(g) / (10.0 * np.arange(1, len(g) + 1))
-    res = ReliabilityResult("Sequential MC", r.lole, r.eens, time.time() - t0, hist)
+    r = eng.seq_mc(years, seed=seed, year0=year0, init_mode=init_mode, years_per_chain=years_per_chain, history=10)
+    res = ReliabilityResult("Sequential MC", r.lole, r.eens, time.time() - t0, r.history)
     return (res, r) if details else res
 
 

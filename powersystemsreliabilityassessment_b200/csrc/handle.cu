@@ -44,6 +44,41 @@ int psra_reserve_outputs(psra_handle *h, int64_t n)
     return PSRA_OK;
 }
 
+// running mean of the group sums: one block, each thread owns a contiguous chunk, block scan of the chunk totals
+__global__ void __launch_bounds__(1024) history_kernel(const long long *__restrict__ g, long long n, int group, double *__restrict__ out)
+{
+    __shared__ long long sh[1024];
+    const int t = threadIdx.x;
+    const long long chunk = (n + 1023) / 1024, lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    long long s = 0;
+    for (long long i = lo; i < hi; i++) s += g[i];
+    sh[t] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        long long v = 0;
+        if (t >= d) v = sh[t - d];
+        __syncthreads();
+        if (t >= d) sh[t] += v;
+        __syncthreads();
+    }
+    long long run = sh[t] - s;
+    for (long long i = lo; i < hi; i++) {
+        run += g[i];
+        out[i] = (double)run / ((double)group * (double)(i + 1));     // cum_lole / y, PSA.jl:203,264
+    }
+}
+
+int psra_history_to_host(psra_handle *h, const long long *d_group, int64_t nfull, int group, double *history)
+{
+    if (nfull <= 0) return PSRA_OK;
+    int rc = psra_reserve(h, &h->d_scratch2, &h->scratch2_cap, sizeof(double) * (size_t)nfull);
+    if (rc) return rc;
+    history_kernel<<<1, 1024, 0, h->stream>>>(d_group, nfull, group, (double *)h->d_scratch2);
+    PSRA_CUDA(h, cudaGetLastError());
+    PSRA_CUDA(h, cudaMemcpyAsync(history, h->d_scratch2, sizeof(double) * (size_t)nfull, cudaMemcpyDeviceToHost, h->stream));
+    return PSRA_OK;
+}
+
 extern "C" int psra_version(void) { return PSRA_VERSION; }
 
 extern "C" const char *psra_last_error(const psra_handle *h) { return h ? h->err : "null handle"; }

@@ -201,7 +201,7 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
         if (out->states) a.states = (uint32_t *)((unsigned char *)h->d_scratch2 + cap_bytes);
     }
     long long ngroups = 0;
-    if (out && out->group_lol) {
+    if (out && (out->group_lol || out->history)) {
         PSRA_REQUIRE(h, out->group >= 1, "group must be >= 1");
         a.group = out->group;
         ngroups = (n + a.group - 1) / a.group;
@@ -239,6 +239,10 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
         if (out->cap_avail) PSRA_CUDA(h, cudaMemcpyAsync(out->cap_avail, a.cap_out, cap_bytes, cudaMemcpyDeviceToHost, h->stream));
         if (out->states)    PSRA_CUDA(h, cudaMemcpyAsync(out->states, a.states, st_bytes, cudaMemcpyDeviceToHost, h->stream));
         if (out->group_lol) PSRA_CUDA(h, cudaMemcpyAsync(out->group_lol, h->d_group, sizeof(long long) * (size_t)ngroups, cudaMemcpyDeviceToHost, h->stream));
+        if (out->history) {
+            rc = psra_history_to_host(h, h->d_group, n / a.group, a.group, out->history);
+            if (rc) return rc;
+        }
     }
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     float ms = 0.f;

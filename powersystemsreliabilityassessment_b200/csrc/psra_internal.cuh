@@ -75,6 +75,8 @@ int psra_fail(psra_handle *h, int code, const char *fmt, ...);
 // grow-only device buffer helpers (host side)
 int psra_reserve(psra_handle *h, void **p, size_t *cap, size_t bytes);
 int psra_reserve_outputs(psra_handle *h, int64_t n);
+// running means cumsum(group sums)[k] / (group * (k+1)), k < nfull, into host buffer `history` (uses d_scratch2)
+int psra_history_to_host(psra_handle *h, const long long *d_group, int64_t nfull, int group, double *history);
 
 // ------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

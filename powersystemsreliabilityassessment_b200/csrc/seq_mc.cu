@@ -386,7 +386,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         a.fail = h->d_fail;
     }
     long long ngroups = 0;
-    if (out && out->group_lol) {
+    if (out && (out->group_lol || out->history)) {
         PSRA_REQUIRE(h, out->group >= 1, "group must be >= 1");
         a.group = out->group;
         ngroups = (nyears + a.group - 1) / a.group;
@@ -436,6 +436,10 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         if (out->entries)   PSRA_CUDA(h, cudaMemcpyAsync(out->entries, h->d_ent, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
         if (out->fail_count) PSRA_CUDA(h, cudaMemcpyAsync(out->fail_count, h->d_fail, sizeof(uint32_t) * (size_t)h->H, cudaMemcpyDeviceToHost, h->stream));
         if (out->group_lol) PSRA_CUDA(h, cudaMemcpyAsync(out->group_lol, h->d_group, sizeof(long long) * (size_t)ngroups, cudaMemcpyDeviceToHost, h->stream));
+        if (out->history) {
+            int rc = psra_history_to_host(h, h->d_group, nyears / a.group, a.group, out->history);
+            if (rc) return rc;
+        }
     }
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     float ms = 0.f;

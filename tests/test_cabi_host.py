@@ -26,9 +26,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Config) == 32
     assert ctypes.sizeof(_lib.SeqSummary) == 80
-    assert ctypes.sizeof(_lib.SeqOutputs) == 48
+    assert ctypes.sizeof(_lib.SeqOutputs) == 56
     assert ctypes.sizeof(_lib.NonseqSummary) == 64
-    assert ctypes.sizeof(_lib.NonseqOutputs) == 48
+    assert ctypes.sizeof(_lib.NonseqOutputs) == 56
     assert ctypes.sizeof(_lib.TailOut) == 40
     assert ctypes.sizeof(_lib.DetailedSystem) == 48
 

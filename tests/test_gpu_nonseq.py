@@ -59,6 +59,16 @@ def test_philox_bit_exact_and_sharding(engine, rts):
         assert g["raw"][k] == a["raw"][k] + b["raw"][k]
 
 
+def test_convergence_history_computed_on_device(engine, rts):
+    """running mean of LOL hours every 100 iterations (PSA.jl:202-204)."""
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(rts["load_int"])
+    for n in (100, 1234, 100_000):
+        g = engine.nonseq_mc(n, seed=5, per_sample=True, history=100)
+        k = n // 100
+        want = np.cumsum(g["lol_hours"][: 100 * k].astype(np.float64)).reshape(k, 100)[:, -1] / (100.0 * np.arange(1, k + 1))
+        assert g["history"].shape == (k,) and np.array_equal(g["history"], want)
+
+
 def test_philox_many_units(engine, rts):
     from powersystemsreliabilityassessment_b200 import rts79
     cap, mttf, mttr, load = rts79.synthetic_system(32, 37.0)

@@ -147,6 +147,23 @@ def test_sharding_invariance_and_segments(engine, rts):
             assert r2.raw["events"] == full.raw["events"]
 
 
+def test_convergence_history_computed_on_device(engine, rts):
+    """convergence_history = cum_lole / y every 10 years (PSA.jl:263-265); ragged tail years are dropped."""
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(rts["load_int"])
+    for years in (10, 37, 4096, 25_013):
+        r = engine.seq_mc(years, seed=11, per_year=True, history=10)
+        k = years // 10
+        want = np.cumsum(r.lol_hours[: 10 * k].astype(np.float64)).reshape(k, 10)[:, -1] / (10.0 * np.arange(1, k + 1))
+        assert r.history.shape == (k,) and np.array_equal(r.history, want)
+    assert engine.seq_mc(9, seed=11, history=10).history.shape == (0,)
+    import powersystemsreliabilityassessment_b200 as P
+    gens = [P.Generator(i + 1, c, f, m) for i, (c, f, m) in enumerate(zip(rts["cap"], rts["mttf"], rts["mttr"]))]
+    res = P.run_sequential_mc(gens, P.LoadModel(rts["load_int"].astype(np.float64)), 1000, seed=11, engine=engine)
+    ref = engine.seq_mc(1000, seed=11, per_year=True)
+    assert res.method == "Sequential MC" and len(res.convergence_history) == 100
+    assert res.convergence_history[-1] == ref.lol_hours.sum() / 1000.0 == res.lole_hours_yr
+
+
 def test_fast_and_generic_kernels_agree_in_chain_mode(engine, rts):
     """seq_fast.cu (wave / prefix-sum formulation) and seq_mc.cu (FP64 residual recurrence) are two
     independent implementations of the same chain; multi-year chains exercise the pending list."""
