@@ -53,7 +53,7 @@ __host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, boo
     const int halves = two_halves ? 2 : 1;
     size_t b = sizeof(FastWarpSmem) + (two_halves ? sizeof(uint32_t) * FAST_PEND_CAP : 0) +
                sizeof(uint32_t) * (size_t)halves * ev_cap +                          // event lists
-               3 * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);        // word sums, negative sums, list heads
+               3 * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);        // per word: {sum, negative sum, list head}
     return (b + 15) & ~(size_t)15;
 }
 
@@ -86,6 +86,28 @@ __device__ __forceinline__ void list_push_shared_if(uint32_t head_saddr, uint32_
                  :: "r"(head_saddr), "r"(ev_saddr), "r"(idx1), "r"(ent), "r"((int)p) : "memory");
 }
 
+
+// Single-segment scatter of one event (the whole chain is one timeline segment): if hour `hs` lies in the
+// year, add `delta` to the word's sum (and to its negative sum when the event takes the unit down, i.e.
+// when s0i == qodd), push the event onto the word's list and count it.  `wa` = shared address of the word
+// record {sum, negative sum, head}; the list slot idx1 - 1 is private to this lane (no compaction needed).
+__device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, uint32_t wa, int delta, uint32_t s0i, uint32_t qodd,
+                                                     uint32_t idx1, uint32_t ev_saddr, uint32_t ent, unsigned int &n_events)
+{
+    asm volatile("{\n .reg .pred p, pn;\n .reg .b32 nx;\n"
+                 " setp.lt.u32 p, %1, %2;\n"
+                 " setp.eq.and.u32 pn, %5, %6, p;\n"
+                 " @p red.shared.add.s32 [%3], %4;\n"
+                 " @pn red.shared.add.s32 [%3+4], %4;\n"
+                 " @p atom.shared.exch.b32 nx, [%3+8], %7;\n"
+                 " @p mad.lo.u32 nx, nx, 1048576, %9;\n"
+                 " @p st.shared.b32 [%8], nx;\n"
+                 " @p add.u32 %0, %0, 1;\n}\n"
+                 : "+r"(n_events)
+                 : "r"(hs), "r"(H), "r"(wa), "r"(delta), "r"(s0i), "r"(qodd), "r"(idx1), "r"(ev_saddr), "r"(ent)
+                 : "memory");
+}
+
 template <bool kDisc, bool kTwo>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
 {
@@ -111,9 +133,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                                                                   // 32-hour word form a linked list (next = 1 + index, 0 = end)
     const int seg_slots = a.seg_words * 32;
     const int ring_words = (halves * a.seg_words + 3) & ~3;
-    int32_t *wsum = reinterpret_cast<int32_t *>(evl + (size_t)halves * ev_cap);  // per 32-hour word: sum of deltas
-    int32_t *wneg = wsum + ring_words;                                          //                   sum of negative deltas
-    uint32_t *whead = reinterpret_cast<uint32_t *>(wneg + ring_words);          //                   1 + index of its newest event (0 = none)
+    // one 12-byte record per 32-hour word: sum of deltas, sum of negative deltas, 1 + index of its newest event (0 = none)
+    int32_t *wtab = reinterpret_cast<int32_t *>(evl + (size_t)halves * ev_cap);
+#define WSUM(i) wtab[3 * (i)]
+#define WNEG(i) wtab[3 * (i) + 1]
+#define WHEAD(i) (reinterpret_cast<uint32_t *>(wtab)[3 * (i) + 2])
 
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
         if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
@@ -126,9 +150,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
-    for (int i = lane; i < ring_words; i += 32) { wsum[i] = 0; wneg[i] = 0; whead[i] = 0u; }
-    const uint32_t wsum_s = (uint32_t)__cvta_generic_to_shared(wsum), wneg_s = (uint32_t)__cvta_generic_to_shared(wneg),
-                   whead_s = (uint32_t)__cvta_generic_to_shared(whead);
+    for (int i = lane; i < 3 * ring_words; i += 32) wtab[i] = 0;
+    const uint32_t wtab_s = (uint32_t)__cvta_generic_to_shared(wtab);
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
@@ -193,11 +216,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         if (take) {                       // pending events are beyond abs1: next half
                             const int c = s_cap[(e >> 1) & 31];
                             const uint32_t hseg = (uint32_t)(hs - abs1);
-                            atomicAdd(&wsum[wbase_nxt + (hseg >> 5)], (e & 1u) ? c : -c);
-                            if (!(e & 1u)) atomicAdd(&wneg[wbase_nxt + (hseg >> 5)], -c);
+                            atomicAdd(&WSUM(wbase_nxt + (hseg >> 5)), (e & 1u) ? c : -c);
+                            if (!(e & 1u)) atomicAdd(&WNEG(wbase_nxt + (hseg >> 5)), -c);
                             const int pos = cnt_nxt + __popc(tm & lt_mask);
                             if (pos < ev_cap) {
-                                const uint32_t nx = atomicExch(&whead[wbase_nxt + (hseg >> 5)], (uint32_t)(pos + 1));
+                                const uint32_t nx = atomicExch(&WHEAD(wbase_nxt + (hseg >> 5)), (uint32_t)(pos + 1));
                                 ev_nxt[pos] = (nx << 20) | (hseg << 6) | (e & 63u);
                             }
                         }
@@ -233,10 +256,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     int off_m, J1;
                     count_scan(n_m, off_m, J1);
                     if (J1 < 32 && !init_wave) {       // spare lanes: one more block of slack for the short units
-                        const int n_x = is_short ? min(FAST_NB_MAX, want + 1) : 0;
-                        int off_x, Jx;
-                        count_scan(n_x, off_x, Jx);
-                        if (Jx <= 32) { n_m = n_x; off_m = off_x; J1 = Jx; }
+                        const bool extra = is_short && want < FAST_NB_MAX;
+                        const uint32_t bx = __ballot_sync(0xffffffffu, extra);
+                        const int Jx = J1 + __popc(bx);
+                        if (Jx <= 32) { n_m += extra ? 1 : 0; off_m += __popc(bx & lt_mask); J1 = Jx; }
                     }
                     int n_u, off, J;
                     if (J1 >= 32 || init_wave || !two_halves) {     // truncate; the remaining demand is served by the next wave
@@ -293,46 +316,69 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const int delta_a = s0u ? cu : -cu;      // draws 0, 2 toggle the unit back to s0
                         if (b == 0u && act) s0mask = s0u ? 1u : 0u;   // init wave (job lane == unit lane), ballot below
                         // hour of an event at tick T: ceil(T / 2^24) - 1 = (T - 1) >> 24 (fits 32 bits: T < 2^56)
-                        const unsigned long long bm1 = base_t - 1ull;
+                        if constexpr (!kTwo) {
+                            // whole chain = one segment: hour in segment = hour in year, ring = year.  Job lane j of a wave
+                            // of J jobs owns the list slots cnt + q*J + j, q = 0..3 (holes of out-of-year events are never linked)
+                            const bool room = cnt_cur + 4 * J <= ev_cap;              // warp-uniform
+                            // lanes without a job (and a full list) are parked far beyond the year
+                            const unsigned long long bm1 = (act && room) ? base_t - 1ull : (0x00800000ull << 32);
+                            const uint32_t s0i = s0u ? 1u : 0u;
+                            uint32_t idx1 = (uint32_t)cnt_cur + (uint32_t)lane + 1u;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
-                            const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
-                            const bool valid = act && !(b == 0u && q == 0);
-                            const uint32_t rel = hs - (uint32_t)abs0;          // >= 0: events are never generated backwards
-                            const int delta = (q & 1) ? -delta_a : delta_a;
-                            const bool in_ring = valid && rel < ring_len;      // ring_len stops at the chain end
-                            const bool in_cur = in_ring && rel < len_cur;
-                            const bool in_nxt = in_ring && !in_cur;
-                            const uint32_t hseg = in_cur ? rel : rel - len_cur;  // hour within its segment
-                            const uint32_t w4 = 4u * ((in_cur ? (uint32_t)wbase_cur : (uint32_t)wbase_nxt) + (hseg >> 5));
-                            red_add_shared_if(wsum_s + w4, delta, in_ring);
-                            red_add_shared_if(wneg_s + w4, delta, in_ring && delta < 0);
-                            const uint32_t ent = (hseg << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
-                            const uint32_t mc = __ballot_sync(0xffffffffu, in_cur);
-                            {
-                                const uint32_t pos = (uint32_t)cnt_cur + __popc(mc & lt_mask);
-                                list_push_shared_if(whead_s + w4, evcur_s + 4u * pos, pos + 1u, ent, in_cur && pos < (uint32_t)ev_cap);
+                            for (int q = 0; q < 4; q++) {
+                                unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
+                                if (q == 0 && b == 0u) tm1 = 0x00800000ull << 32;     // draw 0 of a stream is the initial state
+                                const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
+                                const int delta = (q & 1) ? -delta_a : delta_a;
+                                // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
+                                scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), delta, s0i, (uint32_t)(q & 1), idx1,
+                                                     evcur_s + 4u * idx1 - 4u, (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1))), n_events);
+                                idx1 += (uint32_t)J;
                             }
-                            cnt_cur += __popc(mc);
-                            if (two_halves) {
-                                const uint32_t mn = __ballot_sync(0xffffffffu, in_nxt);
-                                const uint32_t pos = (uint32_t)cnt_nxt + __popc(mn & lt_mask);
-                                list_push_shared_if(whead_s + w4, evnxt_s + 4u * pos, pos + 1u, ent, in_nxt && pos < (uint32_t)ev_cap);
-                                cnt_nxt += __popc(mn);
-                            }
-                            const bool inhor = valid && hs < (uint32_t)chain_end_h;
-                            if (two_halves) {                              // events beyond the ring (a single segment has none)
-                                const bool pnd = inhor && !in_ring;
-                                const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
-                                if (pm) {
-                                    const int pos = pend_cnt + __popc(pm & lt_mask);
-                                    if (pnd && pos < FAST_PEND_CAP)
-                                        pend[pos] = (hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
-                                    pend_cnt += __popc(pm);
+                            cnt_cur += 4 * J;
+                            if (!room) cnt_cur = ev_cap + 1;                          // reported as PSRA_E_OVERFLOW below
+                        } else {
+                            const unsigned long long bm1 = base_t - 1ull;
+    #pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
+                                const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
+                                const bool valid = act && !(b == 0u && q == 0);
+                                const uint32_t rel = hs - (uint32_t)abs0;          // >= 0: events are never generated backwards
+                                const int delta = (q & 1) ? -delta_a : delta_a;
+                                const bool in_ring = valid && rel < ring_len;      // ring_len stops at the chain end
+                                const bool in_cur = in_ring && rel < len_cur;
+                                const bool in_nxt = in_ring && !in_cur;
+                                const uint32_t hseg = in_cur ? rel : rel - len_cur;  // hour within its segment
+                                const uint32_t wa = wtab_s + 12u * ((in_cur ? (uint32_t)wbase_cur : (uint32_t)wbase_nxt) + (hseg >> 5));
+                                red_add_shared_if(wa, delta, in_ring);
+                                red_add_shared_if(wa + 4u, delta, in_ring && delta < 0);
+                                const uint32_t ent = (hseg << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
+                                const uint32_t mc = __ballot_sync(0xffffffffu, in_cur);
+                                {
+                                    const uint32_t pos = (uint32_t)cnt_cur + __popc(mc & lt_mask);
+                                    list_push_shared_if(wa + 8u, evcur_s + 4u * pos, pos + 1u, ent, in_cur && pos < (uint32_t)ev_cap);
                                 }
+                                cnt_cur += __popc(mc);
+                                if (two_halves) {
+                                    const uint32_t mn = __ballot_sync(0xffffffffu, in_nxt);
+                                    const uint32_t pos = (uint32_t)cnt_nxt + __popc(mn & lt_mask);
+                                    list_push_shared_if(wa + 8u, evnxt_s + 4u * pos, pos + 1u, ent, in_nxt && pos < (uint32_t)ev_cap);
+                                    cnt_nxt += __popc(mn);
+                                }
+                                const bool inhor = valid && hs < (uint32_t)chain_end_h;
+                                if (two_halves) {                              // events beyond the ring (a single segment has none)
+                                    const bool pnd = inhor && !in_ring;
+                                    const uint32_t pm = __ballot_sync(0xffffffffu, pnd);
+                                    if (pm) {
+                                        const int pos = pend_cnt + __popc(pm & lt_mask);
+                                        if (pnd && pos < FAST_PEND_CAP)
+                                            pend[pos] = (hs << 6) | ((uint32_t)u << 1) | (delta > 0 ? 1u : 0u);
+                                        pend_cnt += __popc(pm);
+                                    }
+                                }
+                                n_events += inhor ? 1u : 0u;
                             }
-                            n_events += inhor ? 1u : 0u;
                         }
                         __syncwarp();
                     }
@@ -365,8 +411,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 for (int k = 0; k < wpl; k++) {
                     const int w = wb + k;
                     if (w < nwords) {
-                        lmin = min(lmin, loc + wneg[wbase_cur + w] - s_lmax[seg * a.seg_words + w]);
-                        loc += wsum[wbase_cur + w];
+                        lmin = min(lmin, loc + WNEG(wbase_cur + w) - s_lmax[seg * a.seg_words + w]);
+                        loc += WSUM(wbase_cur + w);
                     }
                 }
                 const int incl = warp_incl_scan(loc, lane);
@@ -383,10 +429,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     bool wflag = false;
                     {
                         const int wq = src * wpl + lane;
-                        if (lane < wpl && wq < nwords) {
-                            for (int j = 0; j < lane; j++) c_word += wsum[wbase_cur + src * wpl + j];
-                            wflag = c_word + wneg[wbase_cur + wq] < s_lmax[seg * a.seg_words + wq];
+                        const bool mine = lane < wpl && wq < nwords;
+                        const int ws_l = mine ? WSUM(wbase_cur + wq) : 0;
+                        int ws_i = ws_l;                                  // a run has <= 16 words (seg_words <= 512)
+#pragma unroll
+                        for (int d = 1; d < 16; d <<= 1) {
+                            const int o = __shfl_up_sync(0xffffffffu, ws_i, d);
+                            if (lane >= d) ws_i += o;
                         }
+                        c_word += ws_i - ws_l;
+                        if (mine) wflag = c_word + WNEG(wbase_cur + wq) < s_lmax[seg * a.seg_words + wq];
                     }
                     uint32_t wm = __ballot_sync(0xffffffffu, wflag);
                     while (wm) {                                 // resolve the word hour by hour, lane = hour
@@ -395,7 +447,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                         const int wq = src * wpl + k;
                         const int c_in = __shfl_sync(0xffffffffu, c_word, k);
                         int d = 0;                               // delta of hour `lane` of the word: walk its event list
-                        for (uint32_t i = whead[wbase_cur + wq]; i; ) {
+                        for (uint32_t i = WHEAD(wbase_cur + wq); i; ) {
                             const uint32_t e = ev_cur[i - 1];
                             if (((e >> 6) & 31u) == (uint32_t)lane) {
                                 const int c = s_cap[(e >> 1) & 31];
@@ -422,7 +474,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 capacity += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
                 // clear the evaluated half: word sums to zero, event list empty
-                for (int i = lane; i < nwords; i += 32) { wsum[wbase_cur + i] = 0; wneg[wbase_cur + i] = 0; whead[wbase_cur + i] = 0u; }
+                for (int i = lane; i < 3 * nwords; i += 32) wtab[3 * wbase_cur + i] = 0;
                 if (ring) { ev_cnt1 = 0; ev_cnt0 = cnt_nxt; } else { ev_cnt0 = 0; ev_cnt1 = cnt_nxt; }
                 __syncwarp();
                 if (!two_halves) ring ^= 1;                      // single half: undo the toggle of the loop header
