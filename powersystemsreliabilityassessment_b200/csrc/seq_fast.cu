@@ -87,24 +87,29 @@ __device__ __forceinline__ void list_push_shared_if(uint32_t head_saddr, uint32_
 }
 
 
-// Single-segment scatter of one event (the whole chain is one timeline segment): if hour `hs` lies in the
-// year, add `delta` to the word's sum (and to its negative sum when the event takes the unit down, i.e.
-// when s0i == qodd), push the event onto the word's list and count it.  `wa` = shared address of the word
-// record {sum, negative sum, head}; the list slot idx1 - 1 is private to this lane (no compaction needed).
+// Single-segment scatter of one event (the whole chain is one timeline segment).  If hour `hs` lies in the
+// year: add `delta` to the word's sum (and to its negative sum when the event takes the unit down, i.e. when
+// s0i == qodd), push the event onto the word's list and count it.  `wa` = shared address of the word record
+// {sum, negative sum, head}; the list slot at `evm + 8` is private to this lane.  ptxas turns predicated
+// shared atomics into branches, so the atomics are unconditional instead: an out-of-year event adds 0 and
+// exchanges with its own (never linked) list slot.
 __device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, uint32_t wa, int delta, uint32_t s0i, uint32_t qodd,
-                                                     uint32_t idx1, uint32_t ev_saddr, uint32_t ent, unsigned int &n_events)
+                                                     uint32_t idx1, uint32_t evm, uint32_t ent, unsigned int &n_events)
 {
-    asm volatile("{\n .reg .pred p, pn;\n .reg .b32 nx;\n"
+    asm volatile("{\n .reg .pred p, pn;\n .reg .b32 nx, d0, d1, hb;\n"
                  " setp.lt.u32 p, %1, %2;\n"
                  " setp.eq.and.u32 pn, %5, %6, p;\n"
-                 " @p red.shared.add.s32 [%3], %4;\n"
-                 " @pn red.shared.add.s32 [%3+4], %4;\n"
-                 " @p atom.shared.exch.b32 nx, [%3+8], %7;\n"
-                 " @p mad.lo.u32 nx, nx, 1048576, %9;\n"
-                 " @p st.shared.b32 [%8], nx;\n"
+                 " selp.b32 d0, %4, 0, p;\n"
+                 " selp.b32 d1, %4, 0, pn;\n"
+                 " selp.b32 hb, %3, %8, p;\n"
+                 " red.shared.add.s32 [hb], d0;\n"
+                 " red.shared.add.s32 [hb+4], d1;\n"
+                 " atom.shared.exch.b32 nx, [hb+8], %7;\n"
+                 " mad.lo.u32 nx, nx, 1048576, %9;\n"
+                 " st.shared.b32 [%8+8], nx;\n"
                  " @p add.u32 %0, %0, 1;\n}\n"
                  : "+r"(n_events)
-                 : "r"(hs), "r"(H), "r"(wa), "r"(delta), "r"(s0i), "r"(qodd), "r"(idx1), "r"(ev_saddr), "r"(ent)
+                 : "r"(hs), "r"(H), "r"(wa), "r"(delta), "r"(s0i), "r"(qodd), "r"(idx1), "r"(evm), "r"(ent)
                  : "memory");
 }
 
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                 const int delta = (q & 1) ? -delta_a : delta_a;
                                 // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
                                 scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), delta, s0i, (uint32_t)(q & 1), idx1,
-                                                     evcur_s + 4u * idx1 - 4u, (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1))), n_events);
+                                                     evcur_s + 4u * idx1 - 12u, (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1))), n_events);
                                 idx1 += (uint32_t)J;
                             }
                             cnt_cur += 4 * J;
