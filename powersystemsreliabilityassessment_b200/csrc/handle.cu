@@ -161,11 +161,13 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     std::vector<uint32_t> thr(U);
     std::vector<double> q(U);
     int64_t total = 0;
+    int32_t max_unit = 0;
     double rate = 0.0;
     for (int u = 0; u < U; u++) {
         PSRA_REQUIRE(h, cap_fp[u] >= 0, "negative capacity");
         PSRA_REQUIRE(h, mttf_h[u] > 0 && mttr_h[u] > 0, "MTTF / MTTR must be positive");
         total += cap_fp[u];
+        if (cap_fp[u] > max_unit) max_unit = cap_fp[u];
         rate += 2.0 / (mttf_h[u] + mttr_h[u]);
         mf[u] = (float)mttf_h[u];
         mr[u] = (float)mttr_h[u];
@@ -196,6 +198,7 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     h->U = U;
     h->total_cap = total;
+    h->max_unit_cap = max_unit;
     h->events_per_hour = rate;
     h->tab_valid = false;
     return PSRA_OK;

@@ -28,6 +28,7 @@ struct psra_handle {
     // system (device)
     int U = 0;
     int64_t total_cap = 0;
+    int32_t max_unit_cap = 0;
     double events_per_hour = 0.0;    // sum over units of 2 / (MTTF + MTTR): expected state transitions per hour
     int32_t *d_cap = nullptr;        // [U]
     float *d_mttf = nullptr;         // [U] binary32 means used by the sampler

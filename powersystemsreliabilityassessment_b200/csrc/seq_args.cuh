@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 struct SeqArgs {
-    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves;
+    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves, pack_shift;
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
     const int32_t *load; const int32_t *lmax;
     uint32_t k0, k1;
@@ -20,9 +20,9 @@ struct SeqArgs {
 #define PSRA_TICK_SHIFT 24
 
 // seq_fast.cu
-size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_cap, bool two_halves, bool load16);
-int seq_fast_max_threads();
-cudaError_t seq_fast_prepare(bool disc, bool two, size_t smem, int threads, int *blocks_per_sm);
+size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_cap, bool two_halves, bool load16, bool pack);
+int seq_fast_max_threads(bool two_halves);
+cudaError_t seq_fast_prepare(bool disc, bool two, bool pack, size_t smem, int threads, int *blocks_per_sm);
 void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);
 
 // seq_team.cu

@@ -36,9 +36,8 @@
 
 #define FAST_NB_MAX 4                  // Philox blocks a unit may get per wave
 #define FAST_PEND_CAP 256              // far-future events (beyond the two-segment ring)
-#ifndef FAST_MAX_THREADS
-#define FAST_MAX_THREADS 896
-#endif
+// single-segment variants run 32 warps per SM (<= 64 registers); the ring variants need a few more registers
+#define FAST_MAX_THREADS(two) ((two) ? 896 : 1024)
 
 struct FastWarpSmem {                  // per-warp scratch that precedes the event lists
     unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit
@@ -48,12 +47,13 @@ struct FastWarpSmem {                  // per-warp scratch that precedes the eve
 };
 
 // two_halves: the ring needs its second half (several segments per year, or multi-year chains)
-__host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, bool two_halves)
+// pack: the word's sum and negative sum share one 32-bit integer (single-segment mode only)
+__host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, bool two_halves, bool pack)
 {
     const int halves = two_halves ? 2 : 1;
     size_t b = sizeof(FastWarpSmem) + (two_halves ? sizeof(uint32_t) * FAST_PEND_CAP : 0) +
                sizeof(uint32_t) * (size_t)halves * ev_cap +                          // event lists
-               3 * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);        // per word: {sum, negative sum, list head}
+               (pack ? 2 : 3) * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);   // per word: {sum, negative sum, list head}
     return (b + 15) & ~(size_t)15;
 }
 
@@ -64,12 +64,12 @@ __host__ __device__ inline size_t fast_block_bytes(int Wd, bool load16)
     return (b + 15) & ~(size_t)15;
 }
 
-size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_cap, bool two_halves, bool load16)
+size_t seq_fast_smem_bytes(int Wd, int seg_words, int warps_per_block, int ev_cap, bool two_halves, bool load16, bool pack)
 {
-    return fast_block_bytes(Wd, load16) + (size_t)warps_per_block * fast_warp_bytes(seg_words, ev_cap, two_halves);
+    return fast_block_bytes(Wd, load16) + (size_t)warps_per_block * fast_warp_bytes(seg_words, ev_cap, two_halves, pack);
 }
 
-int seq_fast_max_threads() { return FAST_MAX_THREADS; }
+int seq_fast_max_threads(bool two_halves) { return FAST_MAX_THREADS(two_halves); }
 
 // predicated shared-memory updates (inline PTX keeps them branch-free in SASS)
 __device__ __forceinline__ void red_add_shared_if(uint32_t saddr, int v, bool p)
@@ -113,8 +113,27 @@ __device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, ui
                  : "memory");
 }
 
-template <bool kDisc, bool kTwo>
-__global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const SeqArgs a)
+// Packed variant: the record is {sum + 2^K * negative sum, head}; `delta` already carries both fields
+// (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.
+__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wa, int delta,
+                                                     uint32_t idx1, uint32_t evm, uint32_t ent, unsigned int &n_events)
+{
+    asm volatile("{\n .reg .pred p;\n .reg .b32 nx, d0, hb;\n"
+                 " setp.lt.u32 p, %1, %2;\n"
+                 " selp.b32 d0, %4, 0, p;\n"
+                 " selp.b32 hb, %3, %6, p;\n"
+                 " red.shared.add.s32 [hb], d0;\n"
+                 " atom.shared.exch.b32 nx, [hb+4], %5;\n"
+                 " mad.lo.u32 nx, nx, 1048576, %7;\n"
+                 " st.shared.b32 [%6+4], nx;\n"
+                 " @p add.u32 %0, %0, 1;\n}\n"
+                 : "+r"(n_events)
+                 : "r"(hs), "r"(H), "r"(wa), "r"(delta), "r"(idx1), "r"(evm), "r"(ent)
+                 : "memory");
+}
+
+template <bool kDisc, bool kTwo, bool kPack>
+__global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(const SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -131,18 +150,29 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     constexpr bool two_halves = kTwo;     // the ring needs its second half (several segments per year or multi-year chains)
     const int halves = two_halves ? 2 : 1;
     const int ev_cap = a.ev_cap;
-    unsigned char *wbase = smem_raw + fast_block_bytes(a.Wd, load16) + (size_t)warp * fast_warp_bytes(a.seg_words, ev_cap, two_halves);
+    unsigned char *wbase = smem_raw + fast_block_bytes(a.Wd, load16) + (size_t)warp * fast_warp_bytes(a.seg_words, ev_cap, two_halves, kPack);
     FastWarpSmem *ws = reinterpret_cast<FastWarpSmem *>(wbase);
     uint32_t *pend = reinterpret_cast<uint32_t *>(wbase + sizeof(FastWarpSmem));  // (hour << 6) | (unit << 1) | (delta > 0)
     uint32_t *evl = pend + (two_halves ? FAST_PEND_CAP : 0);                      // [halves][ev_cap]: (next << 20) | (hour in segment << 6) | (unit << 1) | sign; the events of a
                                                                                   // 32-hour word form a linked list (next = 1 + index, 0 = end)
     const int seg_slots = a.seg_words * 32;
     const int ring_words = (halves * a.seg_words + 3) & ~3;
-    // one 12-byte record per 32-hour word: sum of deltas, sum of negative deltas, 1 + index of its newest event (0 = none)
+    // one record per 32-hour word: sum of deltas, sum of negative deltas, 1 + index of its newest event (0 = none).
+    // kPack: the two sums share one integer v = (sum + 2^(K-1)) + 2^K * neg: |sum| < 2^(K-1), so the biased low field
+    // stays in [0, 2^K) and both fields decode with one mask / one shift; the host proves neg > -2^(31-K) for any
+    // list that fits ev_cap.
+    static_assert(!(kPack && kTwo), "packed word records are a single-segment feature");
+    constexpr int RS = kPack ? 2 : 3;
+    const int pk = a.pack_shift;
+    const int pk_bias = kPack ? (1 << (pk - 1)) : 0, pk_mask = (1 << pk) - 1;
     int32_t *wtab = reinterpret_cast<int32_t *>(evl + (size_t)halves * ev_cap);
+    auto word_sums = [&](int i, int &sm, int &ng) {
+        if constexpr (kPack) { const int v = wtab[RS * i]; sm = (v & pk_mask) - pk_bias; ng = v >> pk; }
+        else { sm = wtab[RS * i]; ng = wtab[RS * i + 1]; }
+    };
 #define WSUM(i) wtab[3 * (i)]
 #define WNEG(i) wtab[3 * (i) + 1]
-#define WHEAD(i) (reinterpret_cast<uint32_t *>(wtab)[3 * (i) + 2])
+#define WHEAD(i) (reinterpret_cast<uint32_t *>(wtab)[RS * (i) + RS - 1])
 
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
         if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
@@ -155,7 +185,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
         s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
     }
-    for (int i = lane; i < 3 * ring_words; i += 32) wtab[i] = 0;
+    for (int i = lane; i < RS * ring_words; i += 32) wtab[i] = (kPack && !(i & 1)) ? pk_bias : 0;
     const uint32_t wtab_s = (uint32_t)__cvta_generic_to_shared(wtab);
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
@@ -329,6 +359,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             const unsigned long long bm1 = (act && room) ? base_t - 1ull : (0x00800000ull << 32);
                             const uint32_t s0i = s0u ? 1u : 0u;
                             uint32_t idx1 = (uint32_t)cnt_cur + (uint32_t)lane + 1u;
+                            const int dn_pk = -cu - (cu << pk);                       // kPack: a down event in both fields
+                            const int pk_a = s0u ? cu : dn_pk, pk_b = s0u ? dn_pk : cu;
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
                                 unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
@@ -336,8 +368,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                                 const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
                                 const int delta = (q & 1) ? -delta_a : delta_a;
                                 // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
-                                scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), delta, s0i, (uint32_t)(q & 1), idx1,
-                                                     evcur_s + 4u * idx1 - 12u, (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1))), n_events);
+                                const uint32_t ent = (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1)));
+                                if constexpr (kPack)
+                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s + 8u * (hs >> 5), (q & 1) ? pk_b : pk_a, idx1,
+                                                         evcur_s + 4u * idx1 - 8u, ent, n_events);
+                                else
+                                    scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), delta, s0i, (uint32_t)(q & 1), idx1,
+                                                         evcur_s + 4u * idx1 - 12u, ent, n_events);
                                 idx1 += (uint32_t)J;
                             }
                             cnt_cur += 4 * J;
@@ -416,8 +453,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 for (int k = 0; k < wpl; k++) {
                     const int w = wb + k;
                     if (w < nwords) {
-                        lmin = min(lmin, loc + WNEG(wbase_cur + w) - s_lmax[seg * a.seg_words + w]);
-                        loc += WSUM(wbase_cur + w);
+                        int sm, ng;
+                        word_sums(wbase_cur + w, sm, ng);
+                        lmin = min(lmin, loc + ng - s_lmax[seg * a.seg_words + w]);
+                        loc += sm;
                     }
                 }
                 const int incl = warp_incl_scan(loc, lane);
@@ -435,7 +474,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                     {
                         const int wq = src * wpl + lane;
                         const bool mine = lane < wpl && wq < nwords;
-                        const int ws_l = mine ? WSUM(wbase_cur + wq) : 0;
+                        int ws_l = 0, wn_l = 0;
+                        if (mine) word_sums(wbase_cur + wq, ws_l, wn_l);
                         int ws_i = ws_l;                                  // a run has <= 16 words (seg_words <= 512)
 #pragma unroll
                         for (int d = 1; d < 16; d <<= 1) {
@@ -443,7 +483,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                             if (lane >= d) ws_i += o;
                         }
                         c_word += ws_i - ws_l;
-                        if (mine) wflag = c_word + WNEG(wbase_cur + wq) < s_lmax[seg * a.seg_words + wq];
+                        if (mine) wflag = c_word + wn_l < s_lmax[seg * a.seg_words + wq];
                     }
                     uint32_t wm = __ballot_sync(0xffffffffu, wflag);
                     while (wm) {                                 // resolve the word hour by hour, lane = hour
@@ -479,7 +519,14 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
                 capacity += __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
                 // clear the evaluated half: word sums to zero, event list empty
-                for (int i = lane; i < 3 * nwords; i += 32) wtab[3 * wbase_cur + i] = 0;
+                if constexpr (!kTwo) {      // the table is 16-byte aligned and padded to a multiple of four records
+                    uint4 *t4 = reinterpret_cast<uint4 *>(wtab);
+                    const int n4 = (RS * ((nwords + 3) & ~3)) >> 2;
+                    const uint4 z = kPack ? make_uint4((uint32_t)pk_bias, 0u, (uint32_t)pk_bias, 0u) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = lane; i < n4; i += 32) t4[i] = z;
+                } else {
+                    for (int i = lane; i < RS * nwords; i += 32) wtab[RS * wbase_cur + i] = 0;
+                }
                 if (ring) { ev_cnt1 = 0; ev_cnt0 = cnt_nxt; } else { ev_cnt0 = 0; ev_cnt1 = cnt_nxt; }
                 __syncwarp();
                 if (!two_halves) ring ^= 1;                      // single half: undo the toggle of the loop header
@@ -528,15 +575,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1) seq_fast_kernel(const Seq
     }
 }
 
-static const void *fast_kernel_ptr(bool disc, bool two)
+static const void *fast_kernel_ptr(bool disc, bool two, bool pack)
 {
-    if (two) return disc ? (const void *)seq_fast_kernel<true, true> : (const void *)seq_fast_kernel<false, true>;
-    return disc ? (const void *)seq_fast_kernel<true, false> : (const void *)seq_fast_kernel<false, false>;
+    if (two) return disc ? (const void *)seq_fast_kernel<true, true, false> : (const void *)seq_fast_kernel<false, true, false>;
+    if (pack) return disc ? (const void *)seq_fast_kernel<true, false, true> : (const void *)seq_fast_kernel<false, false, true>;
+    return disc ? (const void *)seq_fast_kernel<true, false, false> : (const void *)seq_fast_kernel<false, false, false>;
 }
 
-cudaError_t seq_fast_prepare(bool disc, bool two, size_t smem, int threads, int *blocks_per_sm)
+cudaError_t seq_fast_prepare(bool disc, bool two, bool pack, size_t smem, int threads, int *blocks_per_sm)
 {
-    const void *k = fast_kernel_ptr(disc, two);
+    const void *k = fast_kernel_ptr(disc, two, pack);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem);
@@ -545,5 +593,5 @@ cudaError_t seq_fast_prepare(bool disc, bool two, size_t smem, int threads, int 
 void seq_fast_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
 {
     void *args[] = {(void *)&a};
-    cudaLaunchKernel(fast_kernel_ptr(a.disc != 0, a.two_halves != 0), dim3(grid), dim3(threads), args, smem, stream);
+    cudaLaunchKernel(fast_kernel_ptr(a.disc != 0, a.two_halves != 0, a.pack_shift != 0), dim3(grid), dim3(threads), args, smem, stream);
 }

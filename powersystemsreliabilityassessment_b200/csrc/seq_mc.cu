@@ -341,12 +341,23 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     a.pend_cap = seq_team_pend_cap(h->U);
     a.two_halves = (a.nseg > 1 || ypc > 1) ? 1 : 0;
     a.ev_cap = ev_cap_for(seg_words);
+    // seq_fast.cu single-segment mode: the word's sum and negative sum share one int32 (sum + 2^K * neg) when
+    // |sum| <= installed capacity < 2^(K-1) and neg > -2^(31-K).  A list of ev_cap entries holds at most
+    // (ev_cap + U) / 2 + 1 down events (the events of a unit alternate), so the bound below makes a silent
+    // overflow impossible: the list overflow (PSRA_E_OVERFLOW) would trigger first.
+    a.pack_shift = 0;
+    if (fast && !a.two_halves && !h->cfg.reserved[1]) {
+        int K = 2;
+        while ((1ll << (K - 1)) <= h->total_cap) K++;
+        const long long worst = ((long long)(a.ev_cap + h->U) / 2 + 1) * (long long)h->max_unit_cap;
+        if (K <= 20 && worst < (1ll << (31 - K))) a.pack_shift = K;
+    }
     if (fast && a.ev_cap > 2016)
         return psra_fail(h, PSRA_E_INVALID, "unit transition rate too high for the sampler kernel (%d events per 32-hour word)", a.ev_cap);
-    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 28 : 16);
-    wpb = std::max(1, std::min(fast ? seq_fast_max_threads() / 32 : 16, wpb));
+    int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 32 : 16);
+    wpb = std::max(1, std::min(fast ? seq_fast_max_threads(a.two_halves != 0) / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
-        if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16);
+        if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16, a.pack_shift != 0);
         if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words, a.two_halves != 0);
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
@@ -408,7 +419,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     else          kern = one_unit ? seq_mc_kernel<false, true> : seq_mc_kernel<false, false>;
     int bps = 0;
     if (fast) {
-        PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, a.two_halves != 0, smem, wpb * 32, &bps));
+        PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, a.two_halves != 0, a.pack_shift != 0, smem, wpb * 32, &bps));
     } else if (team) {
         PSRA_CUDA(h, seq_team_prepare(smem, &bps));
     } else {

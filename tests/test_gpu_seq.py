@@ -135,9 +135,10 @@ def test_sharding_invariance_and_segments(engine, rts):
     assert np.array_equal(full.raw["ens_fp_vector"], np.concatenate([a.raw["ens_fp_vector"], b.raw["ens_fp_vector"]]))
     for k in ("sum_lol_hours", "sum_ens_fp", "sum_entries", "sum_lol_sq", "sum_ens_sq", "years_with_loss"):
         assert full.raw[k] == a.raw[k] + b.raw[k]
-    for seg, wpb, gen in ((8736, 4, False), (1120, 16, False), (320, 8, False), (32, 2, False), (2208, 24, False),
-                          (8736, 4, True), (1120, 16, True), (320, 8, True)):
-        with Engine(seg_hours=seg, warps_per_block=wpb, force_generic=gen) as e2:
+    for seg, wpb, gen, unp in ((8736, 4, False, False), (1120, 16, False, False), (320, 8, False, False), (32, 2, False, False),
+                               (2208, 24, False, False), (8736, 4, True, False), (1120, 16, True, False), (320, 8, True, False),
+                               (8736, 32, False, True), (8736, 7, False, True)):
+        with Engine(seg_hours=seg, warps_per_block=wpb, force_generic=gen, unpacked_words=unp) as e2:
             e2.set_system(rts["cap"], rts["mttf"], rts["mttr"]); e2.set_load(rts["load_int"])
             r2 = e2.seq_mc(4096, seed=5, per_year=True, group=10)
             assert np.array_equal(full.lol_hours, r2.lol_hours)
