@@ -54,7 +54,9 @@ typedef struct psra_config {
     int32_t blocks_per_sm;    /* 0 = as many as fit */
     int32_t reserved[4];      /* reserved[0] != 0: force the generic sequential kernel (seq_mc.cu) also
                                  for systems of <= 32 units (cross-checks; the default picks seq_fast.cu);
-                                 reserved[1] != 0: seq_fast.cu keeps the word sums unpacked (cross-checks) */
+                                 reserved[1] != 0: seq_fast.cu keeps the word sums unpacked (cross-checks);
+                                 reserved[2] != 0: systems of > 32 units use seq_team.cu also where seq_wide.cu
+                                 applies (cross-checks) */
 } psra_config;
 
 /* lifetime ------------------------------------------------------------------------- */

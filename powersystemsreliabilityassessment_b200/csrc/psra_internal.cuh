@@ -34,6 +34,7 @@ struct psra_handle {
     float *d_mttf = nullptr;         // [U] binary32 means used by the sampler
     float *d_mttr = nullptr;
     uint32_t *d_for_thr = nullptr;   // [U] floor(FOR * 2^32)
+    int32_t *d_order = nullptr;      // [U] unit indices, most transitions per hour first
     double *d_for = nullptr;         // [U] FOR in FP64 (injected-uniform path, PSA.jl:183)
     // load (device)
     int H = 0;

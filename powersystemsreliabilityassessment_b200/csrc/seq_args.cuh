@@ -7,6 +7,7 @@ struct SeqArgs {
     int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves, pack_shift;
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
     const int32_t *load; const int32_t *lmax;
+    const int32_t *order;   // units sorted by decreasing transition rate (seq_wide.cu work queue)
     uint32_t k0, k1;
     long long chain_base;   // absolute index of local chain 0 (Philox counter)
     long long nchains;
@@ -32,3 +33,9 @@ int seq_team_max_units();
 cudaError_t seq_team_prepare(size_t smem, int *blocks_per_sm);
 void seq_team_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t stream);
 #define SEQ_TEAM_WARPS 8
+
+// seq_wide.cu
+size_t seq_wide_smem_bytes(int Wd);
+int seq_wide_threads();
+cudaError_t seq_wide_prepare(size_t smem, int *blocks_per_sm);
+void seq_wide_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t stream);

@@ -304,9 +304,13 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0];
     const bool team = !injected && !one_unit && h->U <= seq_team_max_units() && (long long)ypc * h->H < (1ll << 20) &&
                       !h->cfg.reserved[0];
+    // seq_wide.cu: one block per year with a lane-level work queue over the units, when the whole year is one
+    // shared-memory timeline (independent years, no explicit segment length); seq_team.cu covers the rest
+    const bool wide = team && ypc == 1 && h->cfg.seg_hours == 0 && h->Wd * 32 <= 10240 && !h->cfg.reserved[2];
     SeqArgs a{};
     a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode & ~PSRA_DISC_MATLAB; a.K = K;
     a.disc = (!injected && (init_mode & PSRA_DISC_MATLAB)) ? 1 : 0;
+    a.order = h->d_order;
     a.cap = h->d_cap; a.mttf = h->d_mttf; a.mttr = h->d_mttr; a.for_thr = h->d_for_thr;
     a.load = h->d_load; a.lmax = h->d_lmax;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
@@ -358,13 +362,14 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads(a.two_halves != 0) / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
         if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16, a.pack_shift != 0);
+        if (wide) return seq_wide_smem_bytes(h->Wd);
         if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words, a.two_halves != 0);
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
         if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
         return b;
     };
-    if (team) wpb = SEQ_TEAM_WARPS;
+    if (team) wpb = wide ? seq_wide_threads() / 32 : SEQ_TEAM_WARPS;
     while (wpb > 1 && smem_for(wpb) > h->smem_optin) wpb--;
     const size_t smem = smem_for(wpb);
     if (smem > h->smem_optin)
@@ -420,6 +425,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     int bps = 0;
     if (fast) {
         PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, a.two_halves != 0, a.pack_shift != 0, smem, wpb * 32, &bps));
+    } else if (wide) {
+        PSRA_CUDA(h, seq_wide_prepare(smem, &bps));
     } else if (team) {
         PSRA_CUDA(h, seq_team_prepare(smem, &bps));
     } else {
@@ -434,6 +441,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
 
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (fast) seq_fast_launch(a, (unsigned)grid, wpb * 32, smem, h->stream);
+    else if (wide) seq_wide_launch(a, (unsigned)grid, smem, h->stream);
     else if (team) seq_team_launch(a, (unsigned)grid, smem, h->stream);
     else kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
     PSRA_CUDA(h, cudaGetLastError());

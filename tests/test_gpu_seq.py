@@ -275,6 +275,17 @@ def test_team_kernel_large_systems(engine, rts):
     assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
     big = engine.seq_mc(20000, seed=1)
     assert abs(big.lole - 8.033131) < 4 * big.lole_se          # analytical COPT value
+    # seq_wide.cu (lane-level unit queue, the default for whole-year timelines) against seq_team.cu (wave scheduler)
+    with Engine(force_team=True) as tm:
+        tm.set_system(cap, mttf, mttr); tm.set_load(load)
+        for disc in (0, DISC_MATLAB):
+            w = engine.seq_mc(300, seed=77, init_mode=1 | disc, per_year=True, fail_count=True, group=10)
+            t = tm.seq_mc(300, seed=77, init_mode=1 | disc, per_year=True, fail_count=True, group=10)
+            assert np.array_equal(w.lol_hours, t.lol_hours) and np.array_equal(w.entries, t.entries)
+            assert np.array_equal(w.raw["ens_fp_vector"], t.raw["ens_fp_vector"]) and np.array_equal(w.fail_count, t.fail_count)
+            assert np.array_equal(w.group_lol, t.group_lol) and w.raw["events"] == t.raw["events"] and w.lol_hours.sum() > 0
+            for k in ("sum_lol_hours", "sum_ens_fp", "sum_entries", "sum_lol_sq", "sum_ens_sq", "years_with_loss"):
+                assert w.raw[k] == t.raw[k]
 
 
 def test_high_transition_rate_short_segments(engine):
