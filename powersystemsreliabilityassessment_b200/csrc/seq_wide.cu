@@ -14,10 +14,13 @@
 // order "most transitions first" (longest job first), which keeps the tail of the year short.
 // Out-of-year events are not branched around: they add into a per-lane dummy slot behind the year.
 //
-// Evaluation: all warps reduce the hour deltas to per-32-hour-word sums (redux.sync), warp 0 scans the
-// word sums into the capacity entering each word, flags the words that can contain loss of load
-// (capacity + negative hour deltas < maximum load of the word) and resolves only those hour by hour
-// (shuffle scan, __ballot_sync / __popc for LOL hours and deficit entries, int64 ENS per lane).
+// Evaluation: the warps reduce the hour deltas to per-32-hour-word sums (lane = word, skewed so that the
+// 32 lanes hit 32 different banks); after a barrier every warp scans the word sums into the capacity
+// entering each run of words (redundantly: 9 loads per lane), flags the runs that can contain loss of
+// load (capacity + negative hour deltas < maximum load of a word) and resolves / clears the runs it
+// owns: flagged words hour by hour (shuffle scan, __ballot_sync / __popc for LOL hours and deficit
+// entries, int64 ENS per lane).  The per-year sums meet in shared-memory scalars that are double
+// buffered by year parity, so warp 0 writes year y out while the other warps already generate y + 1.
 #include <limits.h>
 
 #include "psra_internal.cuh"
@@ -26,16 +29,18 @@
 #define WIDE_THREADS 256
 #define WIDE_BLOCKS_PER_SM 4
 
-struct WideShared {
+struct WideShared {     // one per year parity
     int capacity;       // sum of the capacities of the units that start the year UP
     int queue_head;     // next position of the unit order that has not been handed out
+    unsigned int lolh, entries;
+    unsigned long long ens;
 };
 
 size_t seq_wide_smem_bytes(int Wd)
 {
     size_t b = sizeof(int32_t) * ((size_t)Wd * 32 + 32);            // hour timeline + one dummy slot per lane
     b += 3 * sizeof(int32_t) * (size_t)((Wd + 3) & ~3);              // word sums, negative sums, word maxima of the load
-    b += sizeof(WideShared) + 16;
+    b += 2 * sizeof(WideShared) + 16;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -57,13 +62,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const int Hpad = a.Wd * 32, Wd4 = (a.Wd + 3) & ~3;
     int32_t *tl = reinterpret_cast<int32_t *>(smem_raw);                 // [Hpad + 32]
     int32_t *wsum = tl + Hpad + 32;                                      // [Wd4]
     int32_t *wneg = wsum + Wd4;
     int32_t *s_lmax = wneg + Wd4;
-    WideShared *sh = reinterpret_cast<WideShared *>(s_lmax + Wd4);
+    WideShared *sh_all = reinterpret_cast<WideShared *>(s_lmax + Wd4);   // [2], 8-byte aligned (Wd4 is a multiple of 4)
     const uint32_t tl_s = (uint32_t)__cvta_generic_to_shared(tl);
     const uint32_t dummy_s = tl_s + 4u * (uint32_t)(Hpad + lane);
 
@@ -78,10 +82,16 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
     const unsigned long long parked = 0x00800000ull << 32;             // event time of a lane without a unit: far beyond any year
     const bool stationary = a.init_mode == PSRA_INIT_STATIONARY;
 
-    for (long long cl = blockIdx.x; cl < a.nchains; cl += gridDim.x) {
+    if (threadIdx.x < 2) {
+        WideShared *z = sh_all + threadIdx.x;
+        z->capacity = 0; z->queue_head = (int)blockDim.x; z->lolh = 0u; z->entries = 0u; z->ens = 0ull;
+    }
+    __syncthreads();
+
+    int par = 0;
+    for (long long cl = blockIdx.x; cl < a.nchains; cl += gridDim.x, par ^= 1) {
         const unsigned long long chain = (unsigned long long)(a.chain_base + cl);
-        if (threadIdx.x == 0) { sh->capacity = 0; sh->queue_head = (int)blockDim.x; }
-        __syncthreads();                    // also: the timeline of the previous year has been cleared
+        WideShared *sh = sh_all + par;
 
         // ---- generation: lane = unit, block after block; finished lanes pull the next unit from the queue
         int pos = threadIdx.x;              // position in the unit order
@@ -130,17 +140,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
             nb++;
             n_iter += lane == 0 ? 1u : 0u;
             n_jobs += busy ? 1u : 0u;
-            const bool fin = busy && t > end_t;
-            const uint32_t fm = __ballot_sync(0xffffffffu, fin);
-            if (fm) {
-                int base = 0;
-                if (lane == __ffs(fm) - 1) base = atomicAdd(&sh->queue_head, __popc(fm));
-                base = __shfl_sync(0xffffffffu, base, __ffs(fm) - 1);
-                if (fin) {
-                    pos = base + __popc(fm & lt_mask);
-                    busy = pos < a.U;
-                    if (busy) take_unit();
-                }
+            if (busy && t > end_t) {        // unit done: take the next one of the block's queue
+                pos = atomicAdd(&sh->queue_head, 1);
+                busy = pos < a.U;
+                if (busy) take_unit();
             }
         }
 #pragma unroll
@@ -148,17 +151,26 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
         if (lane == 0 && cap_up) atomicAdd(&sh->capacity, cap_up);
         __syncthreads();
 
-        // ---- word sums of the hour deltas (all warps)
-        for (int w = warp; w < a.Wd; w += nwarps) {
-            const int d = tl[w * 32 + lane];
-            const int s = __reduce_add_sync(0xffffffffu, d);
-            const int n = __reduce_add_sync(0xffffffffu, min(d, 0));
-            if (lane == 0) { wsum[w] = s; wneg[w] = n; }
+        // ---- word sums of the hour deltas: lane = word, hour index skewed by the lane (conflict-free)
+        for (int w0 = warp * 32; w0 < a.Wd; w0 += nwarps * 32) {
+            const int w = w0 + lane;
+            if (w < a.Wd) {
+                const int32_t *row = tl + w * 32;
+                int s = 0, n = 0;
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) {
+                    const int d = row[(j + lane) & 31];
+                    s += d;
+                    n += min(d, 0);
+                }
+                wsum[w] = s; wneg[w] = n;
+            }
         }
         __syncthreads();
 
-        // ---- evaluation by warp 0: lane = run of `wpl` consecutive words
-        if (warp == 0) {
+        // ---- evaluation: every warp scans the word sums (lane = run of `wpl` consecutive words), then resolves and
+        //      clears the runs it owns
+        {
             unsigned int lolh = 0, entries = 0;
             long long ens_lane = 0;
             const int nwords = a.Wd;
@@ -175,43 +187,59 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
             const int incl = warp_incl_scan(loc, lane);
             const int cs_lane = sh->capacity + incl - loc;          // capacity entering the lane's run
             const bool flagged = (lmin != INT_MAX) && (cs_lane + lmin < 0);
-            uint32_t fm = __ballot_sync(0xffffffffu, flagged);
-            n_flag += __popc(fm);
-            while (fm) {                                            // rare: a run that may contain loss of load
-                const int src = __ffs(fm) - 1;
-                fm &= fm - 1;
-                int c_in = __shfl_sync(0xffffffffu, cs_lane, src);
-                for (int k = 0; k < wpl; k++) {
-                    const int wq = src * wpl + k;
-                    if (wq >= nwords) break;
-                    if (c_in + wneg[wq] < s_lmax[wq]) {             // resolve the word hour by hour, lane = hour
-                        const int c = c_in + warp_incl_scan(tl[wq * 32 + lane], lane);
-                        const int hy0 = wq * 32;
-                        const int L = __ldg(&a.load[hy0 + lane]);
-                        const bool lol = c < L;                     // PSA.jl:253 strict
-                        const uint32_t mask = __ballot_sync(0xffffffffu, lol);
-                        if (mask) {
-                            const uint32_t prev = (hy0 > 0 && c_in < __ldg(&a.load[hy0 - 1])) ? 1u : 0u;
-                            lolh += __popc(mask);
-                            entries += __popc(mask & ~((mask << 1) | prev));   // calnlc.m:22-34
-                            if (lol) {
-                                ens_lane += (long long)(L - c);
-                                if (a.fail) atomicAdd(&a.fail[hy0 + lane], 1u);
+            const uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+            if (warp == 0) n_flag += __popc(fm);
+            for (int src = warp; src < 32; src += nwarps) {         // runs owned by this warp
+                if ((fm >> src) & 1u) {                             // rare: the run may contain loss of load
+                    int c_in = __shfl_sync(0xffffffffu, cs_lane, src);
+                    for (int k = 0; k < wpl; k++) {
+                        const int wq = src * wpl + k;
+                        if (wq >= nwords) break;
+                        if (c_in + wneg[wq] < s_lmax[wq]) {         // resolve the word hour by hour, lane = hour
+                            const int c = c_in + warp_incl_scan(tl[wq * 32 + lane], lane);
+                            const int hy0 = wq * 32;
+                            const int L = __ldg(&a.load[hy0 + lane]);
+                            const bool lol = c < L;                 // PSA.jl:253 strict
+                            const uint32_t mask = __ballot_sync(0xffffffffu, lol);
+                            if (mask) {
+                                const uint32_t prev = (hy0 > 0 && c_in < __ldg(&a.load[hy0 - 1])) ? 1u : 0u;
+                                lolh += __popc(mask);
+                                entries += __popc(mask & ~((mask << 1) | prev));   // calnlc.m:22-34
+                                if (lol) {
+                                    ens_lane += (long long)(L - c);
+                                    if (a.fail) atomicAdd(&a.fail[hy0 + lane], 1u);
+                                }
                             }
                         }
+                        c_in += wsum[wq];
                     }
-                    c_in += wsum[wq];
+                }
+                // clear the run (wpl * 32 hours; the dummy slots behind the year may keep their garbage)
+                int4 *t4 = reinterpret_cast<int4 *>(tl + src * wpl * 32);
+                const int n4 = min(wpl, max(0, nwords - src * wpl)) * 8;
+                for (int i = lane; i < n4; i += 32) t4[i] = make_int4(0, 0, 0, 0);
+            }
+            if (lolh) {                                             // uniform within the warp
+                const long long ens = warp_sum_ll(ens_lane);
+                if (lane == 0) {
+                    atomicAdd(&sh->lolh, lolh);
+                    atomicAdd(&sh->entries, entries);
+                    atomicAdd(&sh->ens, (unsigned long long)ens);
                 }
             }
-            // ---- per-year indices
-            long long ens = 0;
-            if (lolh) ens = warp_sum_ll(ens_lane);
-            if (lane == 0) {
-                if (a.lol) a.lol[cl] = lolh;
-                if (a.ens) a.ens[cl] = ens;
-                if (a.ent) a.ent[cl] = entries;
-                if (a.group_lol && lolh) atomicAdd(&a.group_lol[cl / a.group], (unsigned long long)lolh);
-            }
+        }
+        __syncthreads();
+
+        // ---- per-year indices: warp 0 writes year `cl` out and re-arms its scalars for the year after next while the
+        //      other warps already generate the next year with the other set
+        if (threadIdx.x == 0) {
+            const unsigned int lolh = sh->lolh, entries = sh->entries;
+            const long long ens = (long long)sh->ens;
+            sh->capacity = 0; sh->queue_head = (int)blockDim.x; sh->lolh = 0u; sh->entries = 0u; sh->ens = 0ull;
+            if (a.lol) a.lol[cl] = lolh;
+            if (a.ens) a.ens[cl] = ens;
+            if (a.ent) a.ent[cl] = entries;
+            if (a.group_lol && lolh) atomicAdd(&a.group_lol[cl / a.group], (unsigned long long)lolh);
             acc_lol += lolh; acc_ens += ens; acc_ent += entries;
             acc_ywl += lolh ? 1 : 0;
             acc_lol2 += (unsigned long long)lolh * lolh;
@@ -220,11 +248,6 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
             const unsigned long long nlo = acc_e2lo + plo;
             acc_e2hi += phi + (nlo < acc_e2lo ? 1ull : 0ull);
             acc_e2lo = nlo;
-        }
-        __syncthreads();
-        {   // clear the year (the dummy slots may keep their garbage)
-            int4 *t4 = reinterpret_cast<int4 *>(tl);
-            for (int i = threadIdx.x; i < Hpad / 4; i += blockDim.x) t4[i] = make_int4(0, 0, 0, 0);
         }
     }
 
