@@ -311,7 +311,7 @@ def main():
                        "samples": clk.get("samples")},
             "roofline": {"bound": "sm_issue", "achieved": achieved, "peak": peak, "unit": "Gwarp-inst/s",
                          "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
-                         "kernel": "seq_fast_kernel<true> (csrc/seq_fast.cu)", "kernel_ms_per_launch": ksum_ms / args.steps,
+                         "kernel": "seq_fast_kernel<disc=0, ring=0, packed=1> (csrc/seq_fast.cu)", "kernel_ms_per_launch": ksum_ms / args.steps,
                          "alg_warp_inst_per_year": w_warp, "events_per_year": events,
                          "peak_source": f"{sm_count} SMs x 4 issue/clk x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json)",
                          "ncu_issue_active_pct": prof.get("issue_active_pct"),
