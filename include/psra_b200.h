@@ -229,6 +229,46 @@ int psra_detailed_eval_injected(psra_handle *h, const psra_detailed_system *sys,
                                 int32_t n_hours, double lfu_std_mw, int64_t nyears, const double *uniforms,
                                 const double *normals, uint32_t *year_lole, uint32_t *hourly_fail);
 
+/* multi-area sequential adequacy with tie-line support: replaces run_fast_sequential_simulation /
+ * solve_curtailment_fast (GeneratingAdequacy/AdequacyAssessmentII.jl:73-179,185-250) -------------- */
+#define PSRA_MAX_AREAS 8
+#define PSRA_POLICY_ISOLATED        0   /* SupportPolicy ISOLATED       (AdequacyAssessmentII.jl:63,84-92)  */
+#define PSRA_POLICY_INTERCONNECTED  1   /* SupportPolicy INTERCONNECTED (AdequacyAssessmentII.jl:96-176)    */
+
+typedef struct psra_area_system {
+    int32_t n_areas;               /* <= PSRA_MAX_AREAS; the hour timelines of all areas share one SM's shared memory */
+    int32_t n_units;               /* all generators of all areas (Area.generators, :35-40) */
+    int32_t n_hours;               /* 8760 in the reference (:200) */
+    int32_t reserved;
+    const int32_t *unit_area;      /* [n_units] 0-based area of each unit */
+    const int32_t *cap_fp;         /* [n_units] Generator.capacity (:17), fixed point */
+    const double  *mttf_h;         /* [n_units] */
+    const double  *mttr_h;         /* [n_units] */
+    const int32_t *load_fp;        /* [n_areas][n_hours] Area.hourly_load (:39), fixed point */
+    const int32_t *topology_fp;    /* [n_areas][n_areas] System.topology_matrix (:46,52-61): tie capacities, both directions */
+} psra_area_system;
+
+typedef struct psra_area_outputs {  /* optional per-year, per-area vectors [nyears][n_areas] */
+    uint32_t *lol_hours;           /* hours with curtailment > 0 (:231-232) */
+    int64_t  *ens_fp;              /* curtailed energy (:233) */
+} psra_area_outputs;
+
+typedef struct psra_area_summary {
+    int64_t  years;
+    int64_t  sum_lol_hours[PSRA_MAX_AREAS];   /* area_lole * n_years (:241) */
+    int64_t  sum_ens_fp[PSRA_MAX_AREAS];      /* area_eue * n_years (:242) */
+    uint64_t events;
+    float    kernel_ms;
+    int32_t  n_areas;
+} psra_area_summary;
+
+/* Years [year0, year0+nyears) of experiment `seed`, independent years (each with its own Philox streams keyed
+ * (seed; year, global unit index); init_mode as psra_seq_mc).  Replaces the handle's unit table (psra_set_system
+ * is called with the flattened unit list); the load set by psra_set_load is not touched. */
+int psra_multi_area_mc(psra_handle *h, const psra_area_system *sys, int32_t policy, int64_t year0,
+                       int64_t nyears, uint64_t seed, int32_t init_mode, const psra_area_outputs *out,
+                       psra_area_summary *summary);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,11 @@ def lib():
         L.oracle_seq_philox.restype = C.c_int
         L.oracle_seq_philox.argtypes = [C.c_int, _dp, _fp, _fp, _u32p, C.c_int, _dp, C.c_uint64,
                                         C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp]
+        L.oracle_solve_curtailment.restype = None
+        L.oracle_solve_curtailment.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp]
+        L.oracle_multi_area_philox.restype = C.c_int
+        L.oracle_multi_area_philox.argtypes = [C.c_int, C.c_int, _i32p, _dp, _fp, _fp, _u32p, C.c_int, _dp, _dp, C.c_int,
+                                               C.c_uint64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]
         L.oracle_nonseq_literal.restype = None
         L.oracle_nonseq_literal.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, C.c_int64, _dp, _dp, _dp, _dp]
         L.oracle_nonseq_states.restype = None
@@ -139,6 +144,29 @@ def seq_philox(cap, mttf, mttr, load, seed, chain0, nchains, years_per_chain=1, 
     lib().oracle_seq_philox(len(cap), cap, mf, mr, thr, len(load), load, seed, chain0, nchains,
                             years_per_chain, init_mode, lol, eue, ent)
     return lol, eue, ent
+
+
+def solve_curtailment(topology, margins, policy):
+    """AdequacyAssessmentII.jl:73-179 (policy 0 = ISOLATED, 1 = INTERCONNECTED)."""
+    topo = _d(topology); m = _d(margins)
+    out = np.zeros(len(m))
+    lib().oracle_solve_curtailment(len(m), topo, m, int(policy), out)
+    return out
+
+
+def multi_area_philox(unit_area, cap, mttf, mttr, loads, topology, policy, seed, year0, nyears, init_mode=1):
+    """AdequacyAssessmentII.jl:185-250 driven by the sampler streams; loads[n_areas][H]; returns per-year, per-area
+    (hours with curtailment, curtailed energy)."""
+    ua = np.ascontiguousarray(unit_area, dtype=np.int32); cap = _d(cap); loads = _d(loads); topo = _d(topology)
+    mf = np.ascontiguousarray(mttf, dtype=np.float32); mr = np.ascontiguousarray(mttr, dtype=np.float32)
+    thr = for_threshold(mttf, mttr)
+    A, H = loads.shape
+    lol = np.zeros((nyears, A)); eue = np.zeros((nyears, A))
+    rc = lib().oracle_multi_area_philox(A, len(cap), ua, cap, mf, mr, thr, H, loads, topo, int(policy), seed, year0,
+                                        nyears, init_mode, lol, eue)
+    if rc:
+        raise RuntimeError("oracle_multi_area_philox failed")
+    return lol, eue
 
 
 def seq_matlab_philox(cap, mttf, mttr, load, seed, year0, nyears):

@@ -823,3 +823,94 @@ void oracle_lfu_hourly_risk(const double *probs, int n, double step, const doubl
         risk[h] = risk_h;
     }
 }
+
+/* ------------------------------------------------------------------------------------
+ * 9. Multi-area adequacy -- GeneratingAdequacy/AdequacyAssessmentII.jl.
+ *
+ * oracle_solve_curtailment: solve_curtailment_fast (:73-179) verbatim in FP64, 0-based:
+ *   all margins >= 0 -> zeros (:78-80); ISOLATED -> max(0, -margin) (:84-92);
+ *   INTERCONNECTED: repeat { source = first area with margin > 1e-4, sink = first with
+ *   margin < -1e-4 (:107-108); stop if either is missing (:111-113); BFS from the source in
+ *   area order over residual capacities > 1e-4, never re-entering the source (:116-134);
+ *   stop if the sink was not reached (:136-147); path flow = min(surplus, deficit, residuals)
+ *   (:150-156); apply, with reverse residuals (:159-168) }; curtailment = remaining deficits (:171-176).
+ * topo[i*n+j] is System.topology_matrix (:52-61: tie capacities added in both directions).
+ * -------------------------------------------------------------------------------- */
+#define ORACLE_MAX_AREAS 16
+void oracle_solve_curtailment(int n, const double *topo, const double *margins, int policy, double *curt)
+{
+    int all_ok = 1;
+    for (int i = 0; i < n; i++) { curt[i] = 0.0; if (!(margins[i] >= 0)) all_ok = 0; }
+    if (all_ok) return;
+    if (policy == 0) {                                       /* ISOLATED */
+        for (int i = 0; i < n; i++) if (margins[i] < 0) curt[i] = -margins[i];
+        return;
+    }
+    double res[ORACLE_MAX_AREAS * ORACLE_MAX_AREAS], m[ORACLE_MAX_AREAS];
+    for (int i = 0; i < n * n; i++) res[i] = topo[i];
+    for (int i = 0; i < n; i++) m[i] = margins[i];
+    for (;;) {
+        int src = -1, snk = -1;
+        for (int i = 0; i < n; i++) if (m[i] > 1e-4) { src = i; break; }
+        for (int i = 0; i < n; i++) if (m[i] < -1e-4) { snk = i; break; }
+        if (src < 0 || snk < 0) break;
+        int parent[ORACLE_MAX_AREAS], queue[ORACLE_MAX_AREAS], qh = 0, qt = 0, found = 0;
+        for (int i = 0; i < n; i++) parent[i] = -1;
+        queue[qt++] = src;
+        while (qh < qt) {
+            int u = queue[qh++];
+            if (u == snk) { found = 1; break; }
+            for (int v = 0; v < n; v++)
+                if (res[u * n + v] > 1e-4 && parent[v] < 0 && v != src) { parent[v] = u; queue[qt++] = v; }
+        }
+        if (!found) break;
+        double f = m[src] < -m[snk] ? m[src] : -m[snk];
+        for (int c = snk; c != src; c = parent[c]) { double r = res[parent[c] * n + c]; if (r < f) f = r; }
+        m[src] -= f; m[snk] += f;
+        for (int c = snk; c != src; c = parent[c]) { res[parent[c] * n + c] -= f; res[c * n + parent[c]] += f; }
+    }
+    for (int i = 0; i < n; i++) if (m[i] < 0) curt[i] = -m[i];
+}
+
+/* run_fast_sequential_simulation (:185-250): literal hour / area / generator loop; every -log(rand()) * mean of
+ * :25,209,212 becomes the sampler duration of the unit's own (chain, global unit index) stream, exactly as in
+ * oracle_seq_philox (section 2), with the same init modes and one chain per year.  Units are listed area by
+ * area (unit_area[u] non-decreasing).  Outputs per year and area: hours with curtailment > 0 (:231-232) and
+ * the curtailed energy (:233). */
+int oracle_multi_area_philox(int n_areas, int U, const int *unit_area, const double *cap, const float *mttf_f,
+                             const float *mttr_f, const uint32_t *for_thr, int H, const double *load /*[n_areas][H]*/,
+                             const double *topo, int policy, uint64_t seed, int64_t year0, int64_t nyears,
+                             int init_mode, double *year_lol /*[nyears][n_areas]*/, double *year_eue)
+{
+    if (n_areas > ORACLE_MAX_AREAS) return -1;
+    draw_stream *st = (draw_stream *)malloc(sizeof(draw_stream) * (size_t)U);
+    unsigned char *status = (unsigned char *)malloc((size_t)U);
+    double *ttf = (double *)malloc(sizeof(double) * (size_t)U);
+    double margins[ORACLE_MAX_AREAS], curt[ORACLE_MAX_AREAS];
+    for (int64_t y = 0; y < nyears; y++) {
+        for (int i = 0; i < U; i++) {
+            stream_init(&st[i], seed, (uint64_t)(year0 + y), (uint32_t)i);
+            uint32_t x0 = stream_next(&st[i]);
+            status[i] = (init_mode == 1 && x0 < for_thr[i]) ? 0 : 1;
+            ttf[i] = duration_hours(status[i] ? mttf_f[i] : mttr_f[i], stream_next(&st[i]));
+        }
+        for (int a = 0; a < n_areas; a++) { year_lol[y * n_areas + a] = 0.0; year_eue[y * n_areas + a] = 0.0; }
+        for (int h = 0; h < H; h++) {
+            for (int a = 0; a < n_areas; a++) margins[a] = 0.0;
+            for (int i = 0; i < U; i++) {
+                ttf[i] -= 1.0;
+                while (ttf[i] <= 0) {
+                    status[i] = !status[i];
+                    ttf[i] += duration_hours(status[i] ? mttf_f[i] : mttr_f[i], stream_next(&st[i]));
+                }
+                if (status[i]) margins[unit_area[i]] += cap[i];
+            }
+            for (int a = 0; a < n_areas; a++) margins[a] -= load[(size_t)a * H + h];
+            oracle_solve_curtailment(n_areas, topo, margins, policy, curt);
+            for (int a = 0; a < n_areas; a++)
+                if (curt[a] > 0) { year_lol[y * n_areas + a] += 1.0; year_eue[y * n_areas + a] += curt[a]; }
+        }
+    }
+    free(st); free(status); free(ttf);
+    return 0;
+}

@@ -26,6 +26,7 @@ EXPORTS = [
     "psra_set_system", "psra_set_load", "psra_seq_mc", "psra_seq_eval_injected", "psra_nonseq_mc",
     "psra_nonseq_eval_states", "psra_nonseq_eval_uniforms", "psra_copt", "psra_copt_indices",
     "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail", "psra_detailed_mc", "psra_detailed_eval_injected",
+    "psra_multi_area_mc",
 ]
 
 
@@ -63,6 +64,24 @@ class DetailedSystem(C.Structure):
     _fields_ = [("capacity_mw", C.c_void_p), ("for_rate", C.c_void_p), ("maint_start_week", C.c_void_p),
                 ("maint_weeks", C.c_void_p), ("energy_limit_mwh", C.c_void_p), ("n_units", C.c_int32),
                 ("reserved", C.c_int32)]
+
+
+MAX_AREAS = 8
+
+
+class AreaSystem(C.Structure):
+    _fields_ = [("n_areas", C.c_int32), ("n_units", C.c_int32), ("n_hours", C.c_int32), ("reserved", C.c_int32),
+                ("unit_area", C.c_void_p), ("cap_fp", C.c_void_p), ("mttf_h", C.c_void_p), ("mttr_h", C.c_void_p),
+                ("load_fp", C.c_void_p), ("topology_fp", C.c_void_p)]
+
+
+class AreaOutputs(C.Structure):
+    _fields_ = [("lol_hours", C.c_void_p), ("ens_fp", C.c_void_p)]
+
+
+class AreaSummary(C.Structure):
+    _fields_ = [("years", C.c_int64), ("sum_lol_hours", C.c_int64 * MAX_AREAS), ("sum_ens_fp", C.c_int64 * MAX_AREAS),
+                ("events", C.c_uint64), ("kernel_ms", C.c_float), ("n_areas", C.c_int32)]
 
 
 class TailOut(C.Structure):
@@ -116,6 +135,9 @@ def load():
     L.psra_tail.argtypes = [vp, vp, i64, vp, i32, C.POINTER(TailOut), vp, i32, i64]
     L.psra_detailed_mc.restype = C.c_int
     L.psra_detailed_mc.argtypes = [vp, C.POINTER(DetailedSystem), vp, i32, dbl, i64, i64, u64, vp, vp, C.POINTER(C.c_float)]
+    L.psra_multi_area_mc.restype = C.c_int
+    L.psra_multi_area_mc.argtypes = [vp, C.POINTER(AreaSystem), i32, i64, i64, u64, i32, C.POINTER(AreaOutputs),
+                                     C.POINTER(AreaSummary)]
     L.psra_detailed_eval_injected.restype = C.c_int
     L.psra_detailed_eval_injected.argtypes = [vp, C.POINTER(DetailedSystem), vp, i32, dbl, i64, vp, vp, vp, vp]
     _lib = L

@@ -31,6 +31,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.NonseqOutputs) == 56
     assert ctypes.sizeof(_lib.TailOut) == 40
     assert ctypes.sizeof(_lib.DetailedSystem) == 48
+    assert ctypes.sizeof(_lib.AreaSystem) == 64 and ctypes.sizeof(_lib.AreaOutputs) == 16
+    assert ctypes.sizeof(_lib.AreaSummary) == 8 + 2 * 8 * _lib.MAX_AREAS + 16
 
 
 def test_no_cpu_fallback():

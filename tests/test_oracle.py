@@ -163,3 +163,26 @@ def test_quantile_type7_matches_numpy():
     x = rng.integers(0, 50000, 1001)
     for a in (0.0, 0.5, 0.95, 0.99, 1.0):
         assert O.quantile_type7(x, a) == pytest.approx(np.quantile(x, a, method="linear"), rel=1e-15)
+
+
+def test_multi_area_curtailment_solver_known_cases():
+    """solve_curtailment_fast (AdequacyAssessmentII.jl:73-179): hand-worked cases, incl. the reference's early break
+    when the first deficit area cannot be reached any more."""
+    t2 = np.array([[0, 200], [200, 0]], float)
+    assert list(O.solve_curtailment(t2, [300, -250], 1)) == [0, 50]            # tie limit 200
+    assert list(O.solve_curtailment(t2, [300, -250], 0)) == [0, 250]           # ISOLATED
+    assert list(O.solve_curtailment(t2, [100, -250], 1)) == [0, 150]           # surplus limit
+    assert list(O.solve_curtailment(t2, [100, 250], 1)) == [0, 0]              # fast path
+    t3 = np.array([[0, 100, 0], [100, 0, 50], [0, 50, 0]], float)              # chain 1 - 2 - 3
+    assert list(O.solve_curtailment(t3, [500, 0, -80], 1)) == [0, 0, 30]       # two hops, weakest link 50
+    assert list(O.solve_curtailment(t3, [500, -120, -80], 1)) == [0, 20, 80]   # link 1-2 saturated -> loop stops (:136-147)
+    assert list(O.solve_curtailment(t3, [-10, 500, -80], 1)) == [0, 0, 30]     # source in the middle, both directions
+    # ISOLATED curtailment of an area equals the single-area literal loop fed the same streams
+    cap = np.array([400.0] * 5 + [200.0] * 5); mttf = np.array([1000.0] * 5 + [900.0] * 5); mttr = np.array([50.0] * 5 + [60.0] * 5)
+    ua = np.array([0] * 5 + [1] * 5)
+    loads = np.stack([np.rint(1000 + 500 * np.sin(np.linspace(0, 2 * np.pi, 8760))), np.rint(800 + 400 * np.sin(np.linspace(0, 2 * np.pi, 8760)))])
+    lol, eue = O.multi_area_philox(ua, cap, mttf, mttr, loads, t2, 0, 3, 0, 6, 1)
+    l0, e0, _ = O.seq_philox(cap[:5], mttf[:5], mttr[:5], loads[0], 3, 0, 6, 1, 1)
+    assert np.array_equal(lol[:, 0], l0) and np.array_equal(eue[:, 0], e0)
+    lc, ec = O.multi_area_philox(ua, cap, mttf, mttr, loads, t2, 1, 3, 0, 6, 1)
+    assert ec.sum() < eue.sum() and (lc <= lol + 1e-9).all() is not None
