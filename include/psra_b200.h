@@ -188,6 +188,12 @@ int psra_markov2(psra_handle *h, double lambda, double mu, double dt, int32_t st
 int psra_dtmc_capacity(psra_handle *h, const double *mttf_h, const double *mttr_h,
                        const double *cap_mw, int32_t n_units, const double *r, int32_t n_steps,
                        double *avail_mw);
+/* constant-rate failure-time experiment, Markov_process.jl:39-60: n components, each checked every dt hours against
+ * rand() < lambda*dt (:54) until it fails or t > max_time (:59).  failure_time[i] = the reference's pushed time, or -1
+ * for a component that outlived max_time (the reference pushes nothing).  rand(): r[i*K + k] when r != NULL, else
+ * draw k of the Philox stream keyed (seed; component). */
+int psra_failure_times(psra_handle *h, double lambda, double dt, double max_time, int64_t n, uint64_t seed,
+                       const double *r, int32_t K, double *failure_time);
 
 /* tail risk over per-year ENS: outputs of tail_risk.jl:18-19,79-90,168-175 plus the
  * VaR / CVaR build-side spec: VaR_a = type-7 quantile

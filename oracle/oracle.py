@@ -55,6 +55,8 @@ def lib():
         L.oracle_multi_area_philox.restype = C.c_int
         L.oracle_multi_area_philox.argtypes = [C.c_int, C.c_int, _i32p, _dp, _fp, _fp, _u32p, C.c_int, _dp, _dp, C.c_int,
                                                C.c_uint64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]
+        L.oracle_failure_times.restype = C.c_int
+        L.oracle_failure_times.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int64, C.c_uint64, C.c_void_p, C.c_int, _dp]
         L.oracle_nonseq_literal.restype = None
         L.oracle_nonseq_literal.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, C.c_int64, _dp, _dp, _dp, _dp]
         L.oracle_nonseq_states.restype = None
@@ -167,6 +169,19 @@ def multi_area_philox(unit_area, cap, mttf, mttr, loads, topology, policy, seed,
     if rc:
         raise RuntimeError("oracle_multi_area_philox failed")
     return lol, eue
+
+
+def failure_times(lam, dt, max_time, n, seed=42, uniforms=None):
+    """Markov_process.jl:39-60; returns the per-component array (-1 = outlived max_time)."""
+    out = np.zeros(n)
+    if uniforms is None:
+        rc = lib().oracle_failure_times(lam, dt, max_time, n, seed, None, 0, out)
+    else:
+        r = _d(uniforms)
+        rc = lib().oracle_failure_times(lam, dt, max_time, n, seed, r.ctypes.data_as(C.c_void_p), r.shape[1], out)
+    if rc:
+        raise RuntimeError("oracle_failure_times: injected uniforms exhausted")
+    return out
 
 
 def seq_matlab_philox(cap, mttf, mttr, load, seed, year0, nyears):

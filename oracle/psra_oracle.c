@@ -914,3 +914,32 @@ int oracle_multi_area_philox(int n_areas, int U, const int *unit_area, const dou
     free(st); free(status); free(ttf);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------
+ * 10. Markov_process.jl:39-60 -- constant hourly failure probability => exponential failure times.
+ * Literal loop; rand() is r[i*K + k] (injected) or u = word / 2^32 of the Philox stream keyed
+ * (seed; component, 0x46540000 | block).  out[i] = pushed time, -1 if the component outlived max_time.
+ * -------------------------------------------------------------------------------- */
+int oracle_failure_times(double lambda, double dt, double max_time, int64_t n, uint64_t seed, const double *r, int K, double *out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        double t = 0.0;
+        uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) }, ctr[4], buf[4] = {0, 0, 0, 0};
+        out[i] = -1.0;
+        for (int k = 0;; k++) {
+            double u;
+            if (r) { if (k >= K) return -1; u = r[(size_t)i * K + k]; }
+            else {
+                if ((k & 3) == 0) {
+                    ctr[0] = (uint32_t)i; ctr[1] = (uint32_t)((uint64_t)i >> 32); ctr[2] = 0x46540000u; ctr[3] = (uint32_t)(k >> 2);
+                    oracle_philox4x32_10(ctr, key, buf);
+                }
+                u = (double)buf[k & 3] * 2.3283064365386963e-10;
+            }
+            if (u < lambda * dt) { out[i] = t; break; }      /* :54-56 */
+            t += dt;                                          /* :58 */
+            if (t > max_time) break;                          /* :59 */
+        }
+    }
+    return 0;
+}

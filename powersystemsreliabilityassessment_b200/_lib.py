@@ -26,7 +26,7 @@ EXPORTS = [
     "psra_set_system", "psra_set_load", "psra_seq_mc", "psra_seq_eval_injected", "psra_nonseq_mc",
     "psra_nonseq_eval_states", "psra_nonseq_eval_uniforms", "psra_copt", "psra_copt_indices",
     "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail", "psra_detailed_mc", "psra_detailed_eval_injected",
-    "psra_multi_area_mc",
+    "psra_multi_area_mc", "psra_failure_times",
 ]
 
 
@@ -131,6 +131,8 @@ def load():
     L.psra_fd_recursion.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.POINTER(i32)]
     L.psra_markov2.restype = C.c_int; L.psra_markov2.argtypes = [vp, dbl, dbl, dbl, i32, vp]
     L.psra_dtmc_capacity.restype = C.c_int; L.psra_dtmc_capacity.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp]
+    L.psra_failure_times.restype = C.c_int
+    L.psra_failure_times.argtypes = [vp, dbl, dbl, dbl, i64, u64, vp, i32, vp]
     L.psra_tail.restype = C.c_int
     L.psra_tail.argtypes = [vp, vp, i64, vp, i32, C.POINTER(TailOut), vp, i32, i64]
     L.psra_detailed_mc.restype = C.c_int

@@ -396,6 +396,20 @@ class Engine:
                                                         _ptr(un), _ptr(no), _ptr(yl), _ptr(hf)))
         return yl, hf
 
+    def failure_times(self, lam: float, n_samples: int = 10000, dt: float = 1.0, max_time: float = 5000.0, seed: int = 42,
+                      uniforms=None) -> np.ndarray:
+        """Markov_process.jl:39-60: the `failure_times` vector (components that outlive max_time are dropped, like the
+        reference, which pushes nothing for them).  uniforms[n][K] injects rand()."""
+        out = np.zeros(n_samples, dtype=np.float64)
+        r = None; K = 0
+        if uniforms is not None:
+            r = np.ascontiguousarray(uniforms, dtype=np.float64)
+            if r.ndim != 2 or r.shape[0] != n_samples:
+                raise ValueError("uniforms must be [n_samples][K]")
+            K = r.shape[1]
+        self._check(self._L.psra_failure_times(self._h, float(lam), float(dt), float(max_time), n_samples, seed, _ptr(r), K, _ptr(out)))
+        return out[out >= 0.0]
+
     # ---- multi-area adequacy (AdequacyAssessmentII.jl)
     def multi_area_mc(self, unit_area, cap, mttf, mttr, loads, topology, policy: int, years: int, seed: int = 42,
                       year0: int = 0, init_mode: int = INIT_STATIONARY, per_year: bool = False, fp_scale: float = 1.0,

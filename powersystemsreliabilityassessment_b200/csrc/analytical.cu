@@ -6,6 +6,7 @@
 //  * psra_fd_recursion   : add_unit_educational!, generating_adequacy_frequency.jl:76-129
 //  * psra_markov2        : Markov_process.jl:89-110
 //  * psra_dtmc_capacity  : Markov_process.jl:159-195
+//  * psra_failure_times  : Markov_process.jl:39-60
 //
 // The file is compiled with --fmad=false and every product / sum is a single IEEE operation in
 // the reference's order, so the COPT / F&D tables are bit-identical to the FP64 reference
@@ -363,5 +364,58 @@ extern "C" int psra_dtmc_capacity(psra_handle *h, const double *mttf_h, const do
     PSRA_CUDA(h, cudaGetLastError());
     PSRA_CUDA(h, cudaMemcpyAsync(avail_mw, d_av, sizeof(double) * T, cudaMemcpyDeviceToHost, h->stream));
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PSRA_OK;
+}
+
+// Markov_process.jl:39-60 "why constant rate = exponential distribution": thread = component; every dt hours the
+// component fails with probability lambda * dt (rand() < lambda * dt, :54); t accumulates by repeated addition
+// (:58) and the component is dropped once t > max_time (:59).  rand() is either the injected matrix r[i*K + k]
+// or draw k of the Philox stream keyed (seed; component, 0x46540000 | block): u = word / 2^32 (exact in FP64).
+__global__ void __launch_bounds__(256) failure_time_kernel(double thr, double dt, double max_time, long long n, uint32_t k0,
+                                                           uint32_t k1, const double *__restrict__ r, int K, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0, res = -1.0;
+    uint32_t x[4];
+    for (int k = 0;; k++) {
+        double u;
+        if (r) {
+            if (k >= K) { res = -2.0; break; }               // injected uniforms exhausted (reported as an error)
+            u = r[(size_t)i * K + k];
+        } else {
+            if ((k & 3) == 0) philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), 0x46540000u, (uint32_t)(k >> 2), k0, k1, x);
+            u = (double)x[k & 3] * 2.3283064365386963e-10;    // / 2^32
+        }
+        if (u < thr) { res = t; break; }
+        t += dt;
+        if (t > max_time) break;
+    }
+    out[i] = res;
+}
+
+extern "C" int psra_failure_times(psra_handle *h, double lambda, double dt, double max_time, int64_t n, uint64_t seed,
+                                  const double *r, int32_t K, double *failure_time)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, failure_time && n >= 1, "bad output / component count");
+    PSRA_REQUIRE(h, lambda > 0 && dt > 0 && max_time >= 0 && max_time / dt < 1e8, "bad rate / time step / horizon");
+    PSRA_REQUIRE(h, !r || K >= 1, "injected uniforms need K >= 1");
+    PSRA_CUDA(h, cudaSetDevice(h->device));
+    const size_t nr = r ? (size_t)n * (size_t)K : 0;
+    int rc = psra_reserve(h, &h->d_scratch, &h->scratch_cap, sizeof(double) * ((size_t)n + nr));
+    if (rc) return rc;
+    double *d_out = (double *)h->d_scratch, *d_r = nullptr;
+    if (r) {
+        d_r = d_out + n;
+        PSRA_CUDA(h, cudaMemcpyAsync(d_r, r, sizeof(double) * nr, cudaMemcpyHostToDevice, h->stream));
+    }
+    failure_time_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(lambda * dt, dt, max_time, n, (uint32_t)seed,
+                                                                           (uint32_t)(seed >> 32), d_r, K, d_out);
+    PSRA_CUDA(h, cudaGetLastError());
+    PSRA_CUDA(h, cudaMemcpyAsync(failure_time, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < n; i++)
+        if (failure_time[i] == -2.0) return psra_fail(h, PSRA_E_OVERFLOW, "injected uniforms exhausted: component %lld needed more than K=%d draws", (long long)i, K);
     return PSRA_OK;
 }

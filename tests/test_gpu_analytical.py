@@ -82,3 +82,18 @@ def test_markov2_and_dtmc(engine):
     a = engine.dtmc_capacity(mttf, mttr, cap, r)
     ao = O.dtmc_capacity(mttf, mttr, cap, r)
     assert np.array_equal(a, ao) and a.min() < 600
+
+
+def test_failure_time_experiment(engine):
+    """Markov_process.jl:39-60: injected rand() and sampler streams, bit-exact vs the literal loop; exponential shape."""
+    rng = np.random.default_rng(8)
+    r = rng.random((64, 300)); r[:5] = 0.5                      # five components never fail within max_time = 200
+    ft = engine.failure_times(0.01, 64, dt=1.0, max_time=200.0, uniforms=r)
+    ref = O.failure_times(0.01, 1.0, 200.0, 64, uniforms=r)
+    assert np.array_equal(ft, ref[ref >= 0]) and len(ft) <= 59
+    with pytest.raises(Exception):
+        engine.failure_times(0.01, 64, max_time=200.0, uniforms=r[:, :50] * 0 + 0.5)
+    ft = engine.failure_times(1e-3, 10000, dt=1.0, max_time=5000.0, seed=42)     # the script's parameters
+    ref = O.failure_times(1e-3, 1.0, 5000.0, 10000, seed=42)
+    assert np.array_equal(ft, ref[ref >= 0])
+    assert abs(len(ft) / 10000 - (1 - (1 - 1e-3) ** 5001)) < 0.01 and abs(ft.mean() - 966.0) < 30     # truncated geometric mean
