@@ -132,4 +132,25 @@ function run_fast_sequential_simulation(sys::System, policy::SupportPolicy, n_ye
     return results
 end
 
+# AdequacyAssessmentII.jl:256-290
+function run_demo()
+    gens1 = [Generator("G1_$i", 400.0, 1000.0, 50.0) for i in 1:5]
+    load1 = 1000.0 .+ 500.0 .* sin.(range(0, 2π, length=8760))
+    gens2 = [Generator("G2_$i", 200.0, 900.0, 60.0) for i in 1:5]
+    load2 = 800.0 .+ 400.0 .* sin.(range(0, 2π, length=8760))
+    sys = System([Area(1, "Area_Rich", gens1, collect(load1)), Area(2, "Area_Poor", gens2, collect(load2))], [TieLine(1, 2, 200.0)])
+    res_iso = run_fast_sequential_simulation(sys, ISOLATED, 500)
+    res_int = run_fast_sequential_simulation(sys, INTERCONNECTED, 500)
+    println("\n=== FINAL COMPARISON (FAST METHOD) ===")
+    println("Policy          | Area       | LOLE (h/yr) | EUE (MWh/yr)")
+    println("-"^60)
+    for r in res_iso
+        @printf("ISOLATED        | %-10s | %10.2f  | %10.2f\n", r.area, r.lole, r.eue)
+    end
+    println("-"^60)
+    for r in res_int
+        @printf("INTERCONNECTED  | %-10s | %10.2f  | %10.2f\n", r.area, r.lole, r.eue)
+    end
+end
+
 end # module
