@@ -191,7 +191,7 @@ class Engine:
         o = _lib.SeqOutputs()
         bufs = {}
         if history:
-            bufs["history"] = np.zeros(n // history, dtype=np.float64)
+            bufs["history"] = np.empty(n // history, dtype=np.float64)     # fully overwritten by the library
             o.history = _ptr(bufs["history"]); o.group = history
         if per_year:
             bufs["lol_hours"] = np.zeros(n, dtype=np.uint32)
@@ -256,7 +256,7 @@ class Engine:
         o = _lib.NonseqOutputs()
         bufs = {}
         if history:
-            bufs["history"] = np.zeros(n // history, dtype=np.float64)
+            bufs["history"] = np.empty(n // history, dtype=np.float64)
             o.history = _ptr(bufs["history"]); o.group = history
         if per_sample:
             bufs["lol_hours"] = np.zeros(n, dtype=np.uint32)

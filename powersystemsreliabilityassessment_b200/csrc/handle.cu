@@ -46,39 +46,101 @@ int psra_reserve_outputs(psra_handle *h, int64_t n)
     return PSRA_OK;
 }
 
-// running mean of the group sums: one block, each thread owns a contiguous chunk, block scan of the chunk totals
-__global__ void __launch_bounds__(1024) history_kernel(const long long *__restrict__ g, long long n, int group, double *__restrict__ out)
+// running mean of the group sums, cum_lole / y of PSA.jl:203,264.  Two coalesced passes: (1) every block sums its
+// contiguous chunk; (2) every block adds up the chunk sums in front of it and scans its chunk tile by tile
+// (warp-shuffle scan, 1024 elements per tile, running carry).
+#define HIST_THREADS 1024
+__device__ __forceinline__ long long hist_block_sum(long long v, long long *sh)
 {
-    __shared__ long long sh[1024];
-    const int t = threadIdx.x;
-    const long long chunk = (n + 1023) / 1024, lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    long long s = 0;
-    for (long long i = lo; i < hi; i++) s += g[i];
-    sh[t] = s;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        long long v = 0;
-        if (t >= d) v = sh[t - d];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long t = 0;
+    for (int w = 0; w < HIST_THREADS / 32; w++) t += sh[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(HIST_THREADS) history_partial_kernel(const long long *__restrict__ g, long long n, long long chunk,
+                                                                       int block0, long long *__restrict__ partial)
+{
+    __shared__ long long sh[HIST_THREADS / 32];
+    const int blk = block0 + (int)blockIdx.x;
+    const long long lo = (long long)blk * chunk, hi = min(n, lo + chunk);
+    long long s = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += HIST_THREADS) s += g[i];
+    s = hist_block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blk] = s;
+}
+
+__global__ void __launch_bounds__(HIST_THREADS) history_scan_kernel(const long long *__restrict__ g, long long n, long long chunk,
+                                                                    int block0, const long long *__restrict__ partial, int group,
+                                                                    double *__restrict__ out)
+{
+    __shared__ long long sh[HIST_THREADS / 32];
+    __shared__ long long wtot[HIST_THREADS / 32];
+    const int blk = block0 + (int)blockIdx.x;
+    long long carry = 0;
+    for (int b = threadIdx.x; b < blk; b += HIST_THREADS) carry += partial[b];
+    carry = hist_block_sum(carry, sh);
+    const long long lo = (long long)blk * chunk, hi = min(n, lo + chunk);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = lo; base < hi; base += HIST_THREADS) {
+        const long long i = base + threadIdx.x;
+        long long v = i < hi ? g[i] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += o;
+        }
         __syncthreads();
-        if (t >= d) sh[t] += v;
+        if (lane == 31) wtot[warp] = v;
         __syncthreads();
+        long long before = 0, total = 0;
+        for (int w = 0; w < HIST_THREADS / 32; w++) { const long long t = wtot[w]; total += t; if (w < warp) before += t; }
+        if (i < hi) out[i] = (double)(carry + before + v) / ((double)group * (double)(i + 1));
+        carry += total;
     }
-    long long run = sh[t] - s;
-    for (long long i = lo; i < hi; i++) {
-        run += g[i];
-        out[i] = (double)run / ((double)group * (double)(i + 1));     // cum_lole / y, PSA.jl:203,264
-    }
+}
+
+// groups per scan block: a multiple of the 1024-element tile, about four blocks per SM over the whole sequence
+int64_t psra_history_block(const psra_handle *h, int64_t nfull)
+{
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((nfull + HIST_THREADS - 1) / HIST_THREADS, 4 * (int64_t)h->sm_count));
+    return ((nfull + blocks - 1) / blocks + HIST_THREADS - 1) / HIST_THREADS * HIST_THREADS;
+}
+
+int psra_history_prepare(psra_handle *h, int64_t nfull)
+{
+    if (nfull <= 0) return PSRA_OK;
+    const int64_t chunk = psra_history_block(h, nfull), blocks = (nfull + chunk - 1) / chunk;
+    return psra_reserve(h, &h->d_hist, &h->hist_cap, sizeof(double) * (size_t)nfull + sizeof(long long) * (size_t)blocks);
+}
+
+int psra_history_range(psra_handle *h, const long long *d_group, int64_t nfull, int group, int64_t b0, int64_t b1,
+                       double *history, cudaStream_t stream)
+{
+    if (nfull <= 0) return PSRA_OK;
+    const int64_t chunk = psra_history_block(h, nfull), blocks = (nfull + chunk - 1) / chunk;
+    b1 = std::min(b1, blocks);
+    if (b1 <= b0) return PSRA_OK;
+    double *d_hist = (double *)h->d_hist;
+    long long *d_part = (long long *)(d_hist + nfull);
+    history_partial_kernel<<<(unsigned)(b1 - b0), HIST_THREADS, 0, stream>>>(d_group, nfull, chunk, (int)b0, d_part);
+    history_scan_kernel<<<(unsigned)(b1 - b0), HIST_THREADS, 0, stream>>>(d_group, nfull, chunk, (int)b0, d_part, group, d_hist);
+    PSRA_CUDA(h, cudaGetLastError());
+    const int64_t g0 = b0 * chunk, g1 = std::min(nfull, b1 * chunk);
+    PSRA_CUDA(h, cudaMemcpyAsync(history + g0, d_hist + g0, sizeof(double) * (size_t)(g1 - g0), cudaMemcpyDeviceToHost, stream));
+    return PSRA_OK;
 }
 
 int psra_history_to_host(psra_handle *h, const long long *d_group, int64_t nfull, int group, double *history)
 {
     if (nfull <= 0) return PSRA_OK;
-    int rc = psra_reserve(h, &h->d_scratch2, &h->scratch2_cap, sizeof(double) * (size_t)nfull);
+    int rc = psra_history_prepare(h, nfull);
     if (rc) return rc;
-    history_kernel<<<1, 1024, 0, h->stream>>>(d_group, nfull, group, (double *)h->d_scratch2);
-    PSRA_CUDA(h, cudaGetLastError());
-    PSRA_CUDA(h, cudaMemcpyAsync(history, h->d_scratch2, sizeof(double) * (size_t)nfull, cudaMemcpyDeviceToHost, h->stream));
-    return PSRA_OK;
+    return psra_history_range(h, d_group, nfull, group, 0, INT64_MAX / 2, history, h->stream);
 }
 
 extern "C" int psra_version(void) { return PSRA_VERSION; }
@@ -130,6 +192,8 @@ extern "C" int psra_create(psra_handle **out, const psra_config *cfg)
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
     h->sm_clock_khz = khz;
     PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < PSRA_MAX_CHUNKS; i++) PSRA_CUDA(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     PSRA_CUDA(h, cudaEventCreate(&h->ev0));
     PSRA_CUDA(h, cudaEventCreate(&h->ev1));
     PSRA_CUDA(h, cudaMalloc(&h->d_acc, sizeof(unsigned long long) * ACC_COUNT));
@@ -142,11 +206,13 @@ extern "C" void psra_destroy(psra_handle *h)
     cudaSetDevice(h->device);
     void *bufs[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_load, h->d_lmax,
                     h->d_load_sorted, h->d_load_suffix, h->d_acc, h->d_lol, h->d_ens, h->d_ent, h->d_fail,
-                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order};
+                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order, h->d_hist};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < PSRA_MAX_CHUNKS; i++) if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

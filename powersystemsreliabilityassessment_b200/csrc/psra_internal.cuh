@@ -15,13 +15,16 @@
 #define PSRA_VERSION 1001
 
 #define ACC_COUNT_MAX 32
+#define PSRA_MAX_CHUNKS 8
 struct psra_handle {
     int device = 0;
     int sm_count = 0;
     int sm_clock_khz = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;              // history scan + read-back, overlapped with the kernels of `stream`
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_chunk[PSRA_MAX_CHUNKS] = {nullptr};
     psra_config cfg{};
     char err[512] = {0};
 
@@ -56,6 +59,7 @@ struct psra_handle {
     long long *d_group = nullptr; int64_t group_cap = 0;
     void *d_scratch = nullptr; size_t scratch_cap = 0;   // inputs of injected paths, tail keys
     void *d_scratch2 = nullptr; size_t scratch2_cap = 0;
+    void *d_hist = nullptr; size_t hist_cap = 0;         // convergence history + its scan partials
     unsigned long long last_acc[ACC_COUNT_MAX] = {0};   // accumulators of the last MC call (diagnostics)
 };
 
@@ -77,7 +81,13 @@ int psra_fail(psra_handle *h, int code, const char *fmt, ...);
 // grow-only device buffer helpers (host side)
 int psra_reserve(psra_handle *h, void **p, size_t *cap, size_t bytes);
 int psra_reserve_outputs(psra_handle *h, int64_t n);
-// running means cumsum(group sums)[k] / (group * (k+1)), k < nfull, into host buffer `history` (uses d_scratch2)
+// running means cumsum(group sums)[k] / (group * (k+1)), k < nfull, into the host buffer `history` (device staging in d_hist).
+// The sequence is cut into blocks of psra_history_block(nfull) groups; psra_history_range scans the blocks
+// [b0, b1) on `stream` (all earlier blocks must have been scanned on the same stream) and copies them to the host.
+int64_t psra_history_block(const psra_handle *h, int64_t nfull);
+int psra_history_prepare(psra_handle *h, int64_t nfull);
+int psra_history_range(psra_handle *h, const long long *d_group, int64_t nfull, int group, int64_t b0, int64_t b1,
+                       double *history, cudaStream_t stream);
 int psra_history_to_host(psra_handle *h, const long long *d_group, int64_t nfull, int group, double *history);
 
 // ------------------------------------------------------------------------- device helpers

@@ -439,15 +439,60 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     const long long need = team ? nchains : (nchains + wpb - 1) / wpb;
     if (grid > need) grid = need;
 
+    // Launch plan.  Normally one launch.  When the convergence history of a long run is wanted, the years are cut into
+    // up to PSRA_MAX_CHUNKS launches whose group ranges are whole history-scan blocks: the scan and the read-back
+    // of a finished range run on stream2 while the next launch computes (the history is 8 B per `group` years --
+    // 8 MB for 10^7 RTS-79 years -- and would otherwise be a serial tail of the call).
+    const int64_t nfull = (out && out->history) ? nyears / a.group : 0;
+    int nlaunch = 1;
+    long long chunk_chains = nchains;
+    int64_t hblock = 0, hblocks_per_launch = 0;
+    if (nfull > 0) {
+        int rc = psra_history_prepare(h, nfull);
+        if (rc) return rc;
+        hblock = psra_history_block(h, nfull);
+        const int64_t hblocks = (nfull + hblock - 1) / hblock;
+        // a launch must cover whole scan blocks: hblock groups = hblock * group years = whole chains
+        if (!injected && nyears >= (1ll << 20) && (hblock * a.group) % ypc == 0 && hblocks >= 2 * PSRA_MAX_CHUNKS) {
+            nlaunch = PSRA_MAX_CHUNKS;
+            hblocks_per_launch = (hblocks + nlaunch - 1) / nlaunch;
+            chunk_chains = hblocks_per_launch * hblock * a.group / ypc;
+            nlaunch = (int)((nchains + chunk_chains - 1) / chunk_chains);
+        }
+    }
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    if (fast) seq_fast_launch(a, (unsigned)grid, wpb * 32, smem, h->stream);
-    else if (wide) seq_wide_launch(a, (unsigned)grid, smem, h->stream);
-    else if (team) seq_team_launch(a, (unsigned)grid, smem, h->stream);
-    else kern<<<(unsigned)grid, wpb * 32, smem, h->stream>>>(a);
-    PSRA_CUDA(h, cudaGetLastError());
+    for (int c = 0; c < nlaunch; c++) {
+        SeqArgs b = a;
+        const long long c0 = (long long)c * chunk_chains;
+        b.chain_base = a.chain_base + c0;
+        b.nchains = std::min(chunk_chains, nchains - c0);
+        const long long y0 = c0 * ypc;
+        if (a.lol) b.lol = a.lol + y0;
+        if (a.ens) b.ens = a.ens + y0;
+        if (a.ent) b.ent = a.ent + y0;
+        if (a.group_lol) b.group_lol = a.group_lol + y0 / a.group;      // y0 is a multiple of the group when nlaunch > 1
+        long long g = grid;
+        const long long need_c = (team ? b.nchains : (b.nchains + wpb - 1) / wpb);
+        if (g > need_c) g = need_c;
+        if (fast) seq_fast_launch(b, (unsigned)g, wpb * 32, smem, h->stream);
+        else if (wide) seq_wide_launch(b, (unsigned)g, smem, h->stream);
+        else if (team) seq_team_launch(b, (unsigned)g, smem, h->stream);
+        else kern<<<(unsigned)g, wpb * 32, smem, h->stream>>>(b);
+        PSRA_CUDA(h, cudaGetLastError());
+        if (nlaunch > 1) PSRA_CUDA(h, cudaEventRecord(h->ev_chunk[c], h->stream));
+    }
     PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));
 
     unsigned long long acc[ACC_COUNT];
+    if (nlaunch > 1) {
+        // scan + read back the history range of every launch as soon as that launch has finished
+        for (int c = 0; c < nlaunch; c++) {
+            PSRA_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_chunk[c], 0));
+            int rc = psra_history_range(h, h->d_group, nfull, a.group, c * hblocks_per_launch, (c + 1) * hblocks_per_launch,
+                                        out->history, h->stream2);
+            if (rc) return rc;
+        }
+    }
     PSRA_CUDA(h, cudaMemcpyAsync(acc, h->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, h->stream));
     if (out) {
         if (out->lol_hours) PSRA_CUDA(h, cudaMemcpyAsync(out->lol_hours, h->d_lol, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
@@ -455,11 +500,12 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         if (out->entries)   PSRA_CUDA(h, cudaMemcpyAsync(out->entries, h->d_ent, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
         if (out->fail_count) PSRA_CUDA(h, cudaMemcpyAsync(out->fail_count, h->d_fail, sizeof(uint32_t) * (size_t)h->H, cudaMemcpyDeviceToHost, h->stream));
         if (out->group_lol) PSRA_CUDA(h, cudaMemcpyAsync(out->group_lol, h->d_group, sizeof(long long) * (size_t)ngroups, cudaMemcpyDeviceToHost, h->stream));
-        if (out->history) {
-            int rc = psra_history_to_host(h, h->d_group, nyears / a.group, a.group, out->history);
+        if (nfull > 0 && nlaunch == 1) {
+            int rc = psra_history_range(h, h->d_group, nfull, a.group, 0, INT64_MAX / 2, out->history, h->stream);
             if (rc) return rc;
         }
     }
+    if (nlaunch > 1) PSRA_CUDA(h, cudaStreamSynchronize(h->stream2));
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     float ms = 0.f;
     PSRA_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));

@@ -157,6 +157,17 @@ def test_convergence_history_computed_on_device(engine, rts):
         want = np.cumsum(r.lol_hours[: 10 * k].astype(np.float64)).reshape(k, 10)[:, -1] / (10.0 * np.arange(1, k + 1))
         assert r.history.shape == (k,) and np.array_equal(r.history, want)
     assert engine.seq_mc(9, seed=11, history=10).history.shape == (0,)
+    # long runs are cut into several launches whose history ranges are scanned / read back while the next one computes
+    for years, ypc in ((2_500_003, 1), (1_200_000, 4)):
+        r = engine.seq_mc(years, seed=3, per_year=True, history=10, group=10, years_per_chain=ypc) if years % ypc == 0 else \
+            engine.seq_mc(years, seed=3, per_year=True, history=10, group=10)
+        one = engine.seq_mc(years, seed=3, per_year=True, group=10, years_per_chain=ypc if years % ypc == 0 else 1)
+        k = years // 10
+        want = np.cumsum(r.lol_hours[: 10 * k].astype(np.float64)).reshape(k, 10)[:, -1] / (10.0 * np.arange(1, k + 1))
+        assert np.array_equal(r.history, want) and np.array_equal(r.lol_hours, one.lol_hours)
+        assert np.array_equal(r.group_lol, one.group_lol) and np.array_equal(r.raw["ens_fp_vector"], one.raw["ens_fp_vector"])
+        for key in ("sum_lol_hours", "sum_ens_fp", "sum_entries", "sum_lol_sq", "sum_ens_sq", "years_with_loss", "events"):
+            assert r.raw[key] == one.raw[key]
     import powersystemsreliabilityassessment_b200 as P
     gens = [P.Generator(i + 1, c, f, m) for i, (c, f, m) in enumerate(zip(rts["cap"], rts["mttf"], rts["mttr"]))]
     res = P.run_sequential_mc(gens, P.LoadModel(rts["load_int"].astype(np.float64)), 1000, seed=11, engine=engine)
