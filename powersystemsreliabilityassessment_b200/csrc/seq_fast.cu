@@ -90,45 +90,48 @@ __device__ __forceinline__ void list_push_shared_if(uint32_t head_saddr, uint32_
 // Single-segment scatter of one event (the whole chain is one timeline segment).  If hour `hs` lies in the
 // year: add `delta` to the word's sum (and to its negative sum when the event takes the unit down, i.e. when
 // s0i == qodd), push the event onto the word's list and count it.  `wa` = shared address of the word record
-// {sum, negative sum, head}; the list slot at `evm + 8` is private to this lane.  ptxas turns predicated
-// shared atomics into branches, so the atomics are unconditional instead: an out-of-year event adds 0 and
-// exchanges with its own (never linked) list slot.
-__device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, uint32_t wa, int delta, uint32_t s0i, uint32_t qodd,
-                                                     uint32_t idx1, uint32_t evm, uint32_t ent, unsigned int &n_events)
+// {sum, negative sum, head}; the list slot at `slot_m8 + 8` is private to this lane.  ptxas turns predicated
+// shared atomics into branches, so the atomics are unconditional instead: an out-of-year event adds 0 to the
+// record of word `lane` (address `wlane`; only ever touched by atomics while a segment is being filled) and
+// exchanges with its own, never linked, list slot.
+__device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, uint32_t wa, uint32_t wlane, int delta, uint32_t s0i,
+                                                     uint32_t qodd, uint32_t idx1, uint32_t slot_m8, uint32_t ent, unsigned int &n_events)
 {
-    asm volatile("{\n .reg .pred p, pn;\n .reg .b32 nx, d0, d1, hb;\n"
+    asm volatile("{\n .reg .pred p, pn;\n .reg .b32 nx, d0, d1, hr, hx;\n"
                  " setp.lt.u32 p, %1, %2;\n"
-                 " setp.eq.and.u32 pn, %5, %6, p;\n"
-                 " selp.b32 d0, %4, 0, p;\n"
-                 " selp.b32 d1, %4, 0, pn;\n"
-                 " selp.b32 hb, %3, %8, p;\n"
-                 " red.shared.add.s32 [hb], d0;\n"
-                 " red.shared.add.s32 [hb+4], d1;\n"
-                 " atom.shared.exch.b32 nx, [hb+8], %7;\n"
-                 " mad.lo.u32 nx, nx, 1048576, %9;\n"
-                 " st.shared.b32 [%8+8], nx;\n"
+                 " setp.eq.and.u32 pn, %6, %7, p;\n"
+                 " selp.b32 d0, %5, 0, p;\n"
+                 " selp.b32 d1, %5, 0, pn;\n"
+                 " selp.b32 hr, %3, %4, p;\n"
+                 " selp.b32 hx, %3, %9, p;\n"
+                 " red.shared.add.s32 [hr], d0;\n"
+                 " red.shared.add.s32 [hr+4], d1;\n"
+                 " atom.shared.exch.b32 nx, [hx+8], %8;\n"
+                 " mad.lo.u32 nx, nx, 1048576, %10;\n"
+                 " st.shared.b32 [%9+8], nx;\n"
                  " @p add.u32 %0, %0, 1;\n}\n"
                  : "+r"(n_events)
-                 : "r"(hs), "r"(H), "r"(wa), "r"(delta), "r"(s0i), "r"(qodd), "r"(idx1), "r"(evm), "r"(ent)
+                 : "r"(hs), "r"(H), "r"(wa), "r"(wlane), "r"(delta), "r"(s0i), "r"(qodd), "r"(idx1), "r"(slot_m8), "r"(ent)
                  : "memory");
 }
 
 // Packed variant: the record is {sum + 2^K * negative sum, head}; `delta` already carries both fields
-// (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.
-__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wa, int delta,
-                                                     uint32_t idx1, uint32_t evm, uint32_t ent, unsigned int &n_events)
+// (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.  Out-of-year events as above.
+__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wa, uint32_t wlane, int delta,
+                                                     uint32_t idx1, uint32_t slot_m4, uint32_t ent, unsigned int &n_events)
 {
-    asm volatile("{\n .reg .pred p;\n .reg .b32 nx, d0, hb;\n"
+    asm volatile("{\n .reg .pred p;\n .reg .b32 nx, d0, hr, hx;\n"
                  " setp.lt.u32 p, %1, %2;\n"
-                 " selp.b32 d0, %4, 0, p;\n"
-                 " selp.b32 hb, %3, %6, p;\n"
-                 " red.shared.add.s32 [hb], d0;\n"
-                 " atom.shared.exch.b32 nx, [hb+4], %5;\n"
-                 " mad.lo.u32 nx, nx, 1048576, %7;\n"
-                 " st.shared.b32 [%6+4], nx;\n"
+                 " selp.b32 d0, %5, 0, p;\n"
+                 " selp.b32 hr, %3, %4, p;\n"
+                 " selp.b32 hx, %3, %7, p;\n"
+                 " red.shared.add.s32 [hr], d0;\n"
+                 " atom.shared.exch.b32 nx, [hx+4], %6;\n"
+                 " mad.lo.u32 nx, nx, 1048576, %8;\n"
+                 " st.shared.b32 [%7+4], nx;\n"
                  " @p add.u32 %0, %0, 1;\n}\n"
                  : "+r"(n_events)
-                 : "r"(hs), "r"(H), "r"(wa), "r"(delta), "r"(idx1), "r"(evm), "r"(ent)
+                 : "r"(hs), "r"(H), "r"(wa), "r"(wlane), "r"(delta), "r"(idx1), "r"(slot_m4), "r"(ent)
                  : "memory");
 }
 
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     }
     for (int i = lane; i < RS * ring_words; i += 32) wtab[i] = (kPack && !(i & 1)) ? pk_bias : 0;
     const uint32_t wtab_s = (uint32_t)__cvta_generic_to_shared(wtab);
+    const uint32_t wlane_s = wtab_s + 4u * RS * (uint32_t)min(lane, a.seg_words - 1);     // where this lane's out-of-year events add 0
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
 
@@ -354,11 +358,14 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                         if constexpr (!kTwo) {
                             // whole chain = one segment: hour in segment = hour in year, ring = year.  Job lane j of a wave
                             // of J jobs owns the list slots cnt + q*J + j, q = 0..3 (holes of out-of-year events are never linked)
-                            const bool room = cnt_cur + 4 * J <= ev_cap;              // warp-uniform
+                            // lanes without a job park their dummy exchange in "their" slot too, i.e. up to slot cnt + 3 J + 31
+                            const bool room = cnt_cur + 3 * J + 32 <= ev_cap;         // warp-uniform; implies cnt + 4 J <= ev_cap
                             // lanes without a job (and a full list) are parked far beyond the year
                             const unsigned long long bm1 = (act && room) ? base_t - 1ull : (0x00800000ull << 32);
                             const uint32_t s0i = s0u ? 1u : 0u;
-                            uint32_t idx1 = (uint32_t)cnt_cur + (uint32_t)lane + 1u;
+                            // a lane without a job keeps one dummy slot behind the wave's 4 J slots for all four events
+                            uint32_t idx1 = (uint32_t)(room ? cnt_cur : 0) + (uint32_t)lane + 1u + (act ? 0u : 3u * (uint32_t)J);   // full list: stay in bounds (ev_cap >= 128)
+                            const uint32_t idx_step = act ? (uint32_t)J : 0u;
                             const int dn_pk = -cu - (cu << pk);                       // kPack: a down event in both fields
                             const int pk_a = s0u ? cu : dn_pk, pk_b = s0u ? dn_pk : cu;
 #pragma unroll
@@ -370,12 +377,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                                 // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
                                 const uint32_t ent = (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1)));
                                 if constexpr (kPack)
-                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s + 8u * (hs >> 5), (q & 1) ? pk_b : pk_a, idx1,
+                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s + 8u * (hs >> 5), wlane_s, (q & 1) ? pk_b : pk_a, idx1,
                                                          evcur_s + 4u * idx1 - 8u, ent, n_events);
                                 else
-                                    scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), delta, s0i, (uint32_t)(q & 1), idx1,
+                                    scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, delta, s0i, (uint32_t)(q & 1), idx1,
                                                          evcur_s + 4u * idx1 - 12u, ent, n_events);
-                                idx1 += (uint32_t)J;
+                                idx1 += idx_step;
                             }
                             cnt_cur += 4 * J;
                             if (!room) cnt_cur = ev_cap + 1;                          // reported as PSRA_E_OVERFLOW below

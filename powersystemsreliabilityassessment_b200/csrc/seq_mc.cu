@@ -330,7 +330,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     // by default the whole year is one segment unless that list would exceed 2048 entries
     auto ev_cap_for = [&](int sw) -> int {
         const double e = h->events_per_hour * sw * 32.0 + h->U;
-        const long long c = (long long)(1.75 * e) + 64;
+        const long long c = std::max(160ll, (long long)(1.75 * e) + 64);
         return (int)((c + 31) & ~31ll);
     };
     if (one_unit) {

@@ -21,11 +21,26 @@ with P.Engine() as e:
     r = e.seq_mc(20000, seed=3, keep_on_device=True); print("tail", e.tail(None, n_bins=20, bin_width=2000)[0])
     c5 = rts79.synthetic_system(32, 37.0)
     e.set_system(c5[0], c5[1], c5[2]); e.set_load(c5[3])
-    print("seq team", e.seq_mc(300, seed=4, per_year=True).lole, e.seq_mc(120, seed=4, years_per_chain=4).lole)
+    print("seq wide", e.seq_mc(300, seed=4, per_year=True, fail_count=True, group=10, history=10).lole, "seq team chain", e.seq_mc(120, seed=4, years_per_chain=4).lole)
     gens = [P.DetailedGenerator("A", 400.0, 0.02, 4), P.DetailedGenerator("B", 300.0, 0.04, 3), P.DetailedGenerator("H", 200.0, 0.01, 2, 1e4)]
     base = 500.0 + 150.0 * np.sin(np.arange(8760) / 8760 * 2 * math.pi)
     P.schedule_maintenance(gens, [base[(w - 1) * 168:w * 168].max() for w in range(1, 53)])
     print("detailed", e.detailed_mc(gens, base, 30.0, 512, seed=5)[0].mean())
+    ua = np.array([0] * 5 + [1] * 5 + [2] * 3); acap = np.array([400.0] * 5 + [200.0] * 5 + [100.0] * 3)
+    amttf = np.array([1000.0] * 5 + [900.0] * 5 + [300.0] * 3); amttr = np.array([50.0] * 5 + [60.0] * 5 + [30.0] * 3)
+    x = np.linspace(0, 2 * np.pi, 8760)
+    loads = np.stack([np.rint(1000 + 500 * np.sin(x)), np.rint(800 + 400 * np.sin(x)), np.rint(150 + 100 * np.cos(x))])
+    topo = np.array([[0, 200, 50], [200, 0, 30], [50, 30, 0]], float)
+    print("multi-area", [e.multi_area_mc(ua, acap, amttf, amttr, loads, topo, pol, 200, seed=6, per_year=True)["lole"] for pol in (0, 1)])
+    print("failure times", len(e.failure_times(1e-3, 4000)))
+    e.set_system(cap, mttf, mttr); e.set_load(load)
+    print("seq fast long history", e.seq_mc(1_100_000, seed=1, history=10).history[-1])
+with P.Engine(force_team=True) as t:
+    t.set_system(c5[0], c5[1], c5[2]); t.set_load(c5[3])
+    print("seq team", t.seq_mc(200, seed=4, per_year=True).lole)
+with P.Engine(unpacked_words=True) as g:
+    g.set_system(cap, mttf, mttr); g.set_load(load)
+    print("seq fast unpacked", g.seq_mc(2000, seed=1).lole)
 with P.Engine(force_generic=True) as g:
     g.set_system(cap, mttf, mttr); g.set_load(load)
     print("seq generic", g.seq_mc(2000, seed=1, years_per_chain=4).lole)
