@@ -206,7 +206,7 @@ extern "C" void psra_destroy(psra_handle *h)
     cudaSetDevice(h->device);
     void *bufs[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_load, h->d_lmax,
                     h->d_load_sorted, h->d_load_suffix, h->d_acc, h->d_lol, h->d_ens, h->d_ent, h->d_fail,
-                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order, h->d_hist};
+                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order, h->d_hist, h->d_lol_tab, h->d_byte_tab};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);

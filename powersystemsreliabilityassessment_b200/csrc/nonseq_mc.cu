@@ -13,6 +13,12 @@
 // one binary search in the ascending-sorted load curve (staged in shared memory) plus one
 // suffix-sum lookup:  LOL hours = #{h : load_h > cap},  ENS = sum_{load_h > cap} load_h
 // - cap * LOL hours -- integer arithmetic, hence identical to the hour loop bit for bit.
+//
+// Systems of <= 32 units whose installed capacity (fixed point) stays below 2^16 take nonseq_fast_kernel:
+// the 32 Bernoulli tests are unrolled (thresholds read four at a time from shared memory), the capacity of
+// the packed state word comes from four 256-entry byte tables (sum of the capacities of every byte pattern)
+// and the LOL hours from a table indexed by the integer capacity -- 4 + 1 shared-memory lookups instead of
+// 32 predicated adds and a 14-step binary search.  Same Philox words, same integers.
 #include <algorithm>
 #include <vector>
 
@@ -22,6 +28,9 @@ struct NsArgs {
     int U, H, W, group;
     const int32_t *cap; const uint32_t *for_thr; const double *for_rate;
     const int32_t *sorted;        // [H] ascending
+    const uint16_t *lol_tab;      // [total_cap+1] (fast path)
+    const int32_t *byte_tab;      // [4][256]      (fast path)
+    int total_cap;
     const long long *suffix;      // [H+1] suffix[i] = sum_{k>=i} sorted[k]
     uint32_t k0, k1;
     long long i0, n;
@@ -32,6 +41,73 @@ struct NsArgs {
 };
 
 enum { NS_PHILOX = 0, NS_STATES = 1, NS_UNIFORMS = 2 };
+
+// U <= 32, total_cap < 65536, H < 65536
+__global__ void __launch_bounds__(256) nonseq_fast_kernel(const NsArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t *s_btab = reinterpret_cast<int32_t *>(smem_raw);                      // [4][256]
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_btab + 1024);                // [32]
+    uint16_t *s_lol = reinterpret_cast<uint16_t *>(s_thr + 32);                   // [total_cap+1]
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_btab[i] = a.byte_tab[i];
+    if (threadIdx.x < 32) s_thr[threadIdx.x] = threadIdx.x < a.U ? a.for_thr[threadIdx.x] : 0u;
+    for (int i = threadIdx.x; i <= a.total_cap; i += blockDim.x) s_lol[i] = a.lol_tab[i];
+    __syncthreads();
+    const uint32_t umask = a.U >= 32 ? 0xffffffffu : ((1u << a.U) - 1u);
+    const int nblk = (a.U + 3) >> 2;
+
+    unsigned long long acc_lol = 0, acc_swl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
+    long long acc_ens = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const unsigned long long s = (unsigned long long)(a.i0 + i);
+        uint32_t word = 0;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            if (g < nblk) {                           // uniform
+                uint32_t x[4];
+                philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)g, 0x4E53u, a.k0, a.k1, x);
+                const uint4 t = *reinterpret_cast<const uint4 *>(s_thr + 4 * g);
+                word |= (x[0] >= t.x ? 1u : 0u) << (4 * g);             // PSA.jl:183 in integer form
+                word |= (x[1] >= t.y ? 1u : 0u) << (4 * g + 1);
+                word |= (x[2] >= t.z ? 1u : 0u) << (4 * g + 2);
+                word |= (x[3] >= t.w ? 1u : 0u) << (4 * g + 3);
+            }
+        }
+        word &= umask;
+        const int cap = s_btab[word & 255u] + s_btab[256 + ((word >> 8) & 255u)] + s_btab[512 + ((word >> 16) & 255u)] +
+                        s_btab[768 + (word >> 24)];
+        const unsigned int lolh = s_lol[cap];
+        long long ens = 0;
+        if (lolh) ens = __ldg(&a.suffix[a.H - (int)lolh]) - (long long)cap * (long long)lolh;
+        if (a.states) a.states[i] = word;
+        if (a.lol) a.lol[i] = lolh;
+        if (a.ens) a.ens[i] = ens;
+        if (a.cap_out) a.cap_out[i] = cap;
+        if (a.group_lol && lolh) atomicAdd(&a.group_lol[i / a.group], (unsigned long long)lolh);
+        acc_lol += lolh; acc_ens += ens; acc_swl += lolh ? 1 : 0;
+        acc_lol2 += (unsigned long long)lolh * lolh;
+        const unsigned long long e = (unsigned long long)ens;
+        const unsigned long long plo = e * e, phi = __umul64hi(e, e);
+        const unsigned long long nlo = acc_e2lo + plo;
+        acc_e2hi += phi + (nlo < acc_e2lo ? 1ull : 0ull);
+        acc_e2lo = nlo;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc_lol += __shfl_xor_sync(0xffffffffu, acc_lol, d);
+        acc_ens += __shfl_xor_sync(0xffffffffu, acc_ens, d);
+        acc_swl += __shfl_xor_sync(0xffffffffu, acc_swl, d);
+        acc_lol2 += __shfl_xor_sync(0xffffffffu, acc_lol2, d);
+    }
+    if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
+    if ((threadIdx.x & 31) == 0) {
+        if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
+        if (acc_ens) atomicAdd(&a.acc[ACC_ENS], (unsigned long long)acc_ens);
+        if (acc_swl) atomicAdd(&a.acc[ACC_YWL], acc_swl);
+        if (acc_lol2) atomicAdd(&a.acc[ACC_LOL2], acc_lol2);
+    }
+}
 
 template <int kMode>
 __global__ void __launch_bounds__(256) nonseq_kernel(const NsArgs a)
@@ -143,6 +219,28 @@ static int prepare_sorted(psra_handle *h)
     PSRA_CUDA(h, cudaMalloc(&h->d_load_suffix, sizeof(long long) * ((size_t)h->H + 1)));
     PSRA_CUDA(h, cudaMemcpy(h->d_load_sorted, ld.data(), sizeof(int32_t) * (size_t)h->H, cudaMemcpyHostToDevice));
     PSRA_CUDA(h, cudaMemcpy(h->d_load_suffix, suf.data(), sizeof(long long) * suf.size(), cudaMemcpyHostToDevice));
+    // tables of the fast path (<= 32 units): LOL hours of every integer capacity, capacity of every state byte
+    if (h->d_lol_tab) cudaFree(h->d_lol_tab);
+    if (h->d_byte_tab) cudaFree(h->d_byte_tab);
+    h->d_lol_tab = nullptr; h->d_byte_tab = nullptr;
+    if (h->U <= 32 && h->total_cap < 65536 && h->H < 65536) {
+        std::vector<uint16_t> lt((size_t)h->total_cap + 1);
+        size_t ub = 0;                                         // #{load <= c}
+        for (long long c = 0; c <= h->total_cap; c++) {
+            while (ub < ld.size() && ld[ub] <= c) ub++;
+            lt[(size_t)c] = (uint16_t)(ld.size() - ub);
+        }
+        std::vector<int32_t> capv(h->U), bt(1024, 0);
+        PSRA_CUDA(h, cudaMemcpy(capv.data(), h->d_cap, sizeof(int32_t) * (size_t)h->U, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < 4; b++)
+            for (int v = 0; v < 256; v++)
+                for (int k = 0; k < 8; k++)
+                    if (((v >> k) & 1) && 8 * b + k < h->U) bt[256 * b + v] += capv[8 * b + k];
+        PSRA_CUDA(h, cudaMalloc(&h->d_lol_tab, sizeof(uint16_t) * lt.size()));
+        PSRA_CUDA(h, cudaMalloc(&h->d_byte_tab, sizeof(int32_t) * bt.size()));
+        PSRA_CUDA(h, cudaMemcpy(h->d_lol_tab, lt.data(), sizeof(uint16_t) * lt.size(), cudaMemcpyHostToDevice));
+        PSRA_CUDA(h, cudaMemcpy(h->d_byte_tab, bt.data(), sizeof(int32_t) * bt.size(), cudaMemcpyHostToDevice));
+    }
     h->tab_valid = true;
     return PSRA_OK;
 }
@@ -168,7 +266,10 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
     a.i0 = i0; a.n = n; a.acc = h->d_acc; a.group = 1;
 
-    const size_t smem = sizeof(int32_t) * ((size_t)h->H + h->U) + sizeof(uint32_t) * (size_t)h->U;
+    a.lol_tab = h->d_lol_tab; a.byte_tab = h->d_byte_tab; a.total_cap = (int)h->total_cap;
+    const size_t smem_fast = sizeof(int32_t) * 1024 + sizeof(uint32_t) * 32 + ((sizeof(uint16_t) * ((size_t)h->total_cap + 1) + 15) & ~(size_t)15);
+    const bool fastp = mode == NS_PHILOX && h->d_lol_tab && smem_fast <= 100 * 1024 && !h->cfg.reserved[0];
+    const size_t smem = fastp ? smem_fast : sizeof(int32_t) * ((size_t)h->H + h->U) + sizeof(uint32_t) * (size_t)h->U;
     PSRA_REQUIRE(h, smem <= h->smem_optin, "load curve + unit table exceed shared memory");
 
     if (mode == NS_STATES) {
@@ -216,7 +317,7 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
     }
     PSRA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * ACC_COUNT, h->stream));
 
-    void (*kern)(NsArgs) = mode == NS_PHILOX ? nonseq_kernel<NS_PHILOX>
+    void (*kern)(NsArgs) = fastp ? nonseq_fast_kernel : mode == NS_PHILOX ? nonseq_kernel<NS_PHILOX>
                          : mode == NS_STATES ? nonseq_kernel<NS_STATES> : nonseq_kernel<NS_UNIFORMS>;
     PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = 0;

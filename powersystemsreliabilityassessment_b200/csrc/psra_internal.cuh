@@ -49,6 +49,8 @@ struct psra_handle {
     bool tab_valid = false;
     int32_t *d_load_sorted = nullptr;   // [H] load curve sorted ascending
     int64_t *d_load_suffix = nullptr;   // [H+1] suffix sums of the sorted curve
+    uint16_t *d_lol_tab = nullptr;      // [total_cap+1] LOL hours of every integer capacity (nonseq fast path), or null
+    int32_t *d_byte_tab = nullptr;      // [4][256] capacity of every byte pattern of the 32-unit state word
     // accumulators / scratch
     unsigned long long *d_acc = nullptr;  // [32]
     // per-run outputs kept on the device (grown on demand)

@@ -69,6 +69,26 @@ def test_convergence_history_computed_on_device(engine, rts):
         assert g["history"].shape == (k,) and np.array_equal(g["history"], want)
 
 
+def test_table_path_equals_generic_path(engine, rts):
+    """<= 32 units: the table-driven kernel (byte tables + LOL-by-capacity table) and the generic one (masked sums +
+    binary search) give the same integers, also for few units, a ragged unit count and the peak-load mode (H = 1)."""
+    from powersystemsreliabilityassessment_b200 import Engine
+    rng = np.random.default_rng(12)
+    cases = [(rts["cap"], rts["mttf"], rts["mttr"], rts["load_int"]),
+             (rts["cap"], rts["mttf"], rts["mttr"], np.array([2850], dtype=np.int32)),
+             (rts["cap"][:5], rts["mttf"][:5] / 20, rts["mttr"][:5], rng.integers(0, 300, 100).astype(np.int32)),
+             (rts["cap"][:27], rts["mttf"][:27] / 10, rts["mttr"][:27], rng.integers(1500, 3000, 777).astype(np.int32))]
+    with Engine(force_generic=True) as gen:
+        for cap, mttf, mttr, load in cases:
+            engine.set_system(cap, mttf, mttr); engine.set_load(load)
+            gen.set_system(cap, mttf, mttr); gen.set_load(load)
+            a = engine.nonseq_mc(20_000, seed=4, sample0=77, per_sample=True, states=True, group=100)
+            b = gen.nonseq_mc(20_000, seed=4, sample0=77, per_sample=True, states=True, group=100)
+            for k in ("lol_hours", "ens", "states", "group_lol"):
+                assert np.array_equal(a[k], b[k]), k
+            assert a["raw"] == b["raw"] and a["lol_hours"].sum() > 0
+
+
 def test_philox_many_units(engine, rts):
     from powersystemsreliabilityassessment_b200 import rts79
     cap, mttf, mttr, load = rts79.synthetic_system(32, 37.0)
