@@ -26,8 +26,8 @@
 #include "psra_internal.cuh"
 #include "seq_args.cuh"
 
-#define WIDE_THREADS 256
-#define WIDE_BLOCKS_PER_SM 4
+#define WIDE_THREADS 192
+#define WIDE_BLOCKS_PER_SM 5
 
 struct WideShared {     // one per year parity
     int capacity;       // sum of the capacities of the units that start the year UP
@@ -58,6 +58,7 @@ __device__ __forceinline__ void wide_scatter(uint32_t tl_s, uint32_t dummy_s, ui
                  : "memory");
 }
 
+template <bool kDisc>
 __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_kernel(const SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
 
     unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
     long long acc_ens = 0;
-    unsigned int n_events = 0, n_iter = 0, n_jobs = 0, n_flag = 0;
+    unsigned int n_events = 0, n_jobs = 0, n_flag = 0;
     const unsigned long long end_t = (unsigned long long)a.H << PSRA_TICK_SHIFT;
     const unsigned long long parked = 0x00800000ull << 32;             // event time of a lane without a unit: far beyond any year
     const bool stationary = a.init_mode == PSRA_INIT_STATIONARY;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
             thr = __ldg(&a.for_thr[u]);
             nb = 0u;
             // MATLAB discretisation: a unit that fails after d whole hours is DOWN from hour d+1 (seq_mcsampling.m:63)
-            t = a.disc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
+            t = kDisc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
         };
         if (busy) take_unit();
         while (__any_sync(0xffffffffu, busy)) {
@@ -122,10 +123,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
             }
             const float m_a = s0u ? mdn : mup;      // draws 0, 2 of a block: state s0^1
             const float m_b = s0u ? mup : mdn;      // draws 1, 3: state s0
-            const unsigned long long p1 = first ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, a.disc);
-            const unsigned long long p2 = p1 + dur_ticks_disc(m_b, x[1], s0u, a.disc);
-            const unsigned long long p3 = p2 + dur_ticks_disc(m_a, x[2], !s0u, a.disc);
-            const unsigned long long p4 = p3 + dur_ticks_disc(m_b, x[3], s0u, a.disc);
+            const unsigned long long p1 = first ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, kDisc);
+            const unsigned long long p2 = p1 + dur_ticks_disc(m_b, x[1], s0u, kDisc);
+            const unsigned long long p3 = p2 + dur_ticks_disc(m_a, x[2], !s0u, kDisc);
+            const unsigned long long p4 = p3 + dur_ticks_disc(m_b, x[3], s0u, kDisc);
             // hour of an event at tick T: ceil(T / 2^24) - 1 = (T - 1) >> 24
             const unsigned long long bm1 = busy ? t - 1ull : parked;
             const int delta_a = s0u ? cu : -cu;     // draws 0, 2 toggle the unit back to s0
@@ -138,7 +139,6 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
             }
             t += p4;
             nb++;
-            n_iter += lane == 0 ? 1u : 0u;
             n_jobs += busy ? 1u : 0u;
             if (busy && t > end_t) {        // unit done: take the next one of the block's queue
                 pos = atomicAdd(&sh->queue_head, 1);
@@ -251,16 +251,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
         }
     }
 
-    unsigned long long ev = n_events, it = n_iter, jb = n_jobs;
+    unsigned long long ev = n_events, jb = n_jobs;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         ev += __shfl_xor_sync(0xffffffffu, ev, d);
-        it += __shfl_xor_sync(0xffffffffu, it, d);
         jb += __shfl_xor_sync(0xffffffffu, jb, d);
     }
     if (lane == 0) {
         if (ev) atomicAdd(&a.acc[ACC_EVENTS], ev);
-        atomicAdd(&a.acc[ACC_WAVES], it);
         atomicAdd(&a.acc[ACC_JOBS], jb);
         if (warp == 0) {
             if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
@@ -278,12 +276,15 @@ int seq_wide_threads() { return WIDE_THREADS; }
 
 cudaError_t seq_wide_prepare(size_t smem, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(seq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(seq_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, seq_wide_kernel, WIDE_THREADS, smem);
+    e = cudaFuncSetAttribute(seq_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, seq_wide_kernel<false>, WIDE_THREADS, smem);
 }
 
 void seq_wide_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t stream)
 {
-    seq_wide_kernel<<<grid, WIDE_THREADS, smem, stream>>>(a);
+    if (a.disc) seq_wide_kernel<true><<<grid, WIDE_THREADS, smem, stream>>>(a);
+    else seq_wide_kernel<false><<<grid, WIDE_THREADS, smem, stream>>>(a);
 }
