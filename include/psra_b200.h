@@ -56,7 +56,9 @@ typedef struct psra_config {
                                  for systems of <= 32 units (cross-checks; the default picks seq_fast.cu);
                                  reserved[1] != 0: seq_fast.cu keeps the word sums unpacked (cross-checks);
                                  reserved[2] != 0: systems of > 32 units use seq_team.cu also where seq_wide.cu
-                                 applies (cross-checks) */
+                                 applies (cross-checks);
+                                 reserved[3] > 0: number of statically scheduled Philox blocks per unit in
+                                 seq_fast.cu's single-segment mode (0 = chosen from the expected demand) */
 } psra_config;
 
 /* lifetime ------------------------------------------------------------------------- */

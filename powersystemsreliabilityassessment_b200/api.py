@@ -108,7 +108,8 @@ class Engine:
     """One libpsra_b200 handle = one CUDA device + stream."""
 
     def __init__(self, device: int = 0, warps_per_block: int = 0, seg_hours: int = 0, blocks_per_sm: int = 0,
-                 force_generic: bool = False, unpacked_words: bool = False, force_team: bool = False):
+                 force_generic: bool = False, unpacked_words: bool = False, force_team: bool = False,
+                 static_blocks: int = 0):
         self._L = _lib.load()
         self._h = C.c_void_p()
         cfg = _lib.Config(device=device, warps_per_block=warps_per_block, seg_hours=seg_hours,
@@ -116,6 +117,7 @@ class Engine:
         cfg.reserved[0] = 1 if force_generic else 0
         cfg.reserved[1] = 1 if unpacked_words else 0
         cfg.reserved[2] = 1 if force_team else 0
+        cfg.reserved[3] = int(static_blocks)
         rc = self._L.psra_create(C.byref(self._h), C.byref(cfg))
         if rc != 0:
             msg = self._L.psra_last_error(self._h).decode() if self._h else "psra_create failed"

@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 struct SeqArgs {
-    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves, pack_shift;
+    int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves, pack_shift, static_blocks;
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
     const int32_t *load; const int32_t *lmax;
     const int32_t *order;   // units sorted by decreasing transition rate (seq_wide.cu work queue)

@@ -60,7 +60,7 @@ __host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, boo
 __host__ __device__ inline size_t fast_block_bytes(int Wd, bool load16)
 {
     size_t b = (load16 ? 2 : 4) * (size_t)Wd * 32 + sizeof(int32_t) * (size_t)((Wd + 3) & ~3);   // load curve + word maxima
-    b += 32 * (sizeof(int32_t) + 2 * sizeof(float) + sizeof(uint32_t));                          // unit tables
+    b += 32 * (sizeof(int32_t) + 3 * sizeof(float) + sizeof(uint32_t));                          // unit tables
     return (b + 15) & ~(size_t)15;
 }
 
@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     int32_t *s_cap = s_lmax + ((a.Wd + 3) & ~3);
     float *s_mup = reinterpret_cast<float *>(s_cap + 32);
     float *s_mdn = s_mup + 32;
-    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_mdn + 32);
+    float *s_ispan = s_mdn + 32;         // Philox blocks a unit needs per hour of horizon (a block = 4 durations = 2 up/down cycles)
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_ispan + 32);
     constexpr bool two_halves = kTwo;     // the ring needs its second half (several segments per year or multi-year chains)
     const int halves = two_halves ? 2 : 1;
     const int ev_cap = a.ev_cap;
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
         s_mup[threadIdx.x] = v ? __fmul_rn(a.mttf[threadIdx.x], 16777216.0f) : 1.0f;
         s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
+        s_ispan[threadIdx.x] = v ? __fdividef(0.5f, a.mttf[threadIdx.x] + a.mttr[threadIdx.x]) : 0.f;
     }
     for (int i = lane; i < RS * ring_words; i += 32) wtab[i] = (kPack && !(i & 1)) ? pk_bias : 0;
     const uint32_t wtab_s = (uint32_t)__cvta_generic_to_shared(wtab);
@@ -200,9 +202,6 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     unsigned int n_events = 0;
 
     const bool unit_valid = lane < a.U;
-    const int capu = s_cap[lane];
-    // expected Philox blocks per hour of horizon: a block holds 4 durations = 2 up/down cycles
-    const float inv_span = unit_valid ? __fdividef(0.5f, a.mttf[min(lane, a.U - 1)] + a.mttr[min(lane, a.U - 1)]) : 0.f;
 
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
@@ -219,7 +218,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
         // MATLAB discretisation: a unit that fails after d whole hours is DOWN from hour d+1 (seq_mcsampling.m:63)
         ws->t_run[lane] = kDisc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
         __syncwarp();
-        bool init_wave = true;
+        bool init_wave = kTwo;          // single-segment mode: block 0 of every unit belongs to the static phase
 
         for (int y = 0; y < a.ypc; y++) {
             unsigned int lolh = 0, entries = 0;
@@ -273,6 +272,63 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                     pend_cnt = outc;
                 }
 
+                // ---- static phase (single segment): lane = unit, blocks 0 .. static_blocks-1 of every unit, no scheduling.
+                //      Every unit needs these blocks anyway (the host picks the count from the expected demand), so
+                //      the job mapping, the ballots and the segmented scan of the waves below are skipped for them.
+                if constexpr (!kTwo) {
+                    unsigned long long t = kDisc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
+                    bool s0u = true;
+                    const float mup = s_mup[lane], mdn = s_mdn[lane];
+                    const int capu = s_cap[lane];
+                    const int pk_dn = -capu - (capu << pk);
+                    // list slots as in a wave of J = U jobs: unit u owns cnt + q U + u, q = 0..3; a lane without a unit keeps
+                    // one dummy slot behind them
+                    const uint32_t Uu = (uint32_t)a.U, idx_step = unit_valid ? Uu : 0u;
+                    for (int k = 0; k < a.static_blocks; k++) {
+                        uint32_t x[4];
+                        philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)lane, (uint32_t)k, a.k0, a.k1, x);
+                        if (k == 0) s0u = !(a.init_mode == PSRA_INIT_STATIONARY && x[0] < s_thr[lane]);   // draw 0 = initial state
+                        const float m_a = s0u ? mdn : mup;      // draws 0, 2 of a block: state s0^1
+                        const float m_b = s0u ? mup : mdn;      // draws 1, 3: state s0
+                        const unsigned long long p1 = (k == 0) ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, kDisc);
+                        const unsigned long long p2 = p1 + dur_ticks_disc(m_b, x[1], s0u, kDisc);
+                        const unsigned long long p3 = p2 + dur_ticks_disc(m_a, x[2], !s0u, kDisc);
+                        const unsigned long long p4 = p3 + dur_ticks_disc(m_b, x[3], s0u, kDisc);
+                        const bool room = cnt_cur + 3 * a.U + 32 <= ev_cap;          // warp-uniform
+                        const unsigned long long bm1 = (unit_valid && room) ? t - 1ull : (0x00800000ull << 32);
+                        uint32_t idx1 = (uint32_t)(room ? cnt_cur : 0) + (uint32_t)lane + 1u + (unit_valid ? 0u : 3u * Uu);
+                        const uint32_t s0i = s0u ? 1u : 0u;
+                        const int delta_a = s0u ? capu : -capu;
+                        const int pk_a = s0u ? capu : pk_dn, pk_b = s0u ? pk_dn : capu;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
+                            if (q == 0 && k == 0) tm1 = 0x00800000ull << 32;
+                            const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
+                            const uint32_t ent = (hs << 6) + (((uint32_t)lane << 1) | (s0i ^ (uint32_t)(q & 1)));
+                            if constexpr (kPack)
+                                scatter_event_packed(hs, (uint32_t)a.H, wtab_s + 8u * (hs >> 5), wlane_s, (q & 1) ? pk_b : pk_a, idx1,
+                                                     evcur_s + 4u * idx1 - 8u, ent, n_events);
+                            else
+                                scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, (q & 1) ? -delta_a : delta_a, s0i,
+                                                     (uint32_t)(q & 1), idx1, evcur_s + 4u * idx1 - 12u, ent, n_events);
+                            idx1 += idx_step;
+                        }
+                        t += p4;
+                        if (room) cnt_cur += 4 * a.U; else cnt_cur = ev_cap + 1;    // reported as PSRA_E_OVERFLOW below
+                    }
+                    ws->t_run[lane] = t;
+                    nb = (uint32_t)a.static_blocks;
+                    s0mask = __ballot_sync(0xffffffffu, unit_valid && s0u);
+                    int cp = (unit_valid && s0u) ? capu : 0;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) cp += __shfl_xor_sync(0xffffffffu, cp, d);
+                    capacity = cp;
+                    init_wave = false;
+                    if (lane == 0) { ws->diag[1] += (unsigned int)(a.U * a.static_blocks); ws->diag[0] += (unsigned int)a.static_blocks; }
+                    __syncwarp();
+                }
+
                 // ---- waves: one round of <= 32 (unit, block) jobs each, until every unit covers the segment
                 while (true) {
                     const unsigned long long tlast = ws->t_run[lane];
@@ -282,7 +338,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                     if (init_wave) want = unit_valid ? 1 : 0;
                     else if (unit_valid && tlast <= nxt_end_t) {
                         const float rem_h = (float)(int)((nxt_end_t - tlast) >> PSRA_TICK_SHIFT);
-                        want = min(FAST_NB_MAX, 1 + (int)(rem_h * inv_span));
+                        want = min(FAST_NB_MAX, 1 + (int)(rem_h * s_ispan[lane]));
                     }
                     // exclusive prefix / total of a per-lane count in 0..7 from three ballots
                     auto count_scan = [&](int n, int &excl, int &total) {
@@ -330,13 +386,14 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
 
                         uint32_t x[4];
                         philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, b, a.k0, a.k1, x);
+                        const bool blk0 = kTwo && b == 0u;       // block 0 of a stream: draw 0 is the initial state
                         bool s0u;
-                        if (b == 0u) s0u = !(a.init_mode == PSRA_INIT_STATIONARY && x[0] < s_thr[u]);
+                        if (blk0) s0u = !(a.init_mode == PSRA_INIT_STATIONARY && x[0] < s_thr[u]);
                         else s0u = (s0mask >> u) & 1u;
                         const float mup = s_mup[u], mdn = s_mdn[u];
                         const float m_a = s0u ? mdn : mup;      // draws 0, 2 of a block: state s0^1
                         const float m_b = s0u ? mup : mdn;      // draws 1, 3: state s0
-                        const unsigned long long p1 = (b == 0u) ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, kDisc);
+                        const unsigned long long p1 = blk0 ? 0ull : dur_ticks_disc(m_a, x[0], !s0u, kDisc);
                         const unsigned long long p2 = p1 + dur_ticks_disc(m_b, x[1], s0u, kDisc);
                         const unsigned long long p3 = p2 + dur_ticks_disc(m_a, x[2], !s0u, kDisc);
                         const unsigned long long p4 = p3 + dur_ticks_disc(m_b, x[3], s0u, kDisc);
@@ -353,7 +410,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
 
                         const int cu = s_cap[u];
                         const int delta_a = s0u ? cu : -cu;      // draws 0, 2 toggle the unit back to s0
-                        if (b == 0u && act) s0mask = s0u ? 1u : 0u;   // init wave (job lane == unit lane), ballot below
+                        if (blk0 && act) s0mask = s0u ? 1u : 0u;   // init wave (job lane == unit lane), ballot below
                         // hour of an event at tick T: ceil(T / 2^24) - 1 = (T - 1) >> 24 (fits 32 bits: T < 2^56)
                         if constexpr (!kTwo) {
                             // whole chain = one segment: hour in segment = hour in year, ring = year.  Job lane j of a wave
@@ -371,7 +428,6 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
                                 unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
-                                if (q == 0 && b == 0u) tm1 = 0x00800000ull << 32;     // draw 0 of a stream is the initial state
                                 const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
                                 const int delta = (q & 1) ? -delta_a : delta_a;
                                 // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
@@ -392,7 +448,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                             for (int q = 0; q < 4; q++) {
                                 const unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
                                 const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
-                                const bool valid = act && !(b == 0u && q == 0);
+                                const bool valid = act && !(blk0 && q == 0);
                                 const uint32_t rel = hs - (uint32_t)abs0;          // >= 0: events are never generated backwards
                                 const int delta = (q & 1) ? -delta_a : delta_a;
                                 const bool in_ring = valid && rel < ring_len;      // ring_len stops at the chain end
@@ -434,7 +490,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                     nb += (uint32_t)n_u;
                     if (init_wave) {
                         s0mask = __ballot_sync(0xffffffffu, unit_valid && (s0mask & 1u));
-                        int cp = (unit_valid && ((s0mask >> lane) & 1u)) ? capu : 0;
+                        int cp = (unit_valid && ((s0mask >> lane) & 1u)) ? s_cap[lane] : 0;
 #pragma unroll
                         for (int d = 16; d > 0; d >>= 1) cp += __shfl_xor_sync(0xffffffffu, cp, d);
                         capacity = cp;
@@ -442,9 +498,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                     }
                 }
                 if (lane == 0) ws->diag[4] = max(ws->diag[4], (unsigned int)max(cnt_cur, cnt_nxt));
+                bool list_ok = true;
                 if (cnt_cur > ev_cap || cnt_nxt > ev_cap) {      // reported as PSRA_E_OVERFLOW: choose a shorter segment
                     if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 3ull);
                     cnt_cur = min(cnt_cur, ev_cap); cnt_nxt = min(cnt_nxt, ev_cap);
+                    list_ok = false;                             // the links may be garbage: do not walk the lists
                 }
                 if (pend_cnt > FAST_PEND_CAP) {                  // reported as PSRA_E_OVERFLOW (never seen in practice)
                     if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 2ull);
@@ -469,7 +527,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 const int incl = warp_incl_scan(loc, lane);
                 const int cs_lane = capacity + incl - loc;       // capacity entering the lane's run
                 const bool flagged = (lmin != INT_MAX) && (cs_lane + lmin < 0);
-                uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+                uint32_t fm = list_ok ? __ballot_sync(0xffffffffu, flagged) : 0u;
                 if (lane == 0) ws->diag[3] += (unsigned int)__popc(fm);
                 while (fm) {                                     // rare: a run that may contain loss of load
                     const int src = __ffs(fm) - 1;

@@ -330,7 +330,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     // by default the whole year is one segment unless that list would exceed 2048 entries
     auto ev_cap_for = [&](int sw) -> int {
         const double e = h->events_per_hour * sw * 32.0 + h->U;
-        const long long c = std::max(160ll, (long long)(1.75 * e) + 64);
+        const long long c = std::max(512ll, (long long)(1.75 * e) + 64);     // >= 1 static block + a few waves of 128 slots
         return (int)((c + 31) & ~31ll);
     };
     if (one_unit) {
@@ -358,6 +358,18 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     }
     if (fast && a.ev_cap > 2016)
         return psra_fail(h, PSRA_E_INVALID, "unit transition rate too high for the sampler kernel (%d events per 32-hour word)", a.ev_cap);
+    // seq_fast.cu single-segment mode: the first blocks of every unit are generated lane = unit without any scheduling.
+    // Their number: about 0.7 x the mean demand E[blocks] = (1 + 2 H / (MTTF + MTTR) + 1) / 4 per unit (3 for RTS-79;
+    // a simulation of the scheduler puts the optimum of cost = 250 static + 425 per wave there), at least 1
+    // (block 0 holds the initial state), and such that the list keeps room for the waves.
+    a.static_blocks = 1;
+    if (fast && !a.two_halves) {
+        const double mean_blocks = (2.0 + h->events_per_hour * h->H / h->U) / 4.0 + 0.5;
+        int sb = (int)(0.7 * mean_blocks);
+        sb = std::max(1, std::min(sb, a.ev_cap / (8 * h->U)));            // at most half of the list
+        if (h->cfg.reserved[3] > 0) sb = std::min(h->cfg.reserved[3], std::max(1, (a.ev_cap - 160) / (4 * h->U)));
+        a.static_blocks = sb;
+    }
     int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : (fast ? 32 : 16);
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads(a.two_halves != 0) / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {

@@ -137,8 +137,11 @@ def test_sharding_invariance_and_segments(engine, rts):
         assert full.raw[k] == a.raw[k] + b.raw[k]
     for seg, wpb, gen, unp in ((8736, 4, False, False), (1120, 16, False, False), (320, 8, False, False), (32, 2, False, False),
                                (2208, 24, False, False), (8736, 4, True, False), (1120, 16, True, False), (320, 8, True, False),
-                               (8736, 32, False, True), (8736, 7, False, True)):
-        with Engine(seg_hours=seg, warps_per_block=wpb, force_generic=gen, unpacked_words=unp) as e2:
+                               (8736, 32, False, True), (8736, 7, False, True), (8736, 32, False, 1), (8736, 32, False, 2),
+                               (8736, 32, False, 5), (8736, 20, True, 6)):
+        sb = unp if (unp is not True and unp is not False) else 0       # static_blocks variants of the single-segment kernel
+        with Engine(seg_hours=seg, warps_per_block=wpb, force_generic=gen and sb == 0, unpacked_words=unp is True,
+                    static_blocks=sb) as e2:
             e2.set_system(rts["cap"], rts["mttf"], rts["mttr"]); e2.set_load(rts["load_int"])
             r2 = e2.seq_mc(4096, seed=5, per_year=True, group=10)
             assert np.array_equal(full.lol_hours, r2.lol_hours)
