@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                         }
                         t += p4;
                         if (room) cnt_cur += 4 * a.U; else cnt_cur = ev_cap + 1;    // reported as PSRA_E_OVERFLOW below
+                        __syncwarp();                            // the dummy slots of unit-less lanes are the next block's slots
                     }
                     ws->t_run[lane] = t;
                     nb = (uint32_t)a.static_blocks;
