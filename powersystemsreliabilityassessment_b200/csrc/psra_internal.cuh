@@ -111,18 +111,39 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
+// The same generator with the ten round keys read from a table `rk` = {k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85}
+// (r = 0..9) that the host put into the kernel arguments: the keys become constant-bank operands of the
+// LOP3s instead of 20 registers (or 20 uniform adds per block).
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const uint32_t (&rk)[20], uint32_t (&o)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
 // E = -ln(u) of the draw x, u = (x | 1) / 2^32: integer normalisation + binary32 fma polynomial,
 // a fixed sequence of correctly rounded operations (DESIGN.md "Sampler"), reproducible bit for bit
 // on any IEEE-754 machine.  0 < E <= 32 ln 2.
+// Specification (what the CPU checker spells out): w = x | 1, lz = clz(w), X = w << lz,
+// ix = (X >> 8) + 0x3F000000 + 0x004AFB0D (m = X / 2^31 truncated to 24 bits, fdlibm reduction to
+// [sqrt(.5), sqrt(2))), k = lz + 1 - ((ix >> 23) - 127), m' = (ix & 0x7FFFFF) + 0x3F3504F3.
+// Here the normalisation is one conversion: the binary32 value of w rounded toward zero has the
+// exponent field 158 - lz and the same 23 truncated mantissa bits, so iy = bits(RZ(w)) + 0x004AFB0D
+// equals ix + ((31 - lz) << 23): same mantissa field, k = 159 - (iy >> 23).  (float)k comes from the
+// 2^23 trick (0 <= k <= 32), which keeps the conversion off the ALU pipe.  Checked exhaustively
+// (all 2^32 draws) against the specification on the CPU.
 __device__ __forceinline__ float neglog_u32(uint32_t x)
 {
-    const uint32_t w = x | 1u;
-    const int lz = __clz((int)w);
-    const uint32_t X = w << lz;
-    const uint32_t bits = (X >> 8) + 0x3F000000u;           // m = X / 2^31 truncated to 24 bits
-    const uint32_t ix = bits + 0x004AFB0Du;                 // fdlibm range reduction to [sqrt(.5), sqrt(2))
-    const int k = lz + 1 - ((int)(ix >> 23) - 127);
-    const float m = __uint_as_float((ix & 0x007FFFFFu) + 0x3F3504F3u);
+    const uint32_t iy = __float_as_uint(__uint2float_rz(x | 1u)) + 0x004AFB0Du;
+    const float m = __uint_as_float((iy & 0x007FFFFFu) + 0x3F3504F3u);
+    const float kf = __fadd_rn(__uint_as_float((0x4B000000u + 159u) - (iy >> 23)), -8388608.0f);
     const float t = __fadd_rn(m, -1.0f);
     float p = 0x1.65b9f8p-4f;
     p = __fmaf_rn(p, t, -0x1.27c4d6p-3f);
@@ -133,7 +154,6 @@ __device__ __forceinline__ float neglog_u32(uint32_t x)
     p = __fmaf_rn(p, t, 0x1.5557acp-2f);
     p = __fmaf_rn(p, t, -0x1.fffff4p-2f);
     const float r = __fmaf_rn(__fmul_rn(t, t), p, t);       // ln m
-    const float kf = (float)k;
     return __fmaf_rn(kf, 9.0580006145e-06f, __fmaf_rn(kf, 6.9313812256e-01f, -r));
 }
 

@@ -9,6 +9,7 @@ struct SeqArgs {
     const int32_t *load; const int32_t *lmax;
     const int32_t *order;   // units sorted by decreasing transition rate (seq_wide.cu work queue)
     uint32_t k0, k1;
+    uint32_t rk[20];        // Philox round keys {k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85}, r = 0..9 (constant-bank operands)
     long long chain_base;   // absolute index of local chain 0 (Philox counter)
     long long nchains;
     const double *dur;      // injected durations or nullptr

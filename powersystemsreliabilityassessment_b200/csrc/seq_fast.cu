@@ -46,6 +46,13 @@ struct FastWarpSmem {                  // per-warp scratch that precedes the eve
     unsigned char jobmap[32];
 };
 
+// word records a warp keeps: both ring halves, or -- single segment -- the words of the segment padded to 32 equal
+// runs (one run per lane in the evaluation scan; the padding records stay neutral, so the scan needs no bounds checks)
+__host__ __device__ inline int fast_words_alloc(int seg_words, bool two_halves)
+{
+    return two_halves ? ((2 * seg_words + 3) & ~3) : 32 * ((seg_words + 31) / 32);
+}
+
 // two_halves: the ring needs its second half (several segments per year, or multi-year chains)
 // pack: the word's sum and negative sum share one 32-bit integer (single-segment mode only)
 __host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, bool two_halves, bool pack)
@@ -53,14 +60,16 @@ __host__ __device__ inline size_t fast_warp_bytes(int seg_words, int ev_cap, boo
     const int halves = two_halves ? 2 : 1;
     size_t b = sizeof(FastWarpSmem) + (two_halves ? sizeof(uint32_t) * FAST_PEND_CAP : 0) +
                sizeof(uint32_t) * (size_t)halves * ev_cap +                          // event lists
-               (pack ? 2 : 3) * sizeof(int32_t) * (size_t)((halves * seg_words + 3) & ~3);   // per word: {sum, negative sum, list head}
+               (pack ? 2 : 3) * sizeof(int32_t) * (size_t)fast_words_alloc(seg_words, two_halves);   // per word: {sum, negative sum, list head}
     return (b + 15) & ~(size_t)15;
 }
 
+__host__ __device__ inline int fast_lmax_alloc(int Wd) { return 32 * ((Wd + 31) / 32); }
+
 __host__ __device__ inline size_t fast_block_bytes(int Wd, bool load16)
 {
-    size_t b = (load16 ? 2 : 4) * (size_t)Wd * 32 + sizeof(int32_t) * (size_t)((Wd + 3) & ~3);   // load curve + word maxima
-    b += 32 * (sizeof(int32_t) + 3 * sizeof(float) + sizeof(uint32_t));                          // unit tables
+    size_t b = (load16 ? 2 : 4) * (size_t)Wd * 32 + sizeof(int32_t) * (size_t)fast_lmax_alloc(Wd);   // load curve + word maxima
+    b += 32 * (sizeof(int32_t) + 3 * sizeof(float) + sizeof(uint32_t)) + 64 * sizeof(int32_t);        // unit tables
     return (b + 15) & ~(size_t)15;
 }
 
@@ -117,21 +126,25 @@ __device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, ui
 
 // Packed variant: the record is {sum + 2^K * negative sum, head}; `delta` already carries both fields
 // (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.  Out-of-year events as above.
-__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wa, uint32_t wlane, int delta,
+// `wtab` = shared address of the word table: the record of hour `hs` sits at wtab + 8 * (hs >> 5) (one shift, one
+// multiply-add on the FMA pipe).
+__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wtab, uint32_t wlane, int delta,
                                                      uint32_t idx1, uint32_t slot_m4, uint32_t ent, unsigned int &n_events)
 {
-    asm volatile("{\n .reg .pred p;\n .reg .b32 nx, d0, hr, hx;\n"
+    asm volatile("{\n .reg .pred p;\n .reg .b32 nx, d0, hr, hx, wa;\n"
                  " setp.lt.u32 p, %1, %2;\n"
+                 " shr.u32 wa, %1, 5;\n"
+                 " mad.lo.u32 wa, wa, 8, %3;\n"
                  " selp.b32 d0, %5, 0, p;\n"
-                 " selp.b32 hr, %3, %4, p;\n"
-                 " selp.b32 hx, %3, %7, p;\n"
+                 " selp.b32 hr, wa, %4, p;\n"
+                 " selp.b32 hx, wa, %7, p;\n"
                  " red.shared.add.s32 [hr], d0;\n"
                  " atom.shared.exch.b32 nx, [hx+4], %6;\n"
                  " mad.lo.u32 nx, nx, 1048576, %8;\n"
                  " st.shared.b32 [%7+4], nx;\n"
                  " @p add.u32 %0, %0, 1;\n}\n"
                  : "+r"(n_events)
-                 : "r"(hs), "r"(H), "r"(wa), "r"(wlane), "r"(delta), "r"(idx1), "r"(slot_m4), "r"(ent)
+                 : "r"(hs), "r"(H), "r"(wtab), "r"(wlane), "r"(delta), "r"(idx1), "r"(slot_m4), "r"(ent)
                  : "memory");
 }
 
@@ -146,11 +159,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     int32_t *s_load32 = reinterpret_cast<int32_t *>(smem_raw);
     short *s_load16 = reinterpret_cast<short *>(smem_raw);
     int32_t *s_lmax = reinterpret_cast<int32_t *>(smem_raw + (load16 ? 2 : 4) * (size_t)Hpad);
-    int32_t *s_cap = s_lmax + ((a.Wd + 3) & ~3);
+    int32_t *s_cap = s_lmax + fast_lmax_alloc(a.Wd);
     float *s_mup = reinterpret_cast<float *>(s_cap + 32);
     float *s_mdn = s_mup + 32;
     float *s_ispan = s_mdn + 32;         // Philox blocks a unit needs per hour of horizon (a block = 4 durations = 2 up/down cycles)
     uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_ispan + 32);
+    int32_t *s_dcap = reinterpret_cast<int32_t *>(s_thr + 32);     // [(unit << 1) | sign]: signed capacity step of an event-list entry
     constexpr bool two_halves = kTwo;     // the ring needs its second half (several segments per year or multi-year chains)
     const int halves = two_halves ? 2 : 1;
     const int ev_cap = a.ev_cap;
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     uint32_t *evl = pend + (two_halves ? FAST_PEND_CAP : 0);                      // [halves][ev_cap]: (next << 20) | (hour in segment << 6) | (unit << 1) | sign; the events of a
                                                                                   // 32-hour word form a linked list (next = 1 + index, 0 = end)
     const int seg_slots = a.seg_words * 32;
-    const int ring_words = (halves * a.seg_words + 3) & ~3;
+    const int ring_words = fast_words_alloc(a.seg_words, two_halves);
     // one record per 32-hour word: sum of deltas, sum of negative deltas, 1 + index of its newest event (0 = none).
     // kPack: the two sums share one integer v = (sum + 2^(K-1)) + 2^K * neg: |sum| < 2^(K-1), so the biased low field
     // stays in [0, 2^K) and both fields decode with one mask / one shift; the host proves neg > -2^(31-K) for any
@@ -181,10 +195,21 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
         if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
     }
-    for (int i = threadIdx.x; i < a.Wd; i += blockDim.x) s_lmax[i] = a.lmax[i];
+    if constexpr (kTwo) {
+        for (int i = threadIdx.x; i < a.Wd; i += blockDim.x) s_lmax[i] = a.lmax[i];
+    } else {
+        // single segment: word w is word w % wpl of its lane's run; the evaluation scan keeps a running sum of the
+        // *biased* packed sums, so the bias of the words before w in the run is folded into the table here.  Padding
+        // words can never raise a flag.
+        const int wpl0 = (a.Wd + 31) >> 5;
+        for (int i = threadIdx.x; i < fast_lmax_alloc(a.Wd); i += blockDim.x)
+            s_lmax[i] = i < a.Wd ? a.lmax[i] + pk_bias * (i % wpl0) : -(1 << 30);
+    }
     if (threadIdx.x < 32) {
         const bool v = threadIdx.x < a.U;
         s_cap[threadIdx.x] = v ? a.cap[threadIdx.x] : 0;
+        s_dcap[2 * threadIdx.x] = v ? -a.cap[threadIdx.x] : 0;
+        s_dcap[2 * threadIdx.x + 1] = v ? a.cap[threadIdx.x] : 0;
         s_mup[threadIdx.x] = v ? __fmul_rn(a.mttf[threadIdx.x], 16777216.0f) : 1.0f;
         s_mdn[threadIdx.x] = v ? __fmul_rn(a.mttr[threadIdx.x], 16777216.0f) : 1.0f;
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
@@ -192,6 +217,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     }
     for (int i = lane; i < RS * ring_words; i += 32) wtab[i] = (kPack && !(i & 1)) ? pk_bias : 0;
     const uint32_t wtab_s = (uint32_t)__cvta_generic_to_shared(wtab);
+    const uint32_t jobmap_s = (uint32_t)__cvta_generic_to_shared(ws->jobmap);
     const uint32_t wlane_s = wtab_s + 4u * RS * (uint32_t)min(lane, a.seg_words - 1);     // where this lane's out-of-year events add 0
     __syncthreads();
     auto load_at = [&](int i) -> int { return load16 ? (int)s_load16[i] : s_load32[i]; };
@@ -286,7 +312,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                     const uint32_t Uu = (uint32_t)a.U, idx_step = unit_valid ? Uu : 0u;
                     for (int k = 0; k < a.static_blocks; k++) {
                         uint32_t x[4];
-                        philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)lane, (uint32_t)k, a.k0, a.k1, x);
+                        philox4x32_10_rk((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)lane, (uint32_t)k, a.rk, x);
                         if (k == 0) s0u = !(a.init_mode == PSRA_INIT_STATIONARY && x[0] < s_thr[lane]);   // draw 0 = initial state
                         const float m_a = s0u ? mdn : mup;      // draws 0, 2 of a block: state s0^1
                         const float m_b = s0u ? mup : mdn;      // draws 1, 3: state s0
@@ -307,7 +333,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                             const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
                             const uint32_t ent = (hs << 6) + (((uint32_t)lane << 1) | (s0i ^ (uint32_t)(q & 1)));
                             if constexpr (kPack)
-                                scatter_event_packed(hs, (uint32_t)a.H, wtab_s + 8u * (hs >> 5), wlane_s, (q & 1) ? pk_b : pk_a, idx1,
+                                scatter_event_packed(hs, (uint32_t)a.H, wtab_s, wlane_s, (q & 1) ? pk_b : pk_a, idx1,
                                                      evcur_s + 4u * idx1 - 8u, ent, n_events);
                             else
                                 scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, (q & 1) ? -delta_a : delta_a, s0i,
@@ -336,9 +362,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                     const bool is_short = unit_valid && tlast <= seg_end_t;
                     if (!__any_sync(0xffffffffu, is_short)) break;
                     int want = 0;                      // blocks towards the end of the NEXT segment
-                    if (init_wave) want = unit_valid ? 1 : 0;
-                    else if (unit_valid && tlast <= nxt_end_t) {
-                        const float rem_h = (float)(int)((nxt_end_t - tlast) >> PSRA_TICK_SHIFT);
+                    if (kTwo && init_wave) want = unit_valid ? 1 : 0;
+                    else if (kTwo ? (unit_valid && tlast <= nxt_end_t) : is_short) {    // single segment: next end == this end
+                        const float rem_h = (float)(int)(((kTwo ? nxt_end_t : seg_end_t) - tlast) >> PSRA_TICK_SHIFT);
                         want = min(FAST_NB_MAX, 1 + (int)(rem_h * s_ispan[lane]));
                     }
                     // exclusive prefix / total of a per-lane count in 0..7 from three ballots
@@ -373,20 +399,30 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                         if (lane == 0) ws->diag[2] += (unsigned int)(J - J1);
                     }
                     if (lane == 0) { ws->diag[1] += (unsigned int)J; ws->diag[0]++; }
-#pragma unroll
-                    for (int k = 0; k < FAST_NB_MAX; k++)
-                        if (k < n_u) ws->jobmap[off + k] = (unsigned char)lane;   // off + n_u <= 32
+                    // job map: entries off .. off + n_u - 1 name this unit (off + n_u <= 32).  Plain 32-bit shared addresses
+                    // and predicated byte stores: through the generic pointer ptxas rebuilds the shared window base
+                    // (S2R SR_CgaCtaId, LEA) for every store
+                    {
+                        const uint32_t jm_w = jobmap_s + (uint32_t)off;
+                        asm volatile("{\n .reg .pred p0, p1, p2, p3;\n"
+                                     " setp.gt.s32 p0, %2, 0;\n setp.gt.s32 p1, %2, 1;\n setp.gt.s32 p2, %2, 2;\n setp.gt.s32 p3, %2, 3;\n"
+                                     " @p0 st.shared.u8 [%0], %1;\n @p1 st.shared.u8 [%0+1], %1;\n"
+                                     " @p2 st.shared.u8 [%0+2], %1;\n @p3 st.shared.u8 [%0+3], %1;\n}\n"
+                                     :: "r"(jm_w), "r"(lane), "r"(n_u) : "memory");
+                    }
                     __syncwarp();
                     {
                         const bool act = lane < J;               // lane = job
-                        const int u = act ? (int)ws->jobmap[lane] : 0;
+                        int u;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(u) : "r"(jobmap_s + (uint32_t)lane) : "memory");
+                        u = act ? u : 0;
                         const int offu = __shfl_sync(0xffffffffu, off, u);
                         const int nu = __shfl_sync(0xffffffffu, n_u, u);
                         const uint32_t b = __shfl_sync(0xffffffffu, nb, u) + (uint32_t)(lane - offu);
                         const bool is_last = act && (lane - offu) == nu - 1;
 
                         uint32_t x[4];
-                        philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, b, a.k0, a.k1, x);
+                        philox4x32_10_rk((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, b, a.rk, x);
                         const bool blk0 = kTwo && b == 0u;       // block 0 of a stream: draw 0 is the initial state
                         bool s0u;
                         if (blk0) s0u = !(a.init_mode == PSRA_INIT_STATIONARY && x[0] < s_thr[u]);
@@ -434,7 +470,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                                 // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
                                 const uint32_t ent = (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1)));
                                 if constexpr (kPack)
-                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s + 8u * (hs >> 5), wlane_s, (q & 1) ? pk_b : pk_a, idx1,
+                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s, wlane_s, (q & 1) ? pk_b : pk_a, idx1,
                                                          evcur_s + 4u * idx1 - 8u, ent, n_events);
                                 else
                                     scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, delta, s0i, (uint32_t)(q & 1), idx1,
@@ -516,14 +552,29 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 const int wpl = (nwords + 31) >> 5;
                 const int wb = lane * wpl;
                 int loc = 0, lmin = INT_MAX;
-                for (int k = 0; k < wpl; k++) {
-                    const int w = wb + k;
-                    if (w < nwords) {
-                        int sm, ng;
-                        word_sums(wbase_cur + w, sm, ng);
-                        lmin = min(lmin, loc + ng - s_lmax[seg * a.seg_words + w]);
-                        loc += sm;
+                if constexpr (kTwo) {
+                    for (int k = 0; k < wpl; k++) {
+                        const int w = wb + k;
+                        if (w < nwords) {
+                            int sm, ng;
+                            word_sums(wbase_cur + w, sm, ng);
+                            lmin = min(lmin, loc + ng - s_lmax[seg * a.seg_words + w]);
+                            loc += sm;
+                        }
                     }
+                } else {
+                    // every lane owns wpl records (the table is padded with neutral ones): no bounds checks, and the
+                    // running sum keeps the packing bias (s_lmax carries the same bias, see above)
+                    const int32_t *wp = wtab + RS * wb;
+                    const int32_t *lp = s_lmax + wb;
+                    for (int k = 0; k < wpl; k++) {
+                        int smb, ng;
+                        if constexpr (kPack) { const int v = wp[RS * k]; smb = v & pk_mask; ng = v >> pk; }
+                        else { smb = wp[RS * k]; ng = wp[RS * k + 1]; }
+                        lmin = min(lmin, loc + ng - lp[k]);
+                        loc += smb;
+                    }
+                    loc -= wpl * pk_bias;
                 }
                 const int incl = warp_incl_scan(loc, lane);
                 const int cs_lane = capacity + incl - loc;       // capacity entering the lane's run
@@ -549,7 +600,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                             if (lane >= d) ws_i += o;
                         }
                         c_word += ws_i - ws_l;
-                        if (mine) wflag = c_word + wn_l < s_lmax[seg * a.seg_words + wq];
+                        if (mine) wflag = c_word + wn_l < (kTwo ? s_lmax[seg * a.seg_words + wq] : s_lmax[wq] - pk_bias * lane);
                     }
                     uint32_t wm = __ballot_sync(0xffffffffu, wflag);
                     while (wm) {                                 // resolve the word hour by hour, lane = hour
@@ -560,10 +611,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                         int d = 0;                               // delta of hour `lane` of the word: walk its event list
                         for (uint32_t i = WHEAD(wbase_cur + wq); i; ) {
                             const uint32_t e = ev_cur[i - 1];
-                            if (((e >> 6) & 31u) == (uint32_t)lane) {
-                                const int c = s_cap[(e >> 1) & 31];
-                                d += (e & 1u) ? c : -c;
-                            }
+                            if (((e >> 6) & 31u) == (uint32_t)lane) d += s_dcap[e & 63u];
                             i = e >> 20;
                         }
                         const int c = c_in + warp_incl_scan(d, lane);
@@ -608,9 +656,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 if (a.ent) a.ent[yi] = entries;
                 if (a.group_lol && lolh) atomicAdd(&a.group_lol[yi / a.group], (unsigned long long)lolh);
             }
-            if (lane == 0) {
+            if (lolh && lane == 0) {             // a year without loss of load adds nothing (ENS and entries are 0 as well)
                 ws->acc[0] += lolh; ws->acc[1] += (unsigned long long)ens; ws->acc[2] += entries;
-                ws->acc[3] += lolh ? 1ull : 0ull;
+                ws->acc[3] += 1ull;
                 ws->acc[4] += (unsigned long long)lolh * lolh;
                 const unsigned long long e = (unsigned long long)ens;
                 const unsigned long long plo = e * e, phi = __umul64hi(e, e);

@@ -314,6 +314,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     a.cap = h->d_cap; a.mttf = h->d_mttf; a.mttr = h->d_mttr; a.for_thr = h->d_for_thr;
     a.load = h->d_load; a.lmax = h->d_lmax;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { a.rk[2 * r] = a.k0 + (uint32_t)r * 0x9E3779B9u; a.rk[2 * r + 1] = a.k1 + (uint32_t)r * 0xBB67AE85u; }
     a.chain_base = chain_base; a.nchains = nchains;
     a.acc = h->d_acc;
     a.load16 = load16 ? 1 : 0;

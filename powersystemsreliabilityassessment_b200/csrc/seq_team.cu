@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 3) seq_team_kernel(const SeqA
                             const uint32_t b = __shfl_sync(0xffffffffu, nb, ul) + (uint32_t)(lane - offu);
                             const bool is_last = act && (lane - offu) == nu - 1;
                             uint32_t x[4];
-                            philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, b, a.k0, a.k1, x);
+                            philox4x32_10_rk((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, b, a.rk, x);
                             bool s0u;
                             if (b == 0u) s0u = !(a.init_mode == PSRA_INIT_STATIONARY && x[0] < s_thr[u]);
                             else s0u = (s0mask >> ul) & 1u;

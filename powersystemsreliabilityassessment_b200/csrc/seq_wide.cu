@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
         if (busy) take_unit();
         while (__any_sync(0xffffffffu, busy)) {
             uint32_t x[4];
-            philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, nb, a.k0, a.k1, x);
+            philox4x32_10_rk((uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)u, nb, a.rk, x);
             const bool first = nb == 0u;
             if (first) {                    // draw 0 of a stream is the initial state
                 s0u = !(stationary && x[0] < thr);
