@@ -141,9 +141,17 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
 // (all 2^32 draws) against the specification on the CPU.
 __device__ __forceinline__ float neglog_u32(uint32_t x)
 {
-    const uint32_t iy = __float_as_uint(__uint2float_rz(x | 1u)) + 0x004AFB0Du;
-    const float m = __uint_as_float((iy & 0x007FFFFFu) + 0x3F3504F3u);
-    const float kf = __fadd_rn(__uint_as_float((0x4B000000u + 159u) - (iy >> 23)), -8388608.0f);
+    // Pipe balance (the integer ALU pipe is what limits the sequential kernels): with e = (fw + 0x004AFB0D) >> 23 the
+    // mantissa of m is fw + 0x3F800000 - (e << 23) (one IMAD; 0x004AFB0D + 0x3F3504F3 = 0x3F800000), and
+    // 2k = 2 * (159 - e) is built as a float by an IMAD with the factor -2 (ptxas turns a factor -1 into an ALU
+    // subtract); the two ln 2 constants below are halved instead -- exact scalings, so every fma rounds as specified.
+    const uint32_t fw = __float_as_uint(__uint2float_rz(x | 1u));
+    const uint32_t e = (fw + 0x004AFB0Du) >> 23;
+    uint32_t mb, kb;
+    asm("mad.lo.u32 %0, %1, 0xFF800000, %2;" : "=r"(mb) : "r"(e), "r"(fw + 0x3F800000u));
+    asm("mad.lo.u32 %0, %1, 0xFFFFFFFE, %2;" : "=r"(kb) : "r"(e), "r"(0x4B00013Eu));
+    const float m = __uint_as_float(mb);
+    const float kf2 = __fadd_rn(__uint_as_float(kb), -8388608.0f);     // 2 k, 0 <= k <= 32
     const float t = __fadd_rn(m, -1.0f);
     float p = 0x1.65b9f8p-4f;
     p = __fmaf_rn(p, t, -0x1.27c4d6p-3f);
@@ -154,7 +162,8 @@ __device__ __forceinline__ float neglog_u32(uint32_t x)
     p = __fmaf_rn(p, t, 0x1.5557acp-2f);
     p = __fmaf_rn(p, t, -0x1.fffff4p-2f);
     const float r = __fmaf_rn(__fmul_rn(t, t), p, t);       // ln m
-    return __fmaf_rn(kf, 9.0580006145e-06f, __fmaf_rn(kf, 6.9313812256e-01f, -r));
+    // k * 9.0580006145e-06 + (k * 6.9313812256e-01 - r), written with 2k and the halved constants
+    return __fmaf_rn(kf2, 0x1.2fefa2p-18f, __fmaf_rn(kf2, 0x1.62e3p-2f, -r));
 }
 
 // duration of one draw in ticks of 2^-24 h: RN_int64(max(mean_ticks * E, 1)), mean_ticks = mean * 2^24
@@ -172,13 +181,13 @@ __device__ __forceinline__ unsigned long long dur_ticks_disc(float mean_ticks, u
     return t;
 }
 
-__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+// inclusive warp prefix sum; the shuffle's own "source lane in range" predicate guards the add (no lane compares)
+__device__ __forceinline__ int warp_incl_scan(int v, int /*lane*/)
 {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += o;
-    }
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n .reg .pred p;\n .reg .b32 o;\n shfl.sync.up.b32 o|p, %0, %1, 0, 0xffffffff;\n @p add.s32 %0, %0, o;\n}\n"
+                     : "+r"(v) : "r"(d));
     return v;
 }
 

@@ -125,26 +125,27 @@ __device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, ui
 }
 
 // Packed variant: the record is {sum + 2^K * negative sum, head}; `delta` already carries both fields
-// (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.  Out-of-year events as above.
-// `wtab` = shared address of the word table: the record of hour `hs` sits at wtab + 8 * (hs >> 5) (one shift, one
-// multiply-add on the FMA pipe).
-__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wtab, uint32_t wlane, int delta,
-                                                     uint32_t idx1, uint32_t slot_m4, uint32_t ent, unsigned int &n_events)
+// (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.  `wtab` = shared address of
+// the word table: the record of hour `hs` sits at wtab + 8 * (hs >> 5), its head 4 bytes further (one shift, two
+// multiply-adds on the FMA pipe).  An out-of-year event does both atomics on the lane's own list slot (`slot`,
+// never linked and overwritten by the store below), so the delta needs no select.
+__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wtab, int delta,
+                                                     uint32_t idx1, uint32_t slot, uint32_t ent, unsigned int &n_events)
 {
-    asm volatile("{\n .reg .pred p;\n .reg .b32 nx, d0, hr, hx, wa;\n"
+    asm volatile("{\n .reg .pred p;\n .reg .b32 nx, hr, hx, w;\n"
                  " setp.lt.u32 p, %1, %2;\n"
-                 " shr.u32 wa, %1, 5;\n"
-                 " mad.lo.u32 wa, wa, 8, %3;\n"
-                 " selp.b32 d0, %5, 0, p;\n"
-                 " selp.b32 hr, wa, %4, p;\n"
-                 " selp.b32 hx, wa, %7, p;\n"
-                 " red.shared.add.s32 [hr], d0;\n"
-                 " atom.shared.exch.b32 nx, [hx+4], %6;\n"
-                 " mad.lo.u32 nx, nx, 1048576, %8;\n"
-                 " st.shared.b32 [%7+4], nx;\n"
+                 " shr.u32 w, %1, 5;\n"
+                 " mad.lo.u32 hr, w, 8, %3;\n"
+                 " mad.lo.u32 hx, w, 8, %8;\n"
+                 " selp.b32 hr, hr, %6, p;\n"
+                 " selp.b32 hx, hx, %6, p;\n"
+                 " red.shared.add.s32 [hr], %4;\n"
+                 " atom.shared.exch.b32 nx, [hx], %5;\n"
+                 " mad.lo.u32 nx, nx, 1048576, %7;\n"
+                 " st.shared.b32 [%6], nx;\n"
                  " @p add.u32 %0, %0, 1;\n}\n"
                  : "+r"(n_events)
-                 : "r"(hs), "r"(H), "r"(wtab), "r"(wlane), "r"(delta), "r"(idx1), "r"(slot_m4), "r"(ent)
+                 : "r"(hs), "r"(H), "r"(wtab), "r"(delta), "r"(idx1), "r"(slot), "r"(ent), "r"(wtab + 4u)
                  : "memory");
 }
 
@@ -333,8 +334,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                             const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
                             const uint32_t ent = (hs << 6) + (((uint32_t)lane << 1) | (s0i ^ (uint32_t)(q & 1)));
                             if constexpr (kPack)
-                                scatter_event_packed(hs, (uint32_t)a.H, wtab_s, wlane_s, (q & 1) ? pk_b : pk_a, idx1,
-                                                     evcur_s + 4u * idx1 - 8u, ent, n_events);
+                                scatter_event_packed(hs, (uint32_t)a.H, wtab_s, (q & 1) ? pk_b : pk_a, idx1,
+                                                     evcur_s + 4u * idx1 - 4u, ent, n_events);
                             else
                                 scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, (q & 1) ? -delta_a : delta_a, s0i,
                                                      (uint32_t)(q & 1), idx1, evcur_s + 4u * idx1 - 12u, ent, n_events);
@@ -470,8 +471,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                                 // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
                                 const uint32_t ent = (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1)));
                                 if constexpr (kPack)
-                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s, wlane_s, (q & 1) ? pk_b : pk_a, idx1,
-                                                         evcur_s + 4u * idx1 - 8u, ent, n_events);
+                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s, (q & 1) ? pk_b : pk_a, idx1,
+                                                         evcur_s + 4u * idx1 - 4u, ent, n_events);
                                 else
                                     scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, delta, s0i, (uint32_t)(q & 1), idx1,
                                                          evcur_s + 4u * idx1 - 12u, ent, n_events);
