@@ -197,6 +197,13 @@ int psra_dtmc_capacity(psra_handle *h, const double *mttf_h, const double *mttr_
 int psra_failure_times(psra_handle *h, double lambda, double dt, double max_time, int64_t n, uint64_t seed,
                        const double *r, int32_t K, double *failure_time);
 
+/* Sampler diagnostic: what the sequential kernels make of a 32-bit draw.  e_bits[i] = the binary32
+ * bit pattern of E(draws[i]) = -ln((draw | 1) / 2^32) as the kernels compute it, ticks[i] = the duration
+ * RN_int64(max(RN_f32(RN_f32(mean_h * 2^24) * E), 1)) in ticks of 2^-24 h that replaces the reference's
+ * -log(rand()) / rate (PowerSystemAdequacy.jl:224,243,246).  Either output may be NULL.  Lets a test compare the
+ * device logarithm draw by draw (edge draws included) with its CPU specification. */
+int psra_sampler_durations(psra_handle *h, float mean_h, const uint32_t *draws, int64_t n, uint64_t *ticks, uint32_t *e_bits);
+
 /* tail risk over per-year ENS: outputs of tail_risk.jl:18-19,79-90,168-175 plus the
  * VaR / CVaR build-side spec: VaR_a = type-7 quantile
  * (position 1+(N-1)a, linear interpolation), CVaR_a = mean of values >= VaR_a. ---------- */

@@ -47,6 +47,8 @@ def lib():
         L.oracle_neglog_u32.argtypes = [C.c_uint32]
         L.oracle_duration_hours.restype = C.c_double
         L.oracle_duration_hours.argtypes = [C.c_float, C.c_uint32]
+        L.oracle_sampler_durations.restype = None
+        L.oracle_sampler_durations.argtypes = [C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         L.oracle_seq_philox.restype = C.c_int
         L.oracle_seq_philox.argtypes = [C.c_int, _dp, _fp, _fp, _u32p, C.c_int, _dp, C.c_uint64,
                                         C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp]
@@ -201,6 +203,15 @@ def philox(ctr, key):
 
 def duration_hours(mean: float, x: int) -> float:
     return float(lib().oracle_duration_hours(float(np.float32(mean)), int(x)))
+
+
+def sampler_durations(mean: float, draws):
+    """(ticks, e_bits) of an array of 32-bit draws: the sampler specification of DESIGN.md 3.2, draw by draw."""
+    x = np.ascontiguousarray(draws, dtype=np.uint32)
+    ticks = np.zeros(x.size, dtype=np.uint64)
+    ebits = np.zeros(x.size, dtype=np.uint32)
+    lib().oracle_sampler_durations(float(np.float32(mean)), x.ctypes.data, x.size, ticks.ctypes.data, ebits.ctypes.data)
+    return ticks, ebits
 
 
 def neglog_u32(x: int) -> float:

@@ -168,6 +168,17 @@ static double duration_hours(float mean_f32, uint32_t x)
 
 double oracle_duration_hours(float mean_f32, uint32_t x) { return duration_hours(mean_f32, x); }
 
+/* vector form for the per-draw parity test of the device sampler: ticks of 2^-24 h and the bits of E */
+void oracle_sampler_durations(float mean_f32, const uint32_t *draws, long long n, uint64_t *ticks, uint32_t *e_bits)
+{
+    float mt = mean_f32 * 16777216.0f;
+    for (long long i = 0; i < n; i++) {
+        float e = oracle_neglog_u32(draws[i]);
+        if (e_bits) memcpy(&e_bits[i], &e, 4);
+        if (ticks) ticks[i] = (uint64_t)llrintf(fmaxf(mt * e, 1.0f));
+    }
+}
+
 /* Per-(chain, unit) draw stream: draw j lives in Philox block j/4, word j%4. */
 typedef struct { uint32_t key[2]; uint32_t ctr[4]; uint32_t buf[4]; uint32_t j; } draw_stream;
 

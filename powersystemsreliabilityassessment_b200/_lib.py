@@ -26,7 +26,7 @@ EXPORTS = [
     "psra_set_system", "psra_set_load", "psra_seq_mc", "psra_seq_eval_injected", "psra_nonseq_mc",
     "psra_nonseq_eval_states", "psra_nonseq_eval_uniforms", "psra_copt", "psra_copt_indices",
     "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail", "psra_detailed_mc", "psra_detailed_eval_injected",
-    "psra_multi_area_mc", "psra_failure_times",
+    "psra_multi_area_mc", "psra_failure_times", "psra_sampler_durations",
 ]
 
 
@@ -133,6 +133,8 @@ def load():
     L.psra_dtmc_capacity.restype = C.c_int; L.psra_dtmc_capacity.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp]
     L.psra_failure_times.restype = C.c_int
     L.psra_failure_times.argtypes = [vp, dbl, dbl, dbl, i64, u64, vp, i32, vp]
+    L.psra_sampler_durations.restype = C.c_int
+    L.psra_sampler_durations.argtypes = [vp, C.c_float, vp, i64, vp, vp]
     L.psra_tail.restype = C.c_int
     L.psra_tail.argtypes = [vp, vp, i64, vp, i32, C.POINTER(TailOut), vp, i32, i64]
     L.psra_detailed_mc.restype = C.c_int

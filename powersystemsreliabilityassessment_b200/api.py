@@ -413,6 +413,15 @@ class Engine:
         return out[out >= 0.0]
 
     # ---- multi-area adequacy (AdequacyAssessmentII.jl)
+    def sampler_durations(self, mean_h: float, draws):
+        """Sampler diagnostic: (ticks, e_bits) of 32-bit draws -- the duration in ticks of 2^-24 h that stands for
+        -log(rand()) / rate (PowerSystemAdequacy.jl:224,243,246) and the bit pattern of the device's E = -ln(u)."""
+        x = np.ascontiguousarray(draws, dtype=np.uint32)
+        ticks = np.zeros(x.size, dtype=np.uint64)
+        ebits = np.zeros(x.size, dtype=np.uint32)
+        self._check(self._L.psra_sampler_durations(self._h, float(mean_h), _ptr(x), x.size, _ptr(ticks), _ptr(ebits)))
+        return ticks, ebits
+
     def multi_area_mc(self, unit_area, cap, mttf, mttr, loads, topology, policy: int, years: int, seed: int = 42,
                       year0: int = 0, init_mode: int = INIT_STATIONARY, per_year: bool = False, fp_scale: float = 1.0,
                       strict: bool = True):

@@ -569,3 +569,35 @@ extern "C" int psra_seq_eval_injected(psra_handle *h, const double *durations, i
         if (!(durations[i] > 0.0)) return psra_fail(h, PSRA_E_INVALID, "injected durations must be > 0 (entry %zu)", i);
     return run_seq(h, true, durations, K, 0, nchains, years_per_chain, PSRA_INIT_ALL_UP, 0, out, summary);
 }
+
+// ------------------------------------------------------------------------------- sampler diagnostic
+__global__ void sampler_durations_kernel(float mean_ticks, const uint32_t *__restrict__ draws, long long n,
+                                         unsigned long long *__restrict__ ticks, uint32_t *__restrict__ e_bits)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t x = draws[i];
+        if (e_bits) e_bits[i] = __float_as_uint(neglog_u32(x));
+        if (ticks) ticks[i] = dur_ticks(mean_ticks, x);
+    }
+}
+
+extern "C" int psra_sampler_durations(psra_handle *h, float mean_h, const uint32_t *draws, int64_t n, uint64_t *ticks, uint32_t *e_bits)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, draws && n >= 1 && (ticks || e_bits), "null argument / empty input");
+    PSRA_REQUIRE(h, mean_h > 0.0f && mean_h < 1.0e9f, "mean duration must be positive (hours)");
+    PSRA_CUDA(h, cudaSetDevice(h->device));
+    int rc = psra_reserve(h, &h->d_scratch, &h->scratch_cap, (size_t)n * (sizeof(uint32_t) * 2 + sizeof(uint64_t)));
+    if (rc) return rc;
+    unsigned long long *d_t = (unsigned long long *)h->d_scratch;
+    uint32_t *d_x = (uint32_t *)(d_t + n), *d_e = d_x + n;
+    PSRA_CUDA(h, cudaMemcpyAsync(d_x, draws, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 8);
+    sampler_durations_kernel<<<grid, 256, 0, h->stream>>>(mean_h * 16777216.0f, d_x, n, ticks ? d_t : nullptr, e_bits ? d_e : nullptr);
+    PSRA_CUDA(h, cudaGetLastError());
+    if (ticks) PSRA_CUDA(h, cudaMemcpyAsync(ticks, d_t, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (e_bits) PSRA_CUDA(h, cudaMemcpyAsync(e_bits, d_e, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PSRA_OK;
+}

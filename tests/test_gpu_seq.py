@@ -316,3 +316,22 @@ def test_high_transition_rate_short_segments(engine):
         assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(r.entries.astype(np.float64), ent)
         assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
         assert r.raw["events"] > 30000 * 12 * ypc and lol.sum() > 100
+
+
+@pytest.mark.gpu
+def test_sampler_logarithm_draw_by_draw(engine):
+    """The device logarithm / tick duration of single draws against the CPU specification: edge draws (0, 1, all ones,
+    powers of two and their neighbours, the sqrt(1/2) reduction boundary), a stride over the whole 32-bit range and
+    random draws; several means incl. durations below one tick and above 2^32 ticks."""
+    rng = np.random.default_rng(5)
+    edge = [0, 1, 2, 3, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF, 0x80000001, 0xB504F333, 0xB504F334, 0xB504F332,
+            0x5A827999, 0x5A82799A, 0x00B504F3, 0x00000100, 0x000000FF, 0x01000000, 0x00FFFFFF]
+    edge += [1 << k for k in range(32)] + [(1 << k) - 1 for k in range(1, 32)] + [(1 << k) + 1 for k in range(1, 32)]
+    draws = np.concatenate([np.array(edge, dtype=np.uint64), np.arange(0, 1 << 32, 1021, dtype=np.uint64),
+                            rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64)]).astype(np.uint32)
+    for mean in (2940.0, 450.0, 20.0, 0.1, 1e-7, 3.0e5):
+        t_gpu, e_gpu = engine.sampler_durations(mean, draws)
+        t_cpu, e_cpu = O.sampler_durations(mean, draws)
+        assert np.array_equal(e_gpu, e_cpu)
+        assert np.array_equal(t_gpu, t_cpu)
+    assert t_cpu.max() > (1 << 32) and O.sampler_durations(1e-7, draws)[0].min() == 1

@@ -186,3 +186,32 @@ def test_multi_area_curtailment_solver_known_cases():
     assert np.array_equal(lol[:, 0], l0) and np.array_equal(eue[:, 0], e0)
     lc, ec = O.multi_area_philox(ua, cap, mttf, mttr, loads, t2, 1, 3, 0, 6, 1)
     assert ec.sum() < eue.sum() and (lc <= lol + 1e-9).all() is not None
+
+
+def test_sampler_vector_form_and_device_front_end_identity():
+    """(i) the vector form used by the per-draw GPU test equals the scalar specification; (ii) the integer front end
+    the CUDA kernels use for the logarithm (one round-toward-zero int->float conversion, psra_internal.cuh neglog_u32)
+    yields the same mantissa bits and the same k as the clz / shift specification, over edge draws and a stride
+    through the whole 32-bit range."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([np.array([0, 1, 2, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 0xB504F333, 0xB504F334], dtype=np.uint64),
+                        np.arange(0, 1 << 32, 4099, dtype=np.uint64), rng.integers(0, 1 << 32, 100000, dtype=np.uint64)])
+    x32 = x.astype(np.uint32)
+    ticks, ebits = O.sampler_durations(450.0, x32[:2000])
+    for i in range(0, 2000, 37):
+        assert ebits[i] == np.float32(O.neglog_u32(int(x32[i]))).view(np.uint32)
+        assert ticks[i] == round(O.duration_hours(450.0, int(x32[i])) * 2 ** 24)
+    # specification
+    w = x | 1
+    lz = 32 - np.floor(np.log2(w.astype(np.float64))).astype(np.int64) - 1
+    X = (w << lz.astype(np.uint64)) & 0xFFFFFFFF
+    ix = (X >> 8) + 0x3F000000 + 0x004AFB0D
+    k_spec = lz + 1 - ((ix >> 23).astype(np.int64) - 127)
+    m_spec = (ix & 0x007FFFFF) + 0x3F3504F3
+    # device formulation: fw = bits of RZ_f32(w): exponent field 158 - lz, 23 truncated mantissa bits
+    fw = ((158 - lz).astype(np.uint64) << 23) | ((X >> 8) & 0x7FFFFF)
+    e = (fw + 0x004AFB0D) >> 23
+    m_dev = (fw + 0x3F800000 - (e << 23)) & 0xFFFFFFFF
+    k2_dev = (0x4B00013E - 2 * e.astype(np.int64)) - 0x4B000000          # the float built by the IMAD, minus 2^23
+    assert np.array_equal(m_dev, m_spec)
+    assert np.array_equal(k2_dev, 2 * k_spec) and k_spec.min() >= 0 and k_spec.max() <= 32
