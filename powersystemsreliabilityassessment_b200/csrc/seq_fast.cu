@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
 
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
-    const int chain_end_h = a.ypc * a.H;
+    // single-segment variant: one year per chain, one segment per year -- the loop bounds and the ring geometry below
+    // are compile-time facts there
+    const int n_ypc = kTwo ? a.ypc : 1, n_seg = kTwo ? a.nseg : 1;
+    const int chain_end_h = n_ypc * a.H;
 
     for (long long cl = gw; cl < a.nchains; cl += nw) {
         const unsigned long long chain = (unsigned long long)(a.chain_base + cl);
@@ -247,25 +250,26 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
         __syncwarp();
         bool init_wave = kTwo;          // single-segment mode: block 0 of every unit belongs to the static phase
 
-        for (int y = 0; y < a.ypc; y++) {
+        for (int y = 0; y < n_ypc; y++) {
             unsigned int lolh = 0, entries = 0;
             long long ens_lane = 0;
-            for (int seg = 0; seg < a.nseg; seg++, ring ^= 1) {
-                const int seg_h0 = seg * seg_slots;
-                const int seg_h1 = min(a.H, seg_h0 + seg_slots);
+            for (int seg = 0; seg < n_seg; seg++, ring ^= 1) {
+                const int seg_h0 = kTwo ? seg * seg_slots : 0;
+                const int seg_h1 = kTwo ? min(a.H, seg_h0 + seg_slots) : a.H;
                 const int abs0 = y * a.H + seg_h0, abs1 = y * a.H + seg_h1;   // chain-relative hours
                 // the segment after this one (same year or first of the next year) lives in the other half
-                const int nxt_h0 = (seg + 1 < a.nseg) ? seg_h0 + seg_slots : 0;
-                const int abs2 = min(chain_end_h, abs1 + min(seg_slots, a.H - nxt_h0));
+                const int nxt_h0 = (seg + 1 < n_seg) ? seg_h0 + seg_slots : 0;
+                const int abs2 = kTwo ? min(chain_end_h, abs1 + min(seg_slots, a.H - nxt_h0)) : a.H;
                 const unsigned long long seg_end_t = (unsigned long long)abs1 << PSRA_TICK_SHIFT;
                 const unsigned long long nxt_end_t = (unsigned long long)abs2 << PSRA_TICK_SHIFT;
                 // ring geometry: an event `rel` hours after abs0 belongs to the current half when rel < len_cur,
                 // otherwise to the other half (which holds the next segment from its hour 0)
                 const uint32_t len_cur = (uint32_t)(seg_h1 - seg_h0);
                 const uint32_t ring_len = (uint32_t)(abs2 - abs0);
-                const int wbase_cur = ring * a.seg_words, wbase_nxt = (ring ^ 1) * a.seg_words;
-                uint32_t *ev_cur = evl + (size_t)ring * ev_cap, *ev_nxt = evl + (size_t)(ring ^ 1) * ev_cap;
-                int cnt_cur = ring ? ev_cnt1 : ev_cnt0, cnt_nxt = ring ? ev_cnt0 : ev_cnt1;
+                const int ringc = kTwo ? ring : 0;
+                const int wbase_cur = ringc * a.seg_words, wbase_nxt = (ringc ^ 1) * a.seg_words;
+                uint32_t *ev_cur = evl + (size_t)ringc * ev_cap, *ev_nxt = kTwo ? evl + (size_t)(ringc ^ 1) * ev_cap : evl;
+                int cnt_cur = kTwo ? (ring ? ev_cnt1 : ev_cnt0) : 0, cnt_nxt = kTwo ? (ring ? ev_cnt0 : ev_cnt1) : 0;
                 const uint32_t evcur_s = (uint32_t)__cvta_generic_to_shared(ev_cur), evnxt_s = (uint32_t)__cvta_generic_to_shared(ev_nxt);
 
                 // ---- far-future events that now fall into the next segment's half
@@ -549,7 +553,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 __syncwarp();
 
                 // ---- evaluation of the current half: lane = run of `wpl` consecutive words
-                const int nwords = (seg_h1 - seg_h0 + 31) >> 5;
+                const int nwords = kTwo ? (seg_h1 - seg_h0 + 31) >> 5 : a.Wd;
                 const int wpl = (nwords + 31) >> 5;
                 const int wb = lane * wpl;
                 int loc = 0, lmin = INT_MAX;
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 } else {
                     for (int i = lane; i < RS * nwords; i += 32) wtab[RS * wbase_cur + i] = 0;
                 }
-                if (ring) { ev_cnt1 = 0; ev_cnt0 = cnt_nxt; } else { ev_cnt0 = 0; ev_cnt1 = cnt_nxt; }
+                if constexpr (kTwo) { if (ring) { ev_cnt1 = 0; ev_cnt0 = cnt_nxt; } else { ev_cnt0 = 0; ev_cnt1 = cnt_nxt; } }
                 __syncwarp();
                 if (!two_halves) ring ^= 1;                      // single half: undo the toggle of the loop header
             }
@@ -650,7 +654,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
             // ---- per-year indices
             long long ens = 0;
             if (lolh) ens = warp_sum_ll(ens_lane);
-            const long long yi = cl * a.ypc + y;
+            const long long yi = kTwo ? cl * a.ypc + y : cl;
             if (lane == 0) {
                 if (a.lol) a.lol[yi] = lolh;
                 if (a.ens) a.ens[yi] = ens;
