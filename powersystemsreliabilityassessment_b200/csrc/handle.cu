@@ -206,7 +206,7 @@ extern "C" void psra_destroy(psra_handle *h)
     cudaSetDevice(h->device);
     void *bufs[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_load, h->d_lmax,
                     h->d_load_sorted, h->d_load_suffix, h->d_acc, h->d_lol, h->d_ens, h->d_ent, h->d_fail,
-                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order, h->d_hist, h->d_lol_tab, h->d_byte_tab};
+                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order, h->d_hist, h->d_lol_tab, h->d_byte_tab, h->d_wide_tab};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -247,10 +247,10 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     }
     PSRA_REQUIRE(h, total <= 0x3fffffff, "installed capacity exceeds the int32 fixed-point range");
     if (U != h->U || !h->d_cap) {      // (re)allocate only when the unit count changes
-        void *old[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_order};
+        void *old[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_order, h->d_wide_tab};
         for (void *p : old)
             if (p) cudaFree(p);
-        h->d_cap = nullptr; h->d_mttf = nullptr; h->d_mttr = nullptr; h->d_for_thr = nullptr; h->d_for = nullptr; h->d_order = nullptr;
+        h->d_cap = nullptr; h->d_mttf = nullptr; h->d_mttr = nullptr; h->d_for_thr = nullptr; h->d_for = nullptr; h->d_order = nullptr; h->d_wide_tab = nullptr;
         h->U = 0;
         PSRA_CUDA(h, cudaMalloc(&h->d_cap, sizeof(int32_t) * U));
         PSRA_CUDA(h, cudaMalloc(&h->d_mttf, sizeof(float) * U));
@@ -258,6 +258,7 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
         PSRA_CUDA(h, cudaMalloc(&h->d_for_thr, sizeof(uint32_t) * U));
         PSRA_CUDA(h, cudaMalloc(&h->d_for, sizeof(double) * U));
         PSRA_CUDA(h, cudaMalloc(&h->d_order, sizeof(int32_t) * U));
+        PSRA_CUDA(h, cudaMalloc(&h->d_wide_tab, sizeof(uint4) * U));
     }
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_cap, cap_fp, sizeof(int32_t) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_mttf, mf.data(), sizeof(float) * U, cudaMemcpyHostToDevice, h->stream));
@@ -268,6 +269,16 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     for (int u = 0; u < U; u++) order[u] = u;
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return mttf_h[x] + mttr_h[x] < mttf_h[y] + mttr_h[y]; });
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_order, order.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, h->stream));
+    // one 16-byte record per queue position for seq_wide.cu (the means already in ticks: a power-of-two scaling, exact)
+    std::vector<uint4> wtab(U);
+    for (int k = 0; k < U; k++) {
+        const int u = order[k];
+        const float mup = mf[u] * 16777216.0f, mdn = mr[u] * 16777216.0f;
+        uint32_t bu, bd;
+        memcpy(&bu, &mup, 4); memcpy(&bd, &mdn, 4);
+        wtab[k] = make_uint4((uint32_t)cap_fp[u], bu, bd, thr[u]);
+    }
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_wide_tab, wtab.data(), sizeof(uint4) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     h->U = U;
     h->total_cap = total;

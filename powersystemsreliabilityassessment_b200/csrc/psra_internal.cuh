@@ -38,6 +38,7 @@ struct psra_handle {
     float *d_mttr = nullptr;
     uint32_t *d_for_thr = nullptr;   // [U] floor(FOR * 2^32)
     int32_t *d_order = nullptr;      // [U] unit indices, most transitions per hour first
+    uint4 *d_wide_tab = nullptr;     // [U] in that order: {capacity, bits of mttf * 2^24, bits of mttr * 2^24, FOR threshold} (seq_wide.cu)
     double *d_for = nullptr;         // [U] FOR in FP64 (injected-uniform path, PSA.jl:183)
     // load (device)
     int H = 0;

@@ -8,6 +8,7 @@ struct SeqArgs {
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
     const int32_t *load; const int32_t *lmax;
     const int32_t *order;   // units sorted by decreasing transition rate (seq_wide.cu work queue)
+    const uint4 *wide_tab;  // per queue position: {capacity, bits of mttf * 2^24, bits of mttr * 2^24, FOR threshold}
     uint32_t k0, k1;
     uint32_t rk[20];        // Philox round keys {k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85}, r = 0..9 (constant-bank operands)
     long long chain_base;   // absolute index of local chain 0 (Philox counter)

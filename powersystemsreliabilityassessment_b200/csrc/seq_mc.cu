@@ -310,7 +310,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     SeqArgs a{};
     a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode & ~PSRA_DISC_MATLAB; a.K = K;
     a.disc = (!injected && (init_mode & PSRA_DISC_MATLAB)) ? 1 : 0;
-    a.order = h->d_order;
+    a.order = h->d_order; a.wide_tab = h->d_wide_tab;
     a.cap = h->d_cap; a.mttf = h->d_mttf; a.mttr = h->d_mttr; a.for_thr = h->d_for_thr;
     a.load = h->d_load; a.lmax = h->d_lmax;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);

@@ -70,7 +70,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
     int32_t *s_lmax = wneg + Wd4;
     WideShared *sh_all = reinterpret_cast<WideShared *>(s_lmax + Wd4);   // [2], 8-byte aligned (Wd4 is a multiple of 4)
     const uint32_t tl_s = (uint32_t)__cvta_generic_to_shared(tl);
-    const uint32_t dummy_s = tl_s + 4u * (uint32_t)(Hpad + lane);
+    uint32_t dummy_s = tl_s + 4u * (uint32_t)(Hpad + lane);
+    // keep the two shared addresses in registers: left alone, ptxas rebuilds them (S2R SR_CgaCtaId, LEA, ...) in every
+    // iteration of the generation loop
+    uint32_t tl_o = tl_s;
+    asm volatile("" : "+r"(tl_o), "+r"(dummy_s));
 
     for (int i = threadIdx.x; i < a.Wd; i += blockDim.x) s_lmax[i] = a.lmax[i];
     for (int i = threadIdx.x; i < Hpad + 32; i += blockDim.x) tl[i] = 0;
@@ -103,11 +107,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
         bool s0u = true;
         unsigned long long t = 0ull;
         auto take_unit = [&]() {
+            const uint4 rec = __ldg(&a.wide_tab[pos]);      // one 16-byte record per queue position
             u = __ldg(&a.order[pos]);
-            cu = __ldg(&a.cap[u]);
-            mup = __fmul_rn(__ldg(&a.mttf[u]), 16777216.0f);
-            mdn = __fmul_rn(__ldg(&a.mttr[u]), 16777216.0f);
-            thr = __ldg(&a.for_thr[u]);
+            cu = (int)rec.x;
+            mup = __uint_as_float(rec.y);
+            mdn = __uint_as_float(rec.z);
+            thr = rec.w;
             nb = 0u;
             // MATLAB discretisation: a unit that fails after d whole hours is DOWN from hour d+1 (seq_mcsampling.m:63)
             t = kDisc ? (1ull << PSRA_TICK_SHIFT) : 0ull;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_BLOCKS_PER_SM) seq_wide_ker
                 unsigned long long tm1 = bm1 + (q == 0 ? p1 : q == 1 ? p2 : q == 2 ? p3 : p4);
                 if (q == 0 && first) tm1 = parked;
                 const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
-                wide_scatter(tl_s, dummy_s, hs, (uint32_t)a.H, (q & 1) ? -delta_a : delta_a, n_events);
+                wide_scatter(tl_o, dummy_s, hs, (uint32_t)a.H, (q & 1) ? -delta_a : delta_a, n_events);
             }
             t += p4;
             nb++;
