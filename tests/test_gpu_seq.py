@@ -335,3 +335,45 @@ def test_sampler_logarithm_draw_by_draw(engine):
         assert np.array_equal(e_gpu, e_cpu)
         assert np.array_equal(t_gpu, t_cpu)
     assert t_cpu.max() > (1 << 32) and O.sampler_durations(1e-7, draws)[0].min() == 1
+
+
+@pytest.mark.gpu
+def test_randomised_systems_sampler_path_vs_oracle(engine):
+    """Seeded sweep over random systems through the sampler kernels (single-segment packed / unpacked, two-segment
+    ring, multi-year chains, MATLAB discretisation): unit counts 1..32, ragged hour counts, short and long cycles,
+    loads around the installed capacity -- every year bit-exact against the oracle's literal hour/unit loop."""
+    from powersystemsreliabilityassessment_b200 import DISC_MATLAB
+    rng = np.random.default_rng(20261017)
+    checked = 0
+    for case in range(36):
+        U = int(rng.integers(1, 33))
+        H = int(rng.choice([rng.integers(1, 200), rng.integers(200, 3000), rng.integers(3000, 9000), 8736, 8760]))
+        scale = float(rng.choice([1.0, 1.0, 37.0, 400.0]))                    # large capacities leave the packed-word range
+        cap = np.rint(rng.integers(1, 400, U) * scale).astype(np.float64)
+        cyc = float(rng.choice([15.0, 60.0, 400.0, 2000.0]))
+        mttf = rng.uniform(0.5, 1.5, U) * cyc
+        mttr = rng.uniform(0.05, 0.6, U) * cyc
+        lvl = rng.uniform(0.55, 1.0)
+        load = np.rint(cap.sum() * lvl * (0.75 + 0.25 * np.sin(np.arange(H) / 24.0 * 2 * np.pi) * rng.uniform(0, 1))).astype(np.int32)
+        ypc = int(rng.choice([1, 1, 1, 3]))
+        init = int(rng.choice([0, 1]))
+        disc = bool(rng.integers(0, 4) == 0)
+        if disc:                                      # the MATLAB sampler (seq_mcsampling.m): independent years, all UP at hour 0
+            ypc, init = 1, 0
+        years = 8 * ypc
+        try:
+            engine.set_system(cap, mttf, mttr); engine.set_load(load)
+            r = engine.seq_mc(years, seed=1000 + case, year0=ypc * 5, init_mode=init | (DISC_MATLAB if disc else 0),
+                              years_per_chain=ypc, per_year=True)
+        except Exception as ex:                       # the only legitimate refusal: transition rate too high for the list
+            assert "transition rate too high" in str(ex) or "overflow" in str(ex).lower(), (case, ex)
+            continue
+        if disc:
+            lol, ens, ent = O.seq_matlab_philox(cap, mttf, mttr, load.astype(np.float64), 1000 + case, 5, 8)
+        else:
+            lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 1000 + case, 5, 8, ypc, init)
+        assert np.array_equal(r.lol_hours.astype(np.float64), lol), (case, U, H, ypc, init, disc)
+        assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens), (case, U, H, ypc, init, disc)
+        assert np.array_equal(r.entries.astype(np.float64), ent), (case, U, H, ypc, init, disc)
+        checked += 1
+    assert checked >= 30
