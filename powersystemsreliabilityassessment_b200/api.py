@@ -711,6 +711,46 @@ def run_monte_carlo(gens: Sequence[DetailedGenerator], base_load, params: System
     return float(yl.mean()), prof, yl
 
 
+# ------------------------------------------------------------------ result series / export (SURVEY f-4)
+def cumulative_series(r: SequentialIndices):
+    """Montecarlo_seq/seqMain.m:180-186: results_cum.eens[i] = mean(ENS_1..i) and results_cum.cov[i] =
+    std(ENS_1..i) / (eens[i] * sqrt(i)) (n-1 form; cov[0] = 0 like the reference's untouched first slot), from the
+    per-year ENS vector of a run with per_year=True.  Host-side numpy over device-computed per-year integers."""
+    if r.ens is None:
+        raise ValueError("cumulative_series needs a run with per_year=True")
+    x = np.asarray(r.ens, dtype=np.float64)
+    n = np.arange(1, x.size + 1, dtype=np.float64)
+    s1 = np.cumsum(x); s2 = np.cumsum(x * x)
+    eens = s1 / n
+    var = np.zeros_like(x)
+    var[1:] = np.maximum(s2[1:] - s1[1:] * s1[1:] / n[1:], 0.0) / (n[1:] - 1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cov = np.where(eens > 0, np.sqrt(var) / (eens * np.sqrt(n)), 0.0)
+    cov[0] = 0.0
+    return eens, cov
+
+
+def export_results(prefix: str, r: SequentialIndices) -> List[str]:
+    """Montecarlo_seq/seqMain.m:250-262 at HL1: `<prefix>_yearly.csv` with the per-year vectors the reference keeps
+    in results_year (dlc = LOL hours, nlc = deficit entries, plc = dlc / H is left to the reader, ens in MWh) and the
+    cumulative series of results_cum (eens, cov), plus `<prefix>_indices.csv` with the printed indices.  (The
+    reference's nodal table and component ranking are HL2 outputs.)  Returns the written paths."""
+    if r.lol_hours is None or r.ens is None or r.entries is None:
+        raise ValueError("export_results needs a run with per_year=True")
+    eens, cov = cumulative_series(r)
+    yearly = prefix + "_yearly.csv"
+    with open(yearly, "w") as f:
+        f.write("year,dlc_hours,nlc_occ,ens_mwh,cum_eens_mwh_yr,cum_cov\n")
+        for i in range(len(eens)):
+            f.write(f"{i + 1},{int(r.lol_hours[i])},{int(r.entries[i])},{float(r.ens[i])!r},{float(eens[i])!r},{float(cov[i])!r}\n")
+    idx = prefix + "_indices.csv"
+    with open(idx, "w") as f:
+        f.write("index,value\n")
+        for k in ("years", "lole", "eens", "lolf", "lold", "lole_se", "eens_se", "p_loss_year", "cov_eens"):
+            f.write(f"{k},{getattr(r, k)!r}\n")
+    return [yearly, idx]
+
+
 # ------------------------------------------------------------------ adaptive stopping (SURVEY f-2)
 def run_sequential_until_cov(engine: Engine, cov_threshold: float = 0.05, batch_years: int = 1000,
                              max_years: int = 10_000_000, seed: int = 42, init_mode: int = INIT_STATIONARY,

@@ -108,3 +108,31 @@ def test_pack_unpack_raw_128bit():
     assert sharding.unpack_raw(sharding.pack_raw(raw)) == raw
     two = [a + b for a, b in zip(sharding.pack_raw(raw), sharding.pack_raw(raw))]
     assert sharding.unpack_raw(two)["sum_ens_sq"] == 2 * raw["sum_ens_sq"]
+
+
+def test_cumulative_series_and_export(tmp_path):
+    """seqMain.m:180-186 running EENS / CoV and the HL1 part of the export block (:250-262), on a synthetic result."""
+    import powersystemsreliabilityassessment_b200 as P
+    rng = np.random.default_rng(3)
+    n = 200
+    ens = (rng.exponential(900.0, n) * (rng.random(n) < 0.6)).round()
+    lol = np.where(ens > 0, rng.integers(1, 20, n), 0).astype(np.uint32)
+    ent = np.where(ens > 0, 1, 0).astype(np.uint32)
+    raw = dict(years=n, sum_lol_hours=int(lol.sum()), sum_ens_fp=int(ens.sum()), sum_entries=int(ent.sum()),
+               years_with_loss=int((lol > 0).sum()), sum_lol_sq=int((lol.astype(np.int64) ** 2).sum()),
+               sum_ens_sq=int((ens.astype(np.int64).astype(object) ** 2).sum()), events=0)
+    r = P.indices_from_raw(raw)
+    r.lol_hours, r.ens, r.entries = lol, ens, ent
+    eens, cov = P.cumulative_series(r)
+    for i in (1, 2, 57, n):                                     # the reference's own formulas, year by year
+        assert eens[i - 1] == pytest.approx(ens[:i].mean(), rel=1e-12)
+        ref = 0.0 if i == 1 or ens[:i].mean() == 0 else ens[:i].std(ddof=1) / (ens[:i].mean() * np.sqrt(i))
+        assert cov[i - 1] == pytest.approx(ref, rel=1e-9, abs=1e-15)
+    assert cov[-1] == pytest.approx(r.cov_eens, rel=1e-9)
+    paths = P.export_results(str(tmp_path / "seq"), r)
+    rows = open(paths[0]).read().strip().split("\n")
+    assert rows[0].startswith("year,dlc_hours,nlc_occ,ens_mwh") and len(rows) == n + 1
+    last = rows[-1].split(",")
+    assert int(last[0]) == n and int(last[1]) == int(lol[-1]) and float(last[4]) == eens[-1]
+    idx = dict(line.split(",") for line in open(paths[1]).read().strip().split("\n")[1:])
+    assert float(idx["lole"]) == r.lole and float(idx["eens"]) == r.eens
