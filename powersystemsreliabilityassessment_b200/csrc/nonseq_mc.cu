@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(256) nonseq_fast_kernel(const NsArgs a)
         acc_swl += __shfl_xor_sync(0xffffffffu, acc_swl, d);
         acc_lol2 += __shfl_xor_sync(0xffffffffu, acc_lol2, d);
     }
-    if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
+    warp_sum_u128(acc_e2lo, acc_e2hi);       // one 128-bit atomic per warp, not per thread (they all hit one address)
     if ((threadIdx.x & 31) == 0) {
+        if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
         if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
         if (acc_ens) atomicAdd(&a.acc[ACC_ENS], (unsigned long long)acc_ens);
         if (acc_swl) atomicAdd(&a.acc[ACC_YWL], acc_swl);
@@ -193,8 +194,9 @@ __global__ void __launch_bounds__(256) nonseq_kernel(const NsArgs a)
         acc_swl += __shfl_xor_sync(0xffffffffu, acc_swl, d);
         acc_lol2 += __shfl_xor_sync(0xffffffffu, acc_lol2, d);
     }
-    if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
+    warp_sum_u128(acc_e2lo, acc_e2hi);       // one 128-bit atomic per warp, not per thread (they all hit one address)
     if ((threadIdx.x & 31) == 0) {
+        if (acc_e2lo | acc_e2hi) atomic_add_u128(&a.acc[ACC_ENS2_LO], &a.acc[ACC_ENS2_HI], acc_e2lo, acc_e2hi);
         if (acc_lol) atomicAdd(&a.acc[ACC_LOL], acc_lol);
         if (acc_ens) atomicAdd(&a.acc[ACC_ENS], (unsigned long long)acc_ens);
         if (acc_swl) atomicAdd(&a.acc[ACC_YWL], acc_swl);

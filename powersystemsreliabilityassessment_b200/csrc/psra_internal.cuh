@@ -199,6 +199,17 @@ __device__ __forceinline__ long long warp_sum_ll(long long v)
     return v;
 }
 
+// warp-wide sum of 128-bit values held as (lo, hi) pairs; every lane ends with the total
+__device__ __forceinline__ void warp_sum_u128(unsigned long long &lo, unsigned long long &hi)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long olo = __shfl_xor_sync(0xffffffffu, lo, d), ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+        lo += olo;
+        hi += ohi + (lo < olo ? 1ull : 0ull);
+    }
+}
+
 // 128-bit accumulate into (lo, hi) pair in global memory; order independent.
 __device__ __forceinline__ void atomic_add_u128(unsigned long long *lo, unsigned long long *hi,
                                                 unsigned long long vlo, unsigned long long vhi)
