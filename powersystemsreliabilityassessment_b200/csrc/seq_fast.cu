@@ -125,18 +125,19 @@ __device__ __forceinline__ void scatter_event_single(uint32_t hs, uint32_t H, ui
 }
 
 // Packed variant: the record is {sum + 2^K * negative sum, head}; `delta` already carries both fields
-// (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.  `wtab` = shared address of
-// the word table: the record of hour `hs` sits at wtab + 8 * (hs >> 5), its head 4 bytes further (one shift, two
-// multiply-adds on the FMA pipe).  An out-of-year event does both atomics on the lane's own list slot (`slot`,
+// (c for an up event, -c * (1 + 2^K) for a down event), so one add serves both sums.  The packed layout keeps
+// two arrays, values and list heads (`wval`, `whead` = their shared addresses; 4-byte stride, so the 32 lanes of an
+// atomic spread over all 32 banks): the word of hour `hs` is element hs >> 5 (one shift, two multiply-adds on the FMA
+// pipe).  An out-of-year event does both atomics on the lane's own list slot (`slot`,
 // never linked and overwritten by the store below), so the delta needs no select.
-__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wtab, int delta,
+__device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, uint32_t wval, uint32_t whead, int delta,
                                                      uint32_t idx1, uint32_t slot, uint32_t ent, unsigned int &n_events)
 {
     asm volatile("{\n .reg .pred p;\n .reg .b32 nx, hr, hx, w;\n"
                  " setp.lt.u32 p, %1, %2;\n"
                  " shr.u32 w, %1, 5;\n"
-                 " mad.lo.u32 hr, w, 8, %3;\n"
-                 " mad.lo.u32 hx, w, 8, %8;\n"
+                 " mad.lo.u32 hr, w, 4, %3;\n"
+                 " mad.lo.u32 hx, w, 4, %8;\n"
                  " selp.b32 hr, hr, %6, p;\n"
                  " selp.b32 hx, hx, %6, p;\n"
                  " red.shared.add.s32 [hr], %4;\n"
@@ -145,7 +146,7 @@ __device__ __forceinline__ void scatter_event_packed(uint32_t hs, uint32_t H, ui
                  " st.shared.b32 [%6], nx;\n"
                  " @p add.u32 %0, %0, 1;\n}\n"
                  : "+r"(n_events)
-                 : "r"(hs), "r"(H), "r"(wtab), "r"(delta), "r"(idx1), "r"(slot), "r"(ent), "r"(wtab + 4u)
+                 : "r"(hs), "r"(H), "r"(wval), "r"(delta), "r"(idx1), "r"(slot), "r"(ent), "r"(whead)
                  : "memory");
 }
 
@@ -185,13 +186,15 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
     const int pk = a.pack_shift;
     const int pk_bias = kPack ? (1 << (pk - 1)) : 0, pk_mask = (1 << pk) - 1;
     int32_t *wtab = reinterpret_cast<int32_t *>(evl + (size_t)halves * ev_cap);
+    // kPack: structure of arrays -- packed values [ring_words], then list heads [ring_words]; otherwise records of three
+    int32_t *whd = wtab + ring_words;
     auto word_sums = [&](int i, int &sm, int &ng) {
-        if constexpr (kPack) { const int v = wtab[RS * i]; sm = (v & pk_mask) - pk_bias; ng = v >> pk; }
+        if constexpr (kPack) { const int v = wtab[i]; sm = (v & pk_mask) - pk_bias; ng = v >> pk; }
         else { sm = wtab[RS * i]; ng = wtab[RS * i + 1]; }
     };
 #define WSUM(i) wtab[3 * (i)]
 #define WNEG(i) wtab[3 * (i) + 1]
-#define WHEAD(i) (reinterpret_cast<uint32_t *>(wtab)[RS * (i) + RS - 1])
+#define WHEAD(i) (kPack ? reinterpret_cast<uint32_t *>(whd)[i] : reinterpret_cast<uint32_t *>(wtab)[3 * (i) + 2])
 
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) {
         if (load16) s_load16[i] = (short)a.load[i]; else s_load32[i] = a.load[i];
@@ -216,8 +219,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
         s_thr[threadIdx.x] = v ? a.for_thr[threadIdx.x] : 0u;
         s_ispan[threadIdx.x] = v ? __fdividef(0.5f, a.mttf[threadIdx.x] + a.mttr[threadIdx.x]) : 0.f;
     }
-    for (int i = lane; i < RS * ring_words; i += 32) wtab[i] = (kPack && !(i & 1)) ? pk_bias : 0;
+    for (int i = lane; i < RS * ring_words; i += 32) wtab[i] = (kPack && i < ring_words) ? pk_bias : 0;
     const uint32_t wtab_s = (uint32_t)__cvta_generic_to_shared(wtab);
+    const uint32_t whd_s = wtab_s + 4u * (uint32_t)ring_words;
     const uint32_t jobmap_s = (uint32_t)__cvta_generic_to_shared(ws->jobmap);
     const uint32_t wlane_s = wtab_s + 4u * RS * (uint32_t)min(lane, a.seg_words - 1);     // where this lane's out-of-year events add 0
     __syncthreads();
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                             const uint32_t hs = __funnelshift_r((uint32_t)tm1, (uint32_t)(tm1 >> 32), PSRA_TICK_SHIFT);
                             const uint32_t ent = (hs << 6) + (((uint32_t)lane << 1) | (s0i ^ (uint32_t)(q & 1)));
                             if constexpr (kPack)
-                                scatter_event_packed(hs, (uint32_t)a.H, wtab_s, (q & 1) ? pk_b : pk_a, idx1,
+                                scatter_event_packed(hs, (uint32_t)a.H, wtab_s, whd_s, (q & 1) ? pk_b : pk_a, idx1,
                                                      evcur_s + 4u * idx1 - 4u, ent, n_events);
                             else
                                 scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, (q & 1) ? -delta_a : delta_a, s0i,
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                                 // down events: q even when the stream starts DOWN (s0i == 0), q odd when it starts UP
                                 const uint32_t ent = (hs << 6) + (((uint32_t)u << 1) | (s0i ^ (uint32_t)(q & 1)));
                                 if constexpr (kPack)
-                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s, (q & 1) ? pk_b : pk_a, idx1,
+                                    scatter_event_packed(hs, (uint32_t)a.H, wtab_s, whd_s, (q & 1) ? pk_b : pk_a, idx1,
                                                          evcur_s + 4u * idx1 - 4u, ent, n_events);
                                 else
                                     scatter_event_single(hs, (uint32_t)a.H, wtab_s + 12u * (hs >> 5), wlane_s, delta, s0i, (uint32_t)(q & 1), idx1,
@@ -570,11 +574,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 } else {
                     // every lane owns wpl records (the table is padded with neutral ones): no bounds checks, and the
                     // running sum keeps the packing bias (s_lmax carries the same bias, see above)
-                    const int32_t *wp = wtab + RS * wb;
+                    const int32_t *wp = wtab + (kPack ? 1 : RS) * wb;
                     const int32_t *lp = s_lmax + wb;
                     for (int k = 0; k < wpl; k++) {
                         int smb, ng;
-                        if constexpr (kPack) { const int v = wp[RS * k]; smb = v & pk_mask; ng = v >> pk; }
+                        if constexpr (kPack) { const int v = wp[k]; smb = v & pk_mask; ng = v >> pk; }
                         else { smb = wp[RS * k]; ng = wp[RS * k + 1]; }
                         lmin = min(lmin, loc + ng - lp[k]);
                         loc += smb;
@@ -640,9 +644,15 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 // clear the evaluated half: word sums to zero, event list empty
                 if constexpr (!kTwo) {      // the table is 16-byte aligned and padded to a multiple of four records
                     uint4 *t4 = reinterpret_cast<uint4 *>(wtab);
-                    const int n4 = (RS * ((nwords + 3) & ~3)) >> 2;
-                    const uint4 z = kPack ? make_uint4((uint32_t)pk_bias, 0u, (uint32_t)pk_bias, 0u) : make_uint4(0u, 0u, 0u, 0u);
-                    for (int i = lane; i < n4; i += 32) t4[i] = z;
+                    if constexpr (kPack) {          // values back to the bias, heads to "empty" (both arrays are 16-byte aligned)
+                        uint4 *h4 = reinterpret_cast<uint4 *>(whd);
+                        const int n4 = (nwords + 3) >> 2;
+                        const uint4 zb = make_uint4((uint32_t)pk_bias, (uint32_t)pk_bias, (uint32_t)pk_bias, (uint32_t)pk_bias);
+                        for (int i = lane; i < n4; i += 32) { t4[i] = zb; h4[i] = make_uint4(0u, 0u, 0u, 0u); }
+                    } else {
+                        const int n4 = (RS * ((nwords + 3) & ~3)) >> 2;
+                        for (int i = lane; i < n4; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 } else {
                     for (int i = lane; i < RS * nwords; i += 32) wtab[RS * wbase_cur + i] = 0;
                 }
