@@ -40,4 +40,4 @@ void seq_team_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t 
 size_t seq_wide_smem_bytes(int Wd);
 int seq_wide_threads();
 cudaError_t seq_wide_prepare(size_t smem, int *blocks_per_sm);
-void seq_wide_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t stream);
+void seq_wide_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);

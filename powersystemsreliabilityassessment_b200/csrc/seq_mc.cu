@@ -382,7 +382,15 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
         return b;
     };
-    if (team) wpb = wide ? seq_wide_threads() / 32 : SEQ_TEAM_WARPS;
+    if (team) {
+        wpb = SEQ_TEAM_WARPS;
+        if (wide) {
+            // block size of seq_wide.cu: 4 warps measured best from 64 to 1024 units (scripts/sweep_wide_units.py: +10-18 %
+            // over 6 warps at 96-320 units, equal at 1024; 5 blocks per SM either way); psra_config.warps_per_block overrides
+            const int wmax = seq_wide_threads() / 32;
+            wpb = h->cfg.warps_per_block > 0 ? std::min(wmax, h->cfg.warps_per_block) : std::min(wmax, 4);
+        }
+    }
     while (wpb > 1 && smem_for(wpb) > h->smem_optin) wpb--;
     const size_t smem = smem_for(wpb);
     if (smem > h->smem_optin)
@@ -488,7 +496,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         const long long need_c = (team ? b.nchains : (b.nchains + wpb - 1) / wpb);
         if (g > need_c) g = need_c;
         if (fast) seq_fast_launch(b, (unsigned)g, wpb * 32, smem, h->stream);
-        else if (wide) seq_wide_launch(b, (unsigned)g, smem, h->stream);
+        else if (wide) seq_wide_launch(b, (unsigned)g, wpb * 32, smem, h->stream);
         else if (team) seq_team_launch(b, (unsigned)g, smem, h->stream);
         else kern<<<(unsigned)g, wpb * 32, smem, h->stream>>>(b);
         PSRA_CUDA(h, cudaGetLastError());

@@ -288,8 +288,8 @@ cudaError_t seq_wide_prepare(size_t smem, int *blocks_per_sm)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, seq_wide_kernel<false>, WIDE_THREADS, smem);
 }
 
-void seq_wide_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t stream)
+void seq_wide_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream)
 {
-    if (a.disc) seq_wide_kernel<true><<<grid, WIDE_THREADS, smem, stream>>>(a);
-    else seq_wide_kernel<false><<<grid, WIDE_THREADS, smem, stream>>>(a);
+    if (a.disc) seq_wide_kernel<true><<<grid, threads, smem, stream>>>(a);
+    else seq_wide_kernel<false><<<grid, threads, smem, stream>>>(a);
 }
