@@ -50,3 +50,53 @@ def allreduce_raw(raw: Dict[str, int], device=None, group=None) -> Dict[str, int
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return unpack_raw(t.cpu().tolist())
+
+
+def allreduce_counts(counts, device=None, group=None):
+    """Element-wise sum over ranks of an integer count vector (per-hour failure counts of
+    tail_risk.jl:81,88 / psra_seq_outputs.fail_count, histogram bins of psra_tail): SURVEY.md section 8e."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(np.ascontiguousarray(counts).astype(np.int64), device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def gather_years(values, device=None, group=None):
+    """Per-year (or per-group) vectors of the ranks' contiguous shards -> the vector of the whole experiment, in rank
+    = year order, on every rank.  The shards may differ in length by one chain (shard_range)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    v = np.ascontiguousarray(values)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return v.copy()
+    world = dist.get_world_size(group)
+    n = torch.tensor([v.size], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    width = max(sizes)
+    pad = torch.zeros(width, dtype=torch.int64, device=device)
+    pad[:v.size] = torch.as_tensor(v.astype(np.int64), device=device)
+    parts = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return np.concatenate([p[:k].cpu().numpy() for p, k in zip(parts, sizes)]).astype(v.dtype)
+
+
+def merged_history(group_lol, group: int, device=None, group_pg=None):
+    """PowerSystemAdequacy.jl:263-265 across ranks: the ranks' per-group LOL-hour sums (psra_seq_outputs.group_lol,
+    `group` years each, shards aligned to the group) -> running mean of the LOL hours every `group` years of the
+    whole experiment."""
+    import numpy as np
+    g = gather_years(group_lol, device=device, group=group_pg).astype(np.float64)
+    return np.cumsum(g) / (group * np.arange(1, g.size + 1, dtype=np.float64))
+
+
+def tail_all_ranks(engine, ens_fp_local, alphas=(0.95, 0.99), device=None, group=None):
+    """VaR / CVaR over the years of all ranks: the per-year ENS shards are gathered (8 B per year)
+    and every rank runs the exact device reduction (psra_tail) on the whole vector."""
+    x = gather_years(ens_fp_local, device=device, group=group)
+    return engine.tail(x, alphas=alphas)

@@ -32,6 +32,19 @@ WORKER = textwrap.dedent("""
     assert full["sum_ens_sq"] > 2**64
     r = indices_from_raw(red)
     assert r.years == total and abs(r.lole - lol.mean()) < 1e-12
+    # per-hour failure counts / histogram bins: element-wise sums; per-year vectors: concatenation in year order
+    fc = np.bincount(rng.integers(0, 48, 500)[rank::world], minlength=48)
+    tot = sharding.allreduce_counts(fc)
+    rng2 = np.random.default_rng(0)                      # replay the generator up to the draw of the 500 hours
+    rng2.integers(0, 30, total); rng2.random(total); rng2.integers(1, 10**12, total); rng2.integers(0, 4, total)
+    assert tot.sum() == 500 and np.array_equal(tot, np.bincount(rng2.integers(0, 48, 500), minlength=48))
+    a2, b2 = sharding.shard_range(total, rank, world, 10)
+    assert np.array_equal(sharding.gather_years(ens[a2:b2]), ens)
+    assert np.array_equal(sharding.gather_years(lol[a2:b2].astype(np.uint32)), lol.astype(np.uint32))
+    # PSA.jl:263-265 running mean every 10 years from the ranks' per-group sums
+    glocal = lol[a2:b2].reshape(-1, 10).sum(axis=1)
+    hist = sharding.merged_history(glocal, 10)
+    assert np.allclose(hist, np.cumsum(lol)[9::10] / np.arange(10, total + 1, 10), rtol=1e-14)
     if rank == 0:
         print("GLOO_OK", json.dumps({"world": world, "span": [a, b]}))
     dist.destroy_process_group()
