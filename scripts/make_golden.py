@@ -21,4 +21,15 @@ lol, eue, ent, _ = O.seq_literal(cap, load, 3, dur)
 np.savez(os.path.join(ROOT, "tests/golden/seq_literal_seed123.npz"), lol=lol, eue=eue, ent=ent, dur=dur)
 lol, eue, ent = O.seq_philox(cap, mttf, mttr, load, 42, 0, 64, 1, 1)
 np.savez(os.path.join(ROOT, "tests/golden/seq_philox_seed42.npz"), lol=lol, eue=eue, ent=ent)
+# sampler specification, draw by draw: edge draws + seeded random draws, two means
+rng = np.random.default_rng(2026)
+edge = [0, 1, 2, 3, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF, 0xB504F333, 0xB504F334, 0x5A827999, 0x00FFFFFF, 0x01000000]
+edge += [1 << k for k in range(32)] + [(1 << k) - 1 for k in range(1, 32)]
+draws = np.concatenate([np.array(edge, dtype=np.uint64), rng.integers(0, 1 << 32, 4000, dtype=np.uint64)]).astype(np.uint32)
+t450, eb = O.sampler_durations(450.0, draws)
+t2940, _ = O.sampler_durations(2940.0, draws)
+np.savez(os.path.join(ROOT, "tests/golden/sampler_draws.npz"), draws=draws, e_bits=eb, ticks_450=t450, ticks_2940=t2940)
+# non-sequential sampler (PSA.jl:169-208 on the Philox stream): 256 samples
+nl, ne, st = O.nonseq_philox(cap, mttf, mttr, load, 7, 1000, 256)
+np.savez(os.path.join(ROOT, "tests/golden/nonseq_philox_seed7.npz"), lol=nl, eue=ne, states=st)
 print("golden fixtures written")

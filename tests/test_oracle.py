@@ -215,3 +215,15 @@ def test_sampler_vector_form_and_device_front_end_identity():
     k2_dev = (0x4B00013E - 2 * e.astype(np.int64)) - 0x4B000000          # the float built by the IMAD, minus 2^23
     assert np.array_equal(m_dev, m_spec)
     assert np.array_equal(k2_dev, 2 * k_spec) and k_spec.min() >= 0 and k_spec.max() <= 32
+
+
+def test_sampler_and_nonseq_golden_fixtures():
+    """The oracle still produces the committed sampler / non-sequential fixtures (scripts/make_golden.py)."""
+    g = np.load("tests/golden/sampler_draws.npz")
+    t, e = O.sampler_durations(450.0, g["draws"])
+    assert np.array_equal(e, g["e_bits"]) and np.array_equal(t, g["ticks_450"])
+    assert np.array_equal(O.sampler_durations(2940.0, g["draws"])[0], g["ticks_2940"])
+    cap, mttf, mttr = rts79.units()
+    g = np.load("tests/golden/nonseq_philox_seed7.npz")
+    nl, ne, st = O.nonseq_philox(cap, mttf, mttr, rts79.load_curve_int().astype(float), 7, 1000, 256)
+    assert np.array_equal(nl, g["lol"]) and np.array_equal(ne, g["eue"]) and np.array_equal(st, g["states"])
