@@ -315,6 +315,9 @@ def main():
                          "alg_warp_inst_per_year": w_warp, "events_per_year": events,
                          "peak_source": f"{sm_count} SMs x 4 issue/clk x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json)",
                          "ncu_issue_active_pct": prof.get("issue_active_pct"),
+                         "traffic_source": prof.get("source"),
+                         "hbm": {"achieved": (prof.get("dram_bytes_per_launch") or 0.0) / k_s / 1e9, "peak": peaks.get("hbm_gbs"),
+                                 "unit": "GB/s", "frac": (prof.get("dram_bytes_per_launch") or 0.0) / k_s / 1e9 / float(peaks.get("hbm_gbs") or 6547.5)},
                          "hbm_note": "HBM traffic is per-launch accumulators only; not the bound (SURVEY 8d)"},
             "results": {"years": idx.years, "lole_h_per_yr": idx.lole, "lole_se": idx.lole_se,
                         "eens_mwh_per_yr": idx.eens, "eens_se": idx.eens_se, "lolf_occ_per_yr": idx.lolf,
