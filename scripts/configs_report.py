@@ -52,6 +52,19 @@ with P.Engine() as e:
     P.schedule_maintenance(gens, [base[(w - 1) * 168:min(w * 168, 8760)].max() for w in range(1, 53)])
     yl, hf, ms = e.detailed_mc(gens, base, base.max() * 0.05, 100_000, seed=1)
     out["detailed_mc_1e5"] = dict(kernel_ms=ms, years_per_s=1e5 / ms * 1e3, mean_lole=float(yl.mean()), p95=float(np.quantile(yl, 0.95)))
+    yl, hf, ms = e.detailed_mc(gens, base, base.max() * 0.05, 2_000_000, seed=1)          # thread = year: the GPU fills up at ~3e5 years
+    out["detailed_mc_2e6"] = dict(kernel_ms=ms, years_per_s=2e6 / ms * 1e3, hour_steps_per_s=2e6 * 8760 / ms * 1e3, mean_lole=float(yl.mean()))
+    # multi-area (AdequacyAssessmentII.jl demo: 2 areas x 5 units, one 200 MW tie), both policies
+    ua = np.array([0] * 5 + [1] * 5); acap = np.array([400.0] * 5 + [200.0] * 5)
+    amttf = np.array([1000.0] * 5 + [900.0] * 5); amttr = np.array([50.0] * 5 + [60.0] * 5)
+    xx = np.linspace(0.0, 2.0 * np.pi, 8760)
+    loads = np.stack([np.rint(1000.0 + 500.0 * np.sin(xx)), np.rint(800.0 + 400.0 * np.sin(xx))])
+    topo = np.array([[0.0, 200.0], [200.0, 0.0]])
+    for pol, name in ((0, "isolated"), (1, "interconnected")):
+        e.multi_area_mc(ua, acap, amttf, amttr, loads, topo, pol, 2000, seed=6)
+        m = e.multi_area_mc(ua, acap, amttf, amttr, loads, topo, pol, 1_000_000, seed=6)
+        out[f"multi_area_demo_{name}_1e6"] = dict(kernel_ms=m["kernel_ms"], years_per_s=1e6 / m["kernel_ms"] * 1e3,
+                                                  lole=[float(v) for v in np.atleast_1d(m["lole"])], eue=[float(v) for v in np.atleast_1d(m["eue"])])
     # C5: 1024 units
     c5 = rts79.synthetic_system(32, 37.0)
     e.set_system(c5[0], c5[1], c5[2]); e.set_load(c5[3])
