@@ -21,7 +21,11 @@
 //    events beyond the ring wait in a small pending list.  A wave is one round of <= 32 jobs:
 //    blocks for the units that are short of the current segment first, the spare lanes
 //    pre-generate blocks towards the end of the next segment.  For RTS-79 the whole year is one
-//    segment (no ring switch, no pending traffic).
+//    segment (no ring switch, no pending traffic); that variant (template kTwo = false) first
+//    generates the first blocks of every unit lane = unit without any scheduling (static phase),
+//    keeps the two word sums packed in one int32 (kPack; values and list heads are two arrays, so
+//    the atomics of a scatter step spread over all 32 banks) and pads the word table to 32 equal
+//    runs of neutral records, so the evaluation scan is branch-free.
 //  * Evaluation: lane = run of consecutive words.  One shuffle scan per segment over the word
 //    sums gives the capacity entering each run; conservative flag
 //    capacity + (negative deltas of the word) < max load of the word (table staged in shared
