@@ -123,6 +123,15 @@ int psra_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed,
                 int32_t init_mode, int32_t years_per_chain,
                 const psra_seq_outputs *out, psra_seq_summary *summary);
 
+/* psra_seq_mc plus the weak-point statistic of Montecarlo_seq/seqMain.m:140-150,225-231 restricted to generators
+ * (HL1): down_in_loss[u] = number of simulated hours with loss of load in which unit u is DOWN, summed over the
+ * years of the call; the reference's comp_importance (probability that the component is down given a system
+ * failure) is down_in_loss[u] / summary->sum_lol_hours.  Runs the generic kernel (any unit count; more than 32 units
+ * need years_per_chain = 1); `out` may be NULL. */
+int psra_seq_unit_importance(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed,
+                             int32_t init_mode, int32_t years_per_chain, uint64_t *down_in_loss,
+                             const psra_seq_outputs *out, psra_seq_summary *summary);
+
 /* Same kernel fed with injected durations instead of the sampler (bit-exact parity tests):
  * durations[(chain*U + u)*K + k], k = 0 initial TTF (PSA.jl:224), then TTR, TTF, ...
  * (PSA.jl:243,246); all units start UP; all durations must be > 0. */

@@ -17,7 +17,7 @@ module PowerSystemAdequacyB200
 
 using Printf
 
-export Generator, LoadModel, ReliabilityResult,
+export Generator, LoadModel, ReliabilityResult, unit_importance,
        run_analytical, run_non_sequential_mc, run_sequential_mc, compare_results,
        SequentialIndices, run_sequential_indices, tail_risk, PSRA_INIT_ALL_UP, PSRA_INIT_STATIONARY,
        DetailedGenerator, run_detailed_mc
@@ -201,6 +201,26 @@ function run_sequential_mc(gens::Vector{Generator}, load::LoadModel, years::Int;
     t_start = time()
     r = run_sequential_indices(gens, load, years; kwargs...)
     return ReliabilityResult("Sequential MC", r.lole, r.eens, time() - t_start, r.history)
+end
+
+"Weak-point detection of Montecarlo_seq/seqMain.m:140-150,225-231 at HL1: (comp_importance, down_in_loss, indices)"
+function unit_importance(gens::Vector{Generator}, load::LoadModel, years::Int; seed::Integer=42, year0::Integer=0,
+                         fp_scale::Float64=1.0, init_mode::Int32=PSRA_INIT_STATIONARY, years_per_chain::Integer=1,
+                         engine::Engine=default_engine())
+    set_system!(engine, gens, load; fp_scale=fp_scale)
+    cnt = zeros(UInt64, length(gens))
+    s = PsraSeqSummary()
+    GC.@preserve cnt begin
+        check(engine, ccall((:psra_seq_unit_importance, LIB), Cint,
+                            (Ptr{Cvoid}, Int64, Int64, UInt64, Int32, Int32, Ptr{UInt64}, Ptr{Cvoid}, Ref{PsraSeqSummary}),
+                            engine.h, year0, years, UInt64(seed), init_mode, Int32(years_per_chain), cnt, C_NULL, s))
+    end
+    n = max(s.years, 1)
+    idx = SequentialIndices(s.years, s.sum_lol_hours / n, s.sum_ens_fp / n / fp_scale, s.sum_entries / n,
+                            s.sum_entries > 0 ? s.sum_lol_hours / s.sum_entries : 0.0,
+                            s.years_with_loss / n, s.events, s.kernel_ms, Float64[])
+    imp = s.sum_lol_hours > 0 ? Float64.(cnt) ./ s.sum_lol_hours : zeros(Float64, length(gens))
+    return imp, cnt, idx
 end
 
 "VaR / CVaR of the per-year ENS kept on the device by run_sequential_indices(...; keep_on_device=true)"

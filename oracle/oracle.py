@@ -52,6 +52,9 @@ def lib():
         L.oracle_seq_philox.restype = C.c_int
         L.oracle_seq_philox.argtypes = [C.c_int, _dp, _fp, _fp, _u32p, C.c_int, _dp, C.c_uint64,
                                         C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp]
+        L.oracle_seq_philox_ex.restype = C.c_int
+        L.oracle_seq_philox_ex.argtypes = [C.c_int, _dp, _fp, _fp, _u32p, C.c_int, _dp, C.c_uint64,
+                                           C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.oracle_solve_curtailment.restype = None
         L.oracle_solve_curtailment.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp]
         L.oracle_multi_area_philox.restype = C.c_int
@@ -148,6 +151,19 @@ def seq_philox(cap, mttf, mttr, load, seed, chain0, nchains, years_per_chain=1, 
     lib().oracle_seq_philox(len(cap), cap, mf, mr, thr, len(load), load, seed, chain0, nchains,
                             years_per_chain, init_mode, lol, eue, ent)
     return lol, eue, ent
+
+
+def seq_philox_importance(cap, mttf, mttr, load, seed, chain0, nchains, years_per_chain=1, init_mode=1):
+    """oracle_seq_philox plus unit_down_in_loss[U]: hours with loss of load in which each unit is DOWN
+    (Montecarlo_seq/seqMain.m:140-150,225-231 restricted to generators)."""
+    cap = _d(cap); load = _d(load)
+    mf = np.ascontiguousarray(mttf, dtype=np.float32); mr = np.ascontiguousarray(mttr, dtype=np.float32)
+    thr = for_threshold(mttf, mttr)
+    n = nchains * years_per_chain
+    lol = np.zeros(n); eue = np.zeros(n); ent = np.zeros(n); imp = np.zeros(len(cap))
+    lib().oracle_seq_philox_ex(len(cap), cap, mf, mr, thr, len(load), load, seed, chain0, nchains,
+                               years_per_chain, init_mode, lol, eue, ent, imp)
+    return lol, eue, ent, imp
 
 
 def solve_curtailment(topology, margins, policy):

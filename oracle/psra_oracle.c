@@ -205,10 +205,27 @@ static uint32_t stream_next(draw_stream *s)
  * the duration draws keep the same indices in both modes), 1 = STATIONARY: unit DOWN
  * iff draw0 < for_thr[u] (= floor(FOR * 2^32)), first residual ~ Exp(mean of that state),
  * which is the stationary law of the alternating process by memorylessness. */
+int oracle_seq_philox_ex(int U, const double *cap, const float *mttf_f, const float *mttr_f,
+                         const uint32_t *for_thr, int H, const double *load, uint64_t seed,
+                         int64_t chain0, int64_t nchains, int years_per_chain, int init_mode,
+                         double *year_lol, double *year_eue, double *year_entries, double *unit_down_in_loss);
+
 int oracle_seq_philox(int U, const double *cap, const float *mttf_f, const float *mttr_f,
                       const uint32_t *for_thr, int H, const double *load, uint64_t seed,
                       int64_t chain0, int64_t nchains, int years_per_chain, int init_mode,
                       double *year_lol, double *year_eue, double *year_entries)
+{
+    return oracle_seq_philox_ex(U, cap, mttf_f, mttr_f, for_thr, H, load, seed, chain0, nchains, years_per_chain, init_mode,
+                                year_lol, year_eue, year_entries, NULL);
+}
+
+/* ... plus the weak-point statistic of Montecarlo_seq/seqMain.m:140-150,225-231 restricted to generators:
+ * unit_down_in_loss[u] (optional, accumulated over all years) = number of hours with loss of load in which unit u
+ * is DOWN; comp_importance = unit_down_in_loss / total loss hours. */
+int oracle_seq_philox_ex(int U, const double *cap, const float *mttf_f, const float *mttr_f,
+                         const uint32_t *for_thr, int H, const double *load, uint64_t seed,
+                         int64_t chain0, int64_t nchains, int years_per_chain, int init_mode,
+                         double *year_lol, double *year_eue, double *year_entries, double *unit_down_in_loss)
 {
     draw_stream *st = (draw_stream *)malloc(sizeof(draw_stream) * (size_t)U);
     unsigned char *status = (unsigned char *)malloc((size_t)U);
@@ -240,6 +257,9 @@ int oracle_seq_philox(int U, const double *cap, const float *mttf_f, const float
                     lole += 1.0;
                     eue += load[h] - cap_avail;
                     flag = 1;
+                    if (unit_down_in_loss)
+                        for (int i = 0; i < U; i++)
+                            if (!status[i]) unit_down_in_loss[i] += 1.0;
                 }
                 if (flag && !prev_flag) entries += 1.0;
                 prev_flag = flag;

@@ -26,7 +26,7 @@ EXPORTS = [
     "psra_set_system", "psra_set_load", "psra_seq_mc", "psra_seq_eval_injected", "psra_nonseq_mc",
     "psra_nonseq_eval_states", "psra_nonseq_eval_uniforms", "psra_copt", "psra_copt_indices",
     "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail", "psra_detailed_mc", "psra_detailed_eval_injected",
-    "psra_multi_area_mc", "psra_failure_times", "psra_sampler_durations",
+    "psra_multi_area_mc", "psra_failure_times", "psra_sampler_durations", "psra_seq_unit_importance",
 ]
 
 
@@ -114,6 +114,8 @@ def load():
     L.psra_set_load.restype = C.c_int; L.psra_set_load.argtypes = [vp, vp, i32]
     L.psra_seq_mc.restype = C.c_int
     L.psra_seq_mc.argtypes = [vp, i64, i64, u64, i32, i32, C.POINTER(SeqOutputs), C.POINTER(SeqSummary)]
+    L.psra_seq_unit_importance.restype = C.c_int
+    L.psra_seq_unit_importance.argtypes = [vp, i64, i64, u64, i32, i32, vp, C.POINTER(SeqOutputs), C.POINTER(SeqSummary)]
     L.psra_seq_eval_injected.restype = C.c_int
     L.psra_seq_eval_injected.argtypes = [vp, vp, i64, i32, i32, C.POINTER(SeqOutputs), C.POINTER(SeqSummary)]
     L.psra_nonseq_mc.restype = C.c_int

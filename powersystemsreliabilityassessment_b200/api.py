@@ -237,6 +237,21 @@ class Engine:
                                         C.byref(o), C.byref(s)))
         return self._seq_result(s, bufs)
 
+    def seq_unit_importance(self, years: int, seed: int = 42, year0: int = 0, init_mode: int = INIT_STATIONARY,
+                            years_per_chain: int = 1, per_year: bool = False):
+        """Montecarlo_seq/seqMain.m:140-150,225-231 at HL1 (weak-point detection): returns (importance, down_in_loss,
+        indices) -- down_in_loss[u] = simulated hours with loss of load in which unit u is DOWN, importance =
+        down_in_loss / total loss hours = the reference's comp_importance (P(unit down | system failure))."""
+        o, bufs = self._seq_outputs(years, per_year, False, 0, False, 0)
+        s = _lib.SeqSummary()
+        cnt = np.zeros(self.n_units, dtype=np.uint64)
+        self._check(self._L.psra_seq_unit_importance(self._h, year0, years, seed, init_mode, years_per_chain, _ptr(cnt),
+                                                     C.byref(o), C.byref(s)))
+        r = self._seq_result(s, bufs)
+        tot = int(s.sum_lol_hours)
+        imp = cnt.astype(np.float64) / tot if tot > 0 else np.zeros(self.n_units)
+        return imp, cnt, r
+
     def seq_eval_injected(self, durations, years_per_chain: int = 1, fail_count: bool = False,
                           group: int = 0) -> SequentialIndices:
         """durations[nchains, U, K] (k = 0 initial TTF, then TTR, TTF, ...)."""

@@ -16,6 +16,7 @@ struct SeqArgs {
     const double *dur;      // injected durations or nullptr
     uint32_t *lol; long long *ens; uint32_t *ent; uint32_t *fail;
     unsigned long long *group_lol; unsigned long long *acc;
+    unsigned long long *imp;   // [U] hours with loss of load in which the unit is DOWN (seq_mc.cu only), or nullptr
 };
 
 // duration of one sampler draw in ticks of 2^-24 h (DESIGN.md "Sampler"): mean_ticks = mean * 2^24

@@ -84,6 +84,20 @@ __device__ __forceinline__ void schedule(UnitState &s, double t, int base)
     s.next = (c >= 1.0e9) ? INT_MAX : base + (int)c;
 }
 
+// number of set bits of the loss-of-load bitmap in the hour slots [s0, s1) of a segment
+__device__ __forceinline__ unsigned int lol_bits(const uint32_t *bm, int s0, int s1)
+{
+    unsigned int c = 0;
+    const int w0 = s0 >> 5, w1 = (s1 - 1) >> 5;
+    for (int w = w0; w <= w1; w++) {
+        uint32_t m = bm[w];
+        if (w == w0) m &= 0xffffffffu << (s0 & 31);
+        if (w == w1 && (s1 & 31)) m &= (1u << (s1 & 31)) - 1u;
+        c += __popc(m);
+    }
+    return c;
+}
+
 template <bool kInjected, bool kOneUnit>
 __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
 {
@@ -107,12 +121,18 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
         st_j = reinterpret_cast<uint32_t *>(reinterpret_cast<int *>(reinterpret_cast<double *>(p) + (size_t)wpb * a.U) +
                                             (size_t)wpb * a.U) + (size_t)warp * a.U;
     }
+    // weak-point statistic (a.imp): per-warp bitmap of the hours with loss of load of the current segment; sits behind
+    // the event bitmaps (the host allows it only without persistent unit states)
+    const bool want_imp = a.imp != nullptr;
+    uint32_t *lolbm = reinterpret_cast<uint32_t *>(tl_all + (size_t)wpb * seg_slots) + (size_t)(wpb + warp) * a.seg_words;
+    unsigned long long imp_acc = 0ull;      // kOneUnit: lane = unit
 
     // stage the load curve and the per-word maxima once per block
     for (int i = threadIdx.x; i < Hpad; i += blockDim.x) s_load[i] = a.load[i];
     for (int i = threadIdx.x; i < a.Wd; i += blockDim.x) s_lmax[i] = a.lmax[i];
     for (int i = lane; i < seg_slots; i += 32) tl[i] = 0;
     for (int i = lane; i < a.seg_words; i += 32) bm[i] = 0u;
+    if (want_imp) { for (int i = lane; i < a.seg_words; i += 32) lolbm[i] = 0u; }
     __syncthreads();
 
     unsigned long long acc_lol = 0, acc_ent = 0, acc_ywl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
@@ -144,6 +164,8 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
                 const int abs0 = y * a.H + seg_h0, abs1 = y * a.H + seg_h1;
                 const bool chain_start = (y == 0 && seg == 0);
                 int cap_part = 0;
+                const UnitState st0 = st;        // state at the segment start (replayed for the weak-point statistic)
+                bool seg_lol = false;
 
                 // ---------------- 1. event generation ----------------
                 for (int u = lane; u < (kOneUnit ? 32 : a.U); u += 32) {
@@ -231,6 +253,7 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
                         const bool lol = c < L;                  // PSA.jl:253 strict
                         const uint32_t mask = __ballot_sync(0xffffffffu, lol);
                         if (mask) {
+                            if (want_imp) { if (lane == 0) lolbm[wq] = mask; seg_lol = true; }
                             const uint32_t prev = (hy0 > 0 && csq < s_load[hy0 - 1]) ? 1u : 0u;
                             lolh += __popc(mask);
                             entries += __popc(mask & ~((mask << 1) | prev));   // calnlc.m:22-34
@@ -246,6 +269,49 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
                     capacity += __shfl_sync(0xffffffffu, incl, 31);
                 }
                 __syncwarp();
+
+                // ---------------- 2b. weak points (Montecarlo_seq/seqMain.m:140-150): hours with loss of load in which
+                //                  a unit is DOWN.  Rare (the segment must contain loss of load): every lane replays its
+                //                  units' events over the segment from the state at its start and counts the loss hours
+                //                  inside the DOWN stretches.
+                if (want_imp && seg_lol) {
+                    for (int u = lane; u < (kOneUnit ? 32 : a.U); u += 32) {
+                        if (kOneUnit && u >= a.U) break;
+                        float mf_r = mf, mr_r = mr; uint32_t thr_r = thr;
+                        if constexpr (!kOneUnit) { mf_r = a.mttf[u]; mr_r = a.mttr[u]; thr_r = a.for_thr[u]; }
+                        UnitState sr = st0;
+                        if (chain_start || !kOneUnit) {      // !kOneUnit: no persistent states here, every segment starts a chain
+                            sr.j = 0; sr.status = 1;
+                            if constexpr (!kInjected) {
+                                const uint32_t x0 = next_word<false>(a, chain, u, sr);
+                                if (a.init_mode == PSRA_INIT_STATIONARY && x0 < thr_r) sr.status = 0;
+                            }
+                            const double d0 = next_duration<kInjected>(a, cl, chain, u, sr, mf_r, mr_r);
+                            schedule(sr, (!kInjected && a.disc) ? d0 + 1.0 : d0, -1);
+                        }
+                        unsigned long long cnt = 0ull;
+                        int cur = abs0;                      // first hour of the present constant-state stretch
+                        while (true) {
+                            const int nx = min(sr.next, abs1);
+                            if (!sr.status && nx > cur) cnt += lol_bits(lolbm, cur - abs0, nx - abs0);
+                            if (sr.next >= abs1) break;
+                            double t = sr.r;
+                            do {
+                                sr.status ^= 1;
+                                t = __dadd_rn(t, next_duration<kInjected>(a, cl, chain, u, sr, mf_r, mr_r));
+                            } while (t <= 0.0);
+                            cur = sr.next;                   // the hour of a toggle already shows the new state (PSA.jl:249)
+                            schedule(sr, t, sr.next);
+                        }
+                        if (cnt) {
+                            if constexpr (kOneUnit) imp_acc += cnt;
+                            else atomicAdd(&a.imp[u], cnt);
+                        }
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < nwords; i += 32) lolbm[i] = 0u;
+                    __syncwarp();
+                }
             }
 
             // ---------------- 3. per-year indices ----------------
@@ -269,6 +335,7 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
         }
     }
 
+    if (kOneUnit && want_imp && lane < a.U && imp_acc) atomicAdd(&a.imp[lane], imp_acc);
     unsigned long long ev = n_events;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ev += __shfl_xor_sync(0xffffffffu, ev, d);
@@ -286,7 +353,7 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
 // ------------------------------------------------------------------------------- host side
 static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, long long chain_base,
                    long long nchains, int ypc, int init_mode, uint64_t seed, const psra_seq_outputs *out,
-                   psra_seq_summary *summary)
+                   psra_seq_summary *summary, uint64_t *imp_out = nullptr)
 {
     PSRA_REQUIRE(h, h->U > 0, "psra_set_system has not been called");
     PSRA_REQUIRE(h, h->H > 0, "psra_set_load has not been called");
@@ -301,9 +368,11 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
 
     const bool one_unit = h->U <= 32;
     const bool load16 = h->max_load <= 32767;
-    const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0];
+    // the weak-point statistic (imp_out) lives in the generic kernel of this file only
+    const bool fast = !injected && one_unit && (long long)ypc * h->H < (1ll << 26) && !h->cfg.reserved[0] && !imp_out;
     const bool team = !injected && !one_unit && h->U <= seq_team_max_units() && (long long)ypc * h->H < (1ll << 20) &&
-                      !h->cfg.reserved[0];
+                      !h->cfg.reserved[0] && !imp_out;
+    PSRA_REQUIRE(h, !imp_out || one_unit || ypc == 1, "unit importance for more than 32 units needs years_per_chain = 1");
     // seq_wide.cu: one block per year with a lane-level work queue over the units, when the whole year is one
     // shared-memory timeline (independent years, no explicit segment length); seq_team.cu covers the rest
     const bool wide = team && ypc == 1 && h->cfg.seg_hours == 0 && h->Wd * 32 <= 10240 && !h->cfg.reserved[2];
@@ -380,6 +449,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
         b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
         if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
+        if (imp_out) b += sizeof(uint32_t) * (size_t)w * seg_words;       // loss-of-load bitmaps
         return b;
     };
     if (team) {
@@ -439,6 +509,12 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         a.group = 1;
     }
     PSRA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * ACC_COUNT, h->stream));
+    if (imp_out) {
+        int rc = psra_reserve(h, &h->d_scratch2, &h->scratch2_cap, sizeof(unsigned long long) * (size_t)h->U);
+        if (rc) return rc;
+        PSRA_CUDA(h, cudaMemsetAsync(h->d_scratch2, 0, sizeof(unsigned long long) * (size_t)h->U, h->stream));
+        a.imp = (unsigned long long *)h->d_scratch2;
+    }
 
     void (*kern)(SeqArgs) = nullptr;
     if (injected) kern = one_unit ? seq_mc_kernel<true, true> : seq_mc_kernel<true, false>;
@@ -515,6 +591,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         }
     }
     PSRA_CUDA(h, cudaMemcpyAsync(acc, h->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, h->stream));
+    if (imp_out) PSRA_CUDA(h, cudaMemcpyAsync(imp_out, a.imp, sizeof(uint64_t) * (size_t)h->U, cudaMemcpyDeviceToHost, h->stream));
     if (out) {
         if (out->lol_hours) PSRA_CUDA(h, cudaMemcpyAsync(out->lol_hours, h->d_lol, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
         if (out->ens_fp)    PSRA_CUDA(h, cudaMemcpyAsync(out->ens_fp, h->d_ens, sizeof(int64_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
@@ -576,6 +653,24 @@ extern "C" int psra_seq_eval_injected(psra_handle *h, const double *durations, i
     for (size_t i = 0; i < n; i++)
         if (!(durations[i] > 0.0)) return psra_fail(h, PSRA_E_INVALID, "injected durations must be > 0 (entry %zu)", i);
     return run_seq(h, true, durations, K, 0, nchains, years_per_chain, PSRA_INIT_ALL_UP, 0, out, summary);
+}
+
+extern "C" int psra_seq_unit_importance(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed, int32_t init_mode,
+                                        int32_t years_per_chain, uint64_t *down_in_loss, const psra_seq_outputs *out,
+                                        psra_seq_summary *summary)
+{
+    if (!h) return PSRA_E_INVALID;
+    PSRA_REQUIRE(h, down_in_loss != nullptr, "down_in_loss must not be NULL");
+    PSRA_REQUIRE(h, years_per_chain >= 1, "years_per_chain must be >= 1");
+    PSRA_REQUIRE(h, year0 >= 0 && nyears >= 0, "negative year range");
+    PSRA_REQUIRE(h, year0 % years_per_chain == 0 && nyears % years_per_chain == 0,
+                 "year0 and nyears must be multiples of years_per_chain");
+    PSRA_REQUIRE(h, (init_mode & ~PSRA_DISC_MATLAB) == PSRA_INIT_ALL_UP || (init_mode & ~PSRA_DISC_MATLAB) == PSRA_INIT_STATIONARY,
+                 "unknown init_mode");
+    PSRA_REQUIRE(h, h->U > 0, "psra_set_system has not been called");
+    for (int u = 0; u < h->U; u++) down_in_loss[u] = 0;
+    return run_seq(h, false, nullptr, 0, year0 / years_per_chain, nyears / years_per_chain, years_per_chain,
+                   init_mode, seed, out, summary, down_in_loss);
 }
 
 // ------------------------------------------------------------------------------- sampler diagnostic

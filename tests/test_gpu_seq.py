@@ -377,3 +377,41 @@ def test_randomised_systems_sampler_path_vs_oracle(engine):
         assert np.array_equal(r.entries.astype(np.float64), ent), (case, U, H, ypc, init, disc)
         checked += 1
     assert checked >= 30
+
+
+@pytest.mark.gpu
+def test_unit_importance_weak_points(engine, rts):
+    """Montecarlo_seq/seqMain.m:140-150,225-231 at HL1: hours with loss of load in which each unit is DOWN, against the
+    oracle's literal hour/unit loop -- RTS-79 (both start modes, a multi-year chain, the MATLAB-free default
+    discretisation), a ragged short year with frequent losses, and a 64-unit system (generic strided path)."""
+    load = rts["load_int"]
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(load)
+    for init, ypc, years, y0 in ((1, 1, 96, 32), (0, 1, 64, 0), (1, 4, 64, 8)):
+        imp, cnt, r = engine.seq_unit_importance(years, seed=31, year0=y0, init_mode=init, years_per_chain=ypc, per_year=True)
+        lol, ens, ent, ref = O.seq_philox_importance(rts["cap"], rts["mttf"], rts["mttr"], load.astype(np.float64), 31,
+                                                     y0 // ypc, years // ypc, ypc, init)
+        assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
+        assert np.array_equal(cnt.astype(np.float64), ref) and ref.sum() > 0
+        assert np.allclose(imp, ref / lol.sum())
+        assert imp[21] > 0.5 and imp[22] > 0.5            # the two 400 MW units dominate the loss hours
+    # same per-year integers as the production kernel
+    fast = engine.seq_mc(96, seed=31, year0=32, per_year=True)
+    _, _, r = engine.seq_unit_importance(96, seed=31, year0=32, per_year=True)
+    assert np.array_equal(fast.lol_hours, r.lol_hours) and np.array_equal(fast.raw["ens_fp_vector"], r.raw["ens_fp_vector"])
+    # short ragged year, frequent losses, same-hour double toggles
+    cap = np.array([10.0, 5.0, 7.0]); mttf = np.array([30.0, 20.0, 3.0]); mttr = np.array([10.0, 15.0, 2.0])
+    ld = np.full(1000, 14, dtype=np.int32)
+    engine.set_system(cap, mttf, mttr); engine.set_load(ld)
+    imp, cnt, r = engine.seq_unit_importance(64, seed=3, per_year=True)
+    lol, ens, ent, ref = O.seq_philox_importance(cap, mttf, mttr, ld.astype(np.float64), 3, 0, 64, 1, 1)
+    assert np.array_equal(cnt.astype(np.float64), ref) and np.array_equal(r.lol_hours.astype(np.float64), lol)
+    # 64 units: lane-strided generic path
+    cap2 = np.tile(rts["cap"], 2); mttf2 = np.tile(rts["mttf"], 2); mttr2 = np.tile(rts["mttr"], 2)
+    ld2 = np.rint(2.05 * rts["load_mw"]).astype(np.int32)
+    engine.set_system(cap2, mttf2, mttr2); engine.set_load(ld2)
+    imp, cnt, r = engine.seq_unit_importance(48, seed=17, per_year=True)
+    lol, ens, ent, ref = O.seq_philox_importance(cap2, mttf2, mttr2, ld2.astype(np.float64), 17, 0, 48, 1, 1)
+    assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(cnt.astype(np.float64), ref) and ref.sum() > 0
+    with pytest.raises(Exception):
+        engine.seq_unit_importance(48, seed=17, years_per_chain=4)
+    engine.set_system(rts["cap"], rts["mttf"], rts["mttr"]); engine.set_load(load)
