@@ -43,6 +43,10 @@ with P.Engine() as e:
     t0 = time.perf_counter(); tail, hist = e.tail(None, alphas=(0.95, 0.99), n_bins=50, bin_width=1000); t1 = time.perf_counter()
     out["C4_tail_1e6"] = dict(seq_kernel_ms=r.kernel_ms, tail_wall_ms=(t1 - t0) * 1e3, var95=tail[0]["var"], cvar95=tail[0]["cvar"],
                               var99=tail[1]["var"], cvar99=tail[1]["cvar"], lole=r.lole, eens=r.eens, hist_first_bins=[int(x) for x in hist[:6]])
+    # weak-point detection (seqMain.m:225-231 at HL1) over 1e6 years: generic kernel + replay of the loss segments
+    imp, cnt, ri = e.seq_unit_importance(1_000_000, seed=42)
+    out["unit_importance_1e6"] = dict(kernel_ms=ri.kernel_ms, years_per_s=1e6 / ri.kernel_ms * 1e3, lole=ri.lole,
+                                      top5=[(int(u), float(imp[u])) for u in np.argsort(-imp)[:5]])
     # detailed MC (tail_risk.jl engine), 2000 years and 1e5 years
     gens = [P.DetailedGenerator("Nuclear", 400.0, 0.02, 4), P.DetailedGenerator("Coal_A", 300.0, 0.04, 3),
             P.DetailedGenerator("Coal_B", 300.0, 0.04, 3), P.DetailedGenerator("Gas", 150.0, 0.05, 2),
