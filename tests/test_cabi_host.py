@@ -136,3 +136,21 @@ def test_cumulative_series_and_export(tmp_path):
     assert int(last[0]) == n and int(last[1]) == int(lol[-1]) and float(last[4]) == eens[-1]
     idx = dict(line.split(",") for line in open(paths[1]).read().strip().split("\n")[1:])
     assert float(idx["lole"]) == r.lole and float(idx["eens"]) == r.eens
+
+
+def test_injected_fixture_export_for_the_patched_reference(tmp_path):
+    """tools/export_injected_fixture.py writes what tools/patched_reference.jl reads: raw little-endian Float64 files that
+    round-trip to the committed golden fixture."""
+    import subprocess, sys
+    out = tmp_path / "fx"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "export_injected_fixture.py"), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    U, K, years, H = (int(x) for x in open(out / "meta.txt").read().split())
+    g = np.load(os.path.join(ROOT, "tests", "golden", "seq_literal_seed123.npz"))
+    assert (U, K, years, H) == (32, g["dur"].shape[1], len(g["lol"]), 8736)
+    assert np.array_equal(np.fromfile(out / "dur.f64", dtype="<f8").reshape(U, K), g["dur"])
+    assert np.array_equal(np.fromfile(out / "lol.f64", dtype="<f8"), g["lol"]) and np.array_equal(np.fromfile(out / "eue.f64", dtype="<f8"), g["eue"])
+    assert np.fromfile(out / "load.f64", dtype="<f8").size == H and np.fromfile(out / "cap.f64", dtype="<f8").sum() == 3405.0
+    src = open(os.path.join(ROOT, "tools", "patched_reference.jl")).read()
+    for needle in ("ttf = [-log(rand())/g.lambda for g in gens]", "ttf[i] += -log(rand())/g.mu", "ttf[i] += -log(rand())/g.lambda"):
+        assert needle in src          # the three draws of PowerSystemAdequacy.jl:224,243,246 the tool substitutes
