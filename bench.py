@@ -194,6 +194,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line (NCCL logs its version there)
         dist.init_process_group("nccl", device_id=dev)
 
     Y = int(args.years_per_step)
