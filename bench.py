@@ -192,9 +192,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line (NCCL logs its version there)
+        # NCCL writes its version banner to the process's stdout at the first collective: park fd 1 on stderr until
+        # the JSON line is printed, so that stdout carries that one line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     Y = int(args.years_per_step)
@@ -331,7 +336,10 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{yrs} RTS-79 system-years ({yrs // threads} per thread), literal "
                                               f"hour/unit loop of PSA.jl:214-269, {secs:.1f} s"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
