@@ -556,6 +556,15 @@ def run_sequential_mc(gens: Sequence[Generator], load: LoadModel, years: int, se
     return (res, r) if details else res
 
 
+def unit_importance(gens: Sequence[Generator], load: LoadModel, years: int, seed: int = 42, fp_scale: float = 1.0,
+                    init_mode: int = INIT_STATIONARY, years_per_chain: int = 1, engine: Optional[Engine] = None):
+    """Montecarlo_seq/seqMain.m:140-150,225-231 at HL1 (twin of julia unit_importance): (comp_importance,
+    down_in_loss, SequentialIndices) for the generators of `gens`."""
+    eng = engine or default_engine()
+    eng.set_generators(gens, load, fp_scale)
+    return eng.seq_unit_importance(years, seed=seed, init_mode=init_mode, years_per_chain=years_per_chain)
+
+
 def compare_results(results: List[ReliabilityResult]) -> str:
     """PSA.jl:275-285 table (the Plots.jl figure of :288-297 is presentation, not reproduced)."""
     lines = ["", "==========================================", "       METHOD COMPARISON SUMMARY",
