@@ -19,7 +19,7 @@
  * All citations are path:line under /root/reference/GeneratingAdequacy unless a
  * directory is given.  PSA.jl = PowerSystemAdequacy.jl.
  *
- * Build:  gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (see oracle/Makefile).
+ * Build:  gcc -O3 -ffp-contract=off -fno-fast-math -shared -fPIC (see oracle/Makefile).
  */
 #include <math.h>
 #include <stdint.h>
@@ -122,36 +122,33 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* E = -ln(u) for the draw x, evaluated with integer bit operations and IEEE binary32
- * add/mul/fma only (every step correctly rounded, so any IEEE machine reproduces it bit for bit):
- *   w = x | 1;  lz = clz32(w);  X = w << lz;  u = w / 2^32 = m * 2^-(lz+1), m = X / 2^31 in [1,2);
- *   m is truncated to 24 bits: bits(m) = (X >> 8) + 0x3F000000;  k = lz + 1;
- *   range reduction to [sqrt(1/2), sqrt(2)) on the bit pattern (fdlibm logf):
- *     ix = bits + 0x004AFB0D;  k -= (ix >> 23) - 127;  bits(m_r) = (ix & 0x007FFFFF) + 0x3F3504F3;
- *   t = m_r - 1;  ln m_r = t + t^2 * P7(t) (Horner, fma);  E = fma(k, ln2_lo, fma(k, ln2_hi, -ln m_r))
- *   with the fdlibm split ln2_hi = 0x3f317180, ln2_lo = 0x3717f7d1.  0 < E <= 32 ln 2. */
+/* E = -ln(u) for the draw x (sampler specification v2), evaluated with integer bit operations and IEEE
+ * binary32 add / fma only (every step correctly rounded, so any IEEE machine reproduces it bit for bit):
+ *   w = x | 1;  lz = clz32(w);  X = w << lz;  u = w / 2^32 = m * 2^-k,  k = lz + 1,  m = X / 2^31 in [1,2);
+ *   m is truncated to 24 bits: bits(m) = 0x3F800000 | ((X >> 8) & 0x7FFFFF);
+ *   t = m - 1.5 (exact);  R = P7(t) ~ -ln(1.5 + t)  (Horner with fma; minimax fit on [-0.5, 0.5), |error| < 2.5e-7);
+ *   E = fma(k, LN2, R),  LN2 = 0x1.62e430p-1.
+ * -1.2e-7 <= E <= 32 ln 2: for the 768 draws nearest 2^32 the approximation error makes E <= 0; the duration
+ * clamp (at least one tick) absorbs them.  The coefficients come from a Remez exchange (float64) rounded to
+ * binary32; measured over 2 10^7 random draws: max |E + ln u| = 7.2e-7 (at E > 16, rounding of the result),
+ * mean error 3.4e-8. */
 static float u32_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 
-static const float LOGP[8] = { -0x1.fffff4p-2f, 0x1.5557acp-2f, -0x1.000688p-2f, 0x1.98a666p-3f,
-                               -0x1.52fdeep-3f, 0x1.32c6a8p-3f, -0x1.27c4d6p-3f, 0x1.65b9f8p-4f };
+static const float LOGP[8] = { -0x1.9f324cp-2f, -0x1.555536p-1f, 0x1.c72898p-3f, -0x1.94b470p-4f,
+                               0x1.90d388p-5f, -0x1.a7b9fep-6f, 0x1.1d506cp-6f, -0x1.578b02p-7f };
+#define ORACLE_LN2_F 0x1.62e430p-1f
 
 float oracle_neglog_u32(uint32_t x)
 {
     uint32_t w = x | 1u;
     int lz = __builtin_clz(w);
     uint32_t X = w << lz;
-    uint32_t bits = (X >> 8) + 0x3F000000u;
-    int k = lz + 1;
-    uint32_t ix = bits + 0x004AFB0Du;
-    k -= (int)(ix >> 23) - 127;
-    float m = u32_as_float((ix & 0x007FFFFFu) + 0x3F3504F3u);
-    float t = m - 1.0f;
+    float m = u32_as_float(0x3F800000u | ((X >> 8) & 0x007FFFFFu));
+    float t = m - 1.5f;
     float p = LOGP[7];
     for (int i = 6; i >= 0; i--) p = fmaf(p, t, LOGP[i]);
-    float q = t * t;
-    float r = fmaf(q, p, t);
-    float kf = (float)k;
-    return fmaf(kf, 9.0580006145e-06f, fmaf(kf, 6.9313812256e-01f, -r));
+    float kf = (float)(lz + 1);
+    return fmaf(kf, ORACLE_LN2_F, p);
 }
 
 /* Duration of one draw in hours: quantised to ticks of 2^-24 h so that every residual of the
@@ -688,12 +685,12 @@ int oracle_detailed_mc_injected(int U, const double *cap, const double *for_rate
 }
 
 /* Standard normal from two sampler words, fixed binary32 operation sequence (Box-Muller):
- *   r = sqrt(2 * E(x1)),  E = oracle_neglog_u32;
+ *   r = sqrt(2 * max(E(x1), 0)),  E = oracle_neglog_u32 (which may dip to -1.2e-7 for draws next to 2^32);
  *   angle = 2 pi (4k + f) / 4 with k = x2 >> 30 and f = (2*((x2 >> 7) & 0x7FFFFF) + 1) / 2^24 in (0,1);
  *   phi = f * pi/2 folded to [0, pi/4] (swap sin/cos), Taylor polynomials by fma;  z = r * cos(angle). */
 float oracle_normal_u32x2(uint32_t x1, uint32_t x2)
 {
-    float r = sqrtf(2.0f * oracle_neglog_u32(x1));
+    float r = sqrtf(2.0f * fmaxf(oracle_neglog_u32(x1), 0.0f));
     uint32_t k = x2 >> 30;
     float f = (float)(2u * ((x2 >> 7) & 0x7FFFFFu) + 1u) * 5.9604644775390625e-08f;   /* exact */
     int swap = f > 0.5f;

@@ -33,10 +33,10 @@ struct DmArgs {
     uint32_t *year_lole; uint32_t *hourly_fail;
 };
 
-// standard normal from two words: r = sqrt(2 E(x1)), angle = (k + f) pi/2, fixed binary32 sequence
+// standard normal from two words: r = sqrt(2 max(E(x1), 0)), angle = (k + f) pi/2, fixed binary32 sequence
 __device__ __forceinline__ float normal_u32x2(uint32_t x1, uint32_t x2)
 {
-    const float r = __fsqrt_rn(__fmul_rn(2.0f, neglog_u32(x1)));
+    const float r = __fsqrt_rn(__fmul_rn(2.0f, fmaxf(neglog_u32(x1), 0.0f)));
     const uint32_t k = x2 >> 30;
     const float f = __fmul_rn((float)(2u * ((x2 >> 7) & 0x7FFFFFu) + 1u), 5.9604644775390625e-08f);
     const bool swap = f > 0.5f;

@@ -129,42 +129,33 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-// E = -ln(u) of the draw x, u = (x | 1) / 2^32: integer normalisation + binary32 fma polynomial,
-// a fixed sequence of correctly rounded operations (DESIGN.md "Sampler"), reproducible bit for bit
-// on any IEEE-754 machine.  0 < E <= 32 ln 2.
-// Specification (what the CPU checker spells out): w = x | 1, lz = clz(w), X = w << lz,
-// ix = (X >> 8) + 0x3F000000 + 0x004AFB0D (m = X / 2^31 truncated to 24 bits, fdlibm reduction to
-// [sqrt(.5), sqrt(2))), k = lz + 1 - ((ix >> 23) - 127), m' = (ix & 0x7FFFFF) + 0x3F3504F3.
-// Here the normalisation is one conversion: the binary32 value of w rounded toward zero has the
-// exponent field 158 - lz and the same 23 truncated mantissa bits, so iy = bits(RZ(w)) + 0x004AFB0D
-// equals ix + ((31 - lz) << 23): same mantissa field, k = 159 - (iy >> 23).  (float)k comes from the
-// 2^23 trick (0 <= k <= 32), which keeps the conversion off the ALU pipe.  Checked exhaustively
-// (all 2^32 draws) against the specification on the CPU.
+// E = -ln(u) of the draw x, u = (x | 1) / 2^32 -- sampler specification v2 (the CPU checker
+// oracle_neglog_u32 spells out the same sequence): a fixed sequence of integer operations and correctly rounded
+// binary32 add / fma, reproducible bit for bit on any IEEE-754 machine.
+//   w = x | 1,  lz = clz(w),  u = w / 2^32 = m * 2^-k  with  k = lz + 1 (1..32)  and  m in [1, 2) truncated to 24 bits;
+//   t = m - 1.5 (exact),  R = P7(t) ~ -ln(1.5 + t) (Horner, seven fma; minimax on [-0.5, 0.5), |error| < 2.5e-7);
+//   E = fma(k, LN2, R).   -1.2e-7 <= E <= 32 ln 2: for the 768 draws closest to 2^32 the polynomial's error makes E <= 0;
+//   the duration clamp max(., 1 tick) of dur_ticks absorbs them.
+// Here the normalisation is one conversion: the binary32 value of w rounded toward zero has the exponent field
+// e = 158 - lz and the 23 truncated mantissa bits of m.  -k as a float without an integer -> float conversion: a funnel
+// shift puts e under the exponent of 2^23 (bits 0x4B000000 + e = the float 2^23 + e), and (2^23 + e) - (2^23 + 159) =
+// e - 159 = -k is exact; fma(-k, -LN2, R) rounds the same real number as fma(k, LN2, R).
+// 14 instructions per draw (v1, the fdlibm-style reduction to [sqrt(1/2), sqrt(2)) with a degree-9 polynomial: 21).
+#define PSRA_LN2_F 0x1.62e430p-1f
 __device__ __forceinline__ float neglog_u32(uint32_t x)
 {
-    // Pipe balance (the integer ALU pipe is what limits the sequential kernels): with e = (fw + 0x004AFB0D) >> 23 the
-    // mantissa of m is fw + 0x3F800000 - (e << 23) (one IMAD; 0x004AFB0D + 0x3F3504F3 = 0x3F800000), and
-    // 2k = 2 * (159 - e) is built as a float by an IMAD with the factor -2 (ptxas turns a factor -1 into an ALU
-    // subtract); the two ln 2 constants below are halved instead -- exact scalings, so every fma rounds as specified.
     const uint32_t fw = __float_as_uint(__uint2float_rz(x | 1u));
-    const uint32_t e = (fw + 0x004AFB0Du) >> 23;
-    uint32_t mb, kb;
-    asm("mad.lo.u32 %0, %1, 0xFF800000, %2;" : "=r"(mb) : "r"(e), "r"(fw + 0x3F800000u));
-    asm("mad.lo.u32 %0, %1, 0xFFFFFFFE, %2;" : "=r"(kb) : "r"(e), "r"(0x4B00013Eu));
-    const float m = __uint_as_float(mb);
-    const float kf2 = __fadd_rn(__uint_as_float(kb), -8388608.0f);     // 2 k, 0 <= k <= 32
-    const float t = __fadd_rn(m, -1.0f);
-    float p = 0x1.65b9f8p-4f;
-    p = __fmaf_rn(p, t, -0x1.27c4d6p-3f);
-    p = __fmaf_rn(p, t, 0x1.32c6a8p-3f);
-    p = __fmaf_rn(p, t, -0x1.52fdeep-3f);
-    p = __fmaf_rn(p, t, 0x1.98a666p-3f);
-    p = __fmaf_rn(p, t, -0x1.000688p-2f);
-    p = __fmaf_rn(p, t, 0x1.5557acp-2f);
-    p = __fmaf_rn(p, t, -0x1.fffff4p-2f);
-    const float r = __fmaf_rn(__fmul_rn(t, t), p, t);       // ln m
-    // k * 9.0580006145e-06 + (k * 6.9313812256e-01 - r), written with 2k and the halved constants
-    return __fmaf_rn(kf2, 0x1.2fefa2p-18f, __fmaf_rn(kf2, 0x1.62e3p-2f, -r));
+    const float t = __fadd_rn(__uint_as_float((fw & 0x007FFFFFu) | 0x3F800000u), -1.5f);
+    float p = -0x1.578b02p-7f;
+    p = __fmaf_rn(p, t, 0x1.1d506cp-6f);
+    p = __fmaf_rn(p, t, -0x1.a7b9fep-6f);
+    p = __fmaf_rn(p, t, 0x1.90d388p-5f);
+    p = __fmaf_rn(p, t, -0x1.94b470p-4f);
+    p = __fmaf_rn(p, t, 0x1.c72898p-3f);
+    p = __fmaf_rn(p, t, -0x1.555536p-1f);
+    p = __fmaf_rn(p, t, -0x1.9f324cp-2f);
+    const float nk = __fadd_rn(__uint_as_float(__funnelshift_r(fw, 0x00258000u, 23)), -8388767.0f);   // e - 159 = -k
+    return __fmaf_rn(nk, -PSRA_LN2_F, p);
 }
 
 // duration of one draw in ticks of 2^-24 h: RN_int64(max(mean_ticks * E, 1)), mean_ticks = mean * 2^24
