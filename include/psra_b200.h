@@ -35,7 +35,7 @@ extern "C" {
 #define PSRA_E_INVALID  -1   /* bad argument / call order */
 #define PSRA_E_CUDA     -2   /* CUDA runtime error (no device, OOM, launch failure) */
 #define PSRA_E_OVERFLOW -3   /* injected durations exhausted / table too small */
-#define PSRA_E_NCCL     -4
+#define PSRA_E_NCCL     -4   /* multi-GPU handle: libnccl.so.2 missing, communicator set-up or all-reduce failed */
 
 #define PSRA_INIT_ALL_UP      0  /* PSA.jl:223-224: every unit UP at hour 0 */
 #define PSRA_INIT_STATIONARY  1  /* state ~ Bernoulli(FOR), residual ~ Exp (memoryless) */
@@ -47,18 +47,30 @@ extern "C" {
 typedef struct psra_handle psra_handle;
 
 typedef struct psra_config {
-    int32_t device;           /* CUDA device ordinal */
+    int32_t device;           /* CUDA device ordinal (the first one when ngpus > 1) */
     int32_t warps_per_block;  /* sequential kernel: 0 = default */
     int32_t seg_hours;        /* sequential kernel: hours per shared-memory timeline segment,
                                  multiple of 32; 0 = default */
     int32_t blocks_per_sm;    /* 0 = as many as fit */
     int32_t reserved[4];      /* reserved[0] != 0: force the generic sequential kernel (seq_mc.cu) also
                                  for systems of <= 32 units (cross-checks; the default picks seq_fast.cu);
-                                 reserved[1] != 0: seq_fast.cu keeps the word sums unpacked (cross-checks);
+                                 reserved[1] == 1: seq_fast.cu keeps the word sums unpacked, seq_wide.cu keeps one hour
+                                 per timeline word; == 2: seq_wide.cu packs two hours per word whatever the unit sizes
+                                 (cross-checks of the redo path);
                                  reserved[2] != 0: systems of > 32 units use seq_team.cu also where seq_wide.cu
                                  applies (cross-checks);
                                  reserved[3] > 0: number of statically scheduled Philox blocks per unit in
                                  seq_fast.cu's single-segment mode (0 = chosen from the expected demand) */
+    int32_t ngpus;            /* 0 / 1: one device.  G > 1: the handle spans the devices device .. device + G - 1 of this
+                                 process; psra_seq_mc / psra_nonseq_mc split their year / sample range over them
+                                 (contiguous shards keyed on the global index, so the integers do not depend on G) and
+                                 combine the accumulators, per-hour failure counts and the ENS histogram with
+                                 ncclAllReduce(ncclSum) over NVLink (PSRA_E_NCCL if NCCL is unavailable or fails) */
+    int32_t ev_cap;           /* cross-checks: event-list slots per warp of seq_fast.cu (0 = sized from the expected
+                                 transitions; a small value exercises the redo path) */
+    int32_t tail_bins;        /* bins (1 fixed-point MWh wide) of the per-year ENS histogram kept for psra_tail;
+                                 0 = 64 x the installed capacity, between 2^16 and 2^24 */
+    int32_t reserved2[5];
 } psra_config;
 
 /* lifetime ------------------------------------------------------------------------- */
@@ -96,8 +108,9 @@ typedef struct psra_seq_summary {
     uint64_t sum_ens_sq_lo;     /* sum of ENS^2, 128-bit little-endian pair */
     uint64_t sum_ens_sq_hi;
     uint64_t events;            /* state transitions simulated (diagnostic) */
-    float    kernel_ms;         /* CUDA-event time of the kernel(s) of this call */
-    int32_t  reserved;
+    float    kernel_ms;         /* CUDA-event time of the kernel(s) of this call (multi-GPU: the slowest device) */
+    int32_t  redone;            /* chains a fast kernel handed back and the library replayed with the generic kernel
+                                   (event list full / packed-timeline checksum); results are exact either way */
 } psra_seq_summary;
 
 typedef struct psra_seq_outputs {       /* all optional (NULL = not wanted) */
@@ -112,6 +125,11 @@ typedef struct psra_seq_outputs {       /* all optional (NULL = not wanted) */
     int32_t   keep_on_device; /* !=0: keep the per-year ENS / LOL vectors on the device for psra_tail */
     double   *history;      /* [nyears/group] running mean of LOL hours after every `group` years, i.e.
                                convergence_history of PSA.jl:263-265, computed on the device */
+    int32_t   tail_hist;    /* !=0: the kernel also counts the years by their ENS (bins of 1 fixed-point MWh, see
+                               psra_config.tail_bins) -- the histogram of tail_risk.jl:168-175 / seqMain.m:287; it stays on
+                               the device (all-reduced over the devices of a multi-GPU handle) and psra_tail(values =
+                               NULL) computes exact VaR / CVaR from the counts: no per-year vector in HBM */
+    int32_t   reserved;
 } psra_seq_outputs;
 
 /* Years [year0, year0+nyears) of the experiment `seed`.  Years are grouped in chains of
@@ -223,12 +241,22 @@ typedef struct psra_tail_out {
     int64_t x_lo, x_hi; /* the two order statistics bracketing the quantile position */
 } psra_tail_out;
 
-/* values[n]: per-year ENS (fixed point).  values == NULL uses the vector kept on the device
- * by the last psra_seq_mc call with keep_on_device.  hist (optional) receives n_bins counts
- * of width bin_width starting at 0, last bin open-ended. */
+/* values[n]: per-year ENS (fixed point).  values == NULL uses what the last psra_seq_mc call left on the device: the
+ * ENS histogram (psra_seq_outputs.tail_hist; one kernel launch over the bins, exact order statistics and tail sums
+ * from the counts) or else the per-year vector (keep_on_device; radix select).  hist (optional) receives n_bins counts
+ * of width bin_width starting at 0, last bin open-ended.  PSRA_E_OVERFLOW if a requested quantile lies beyond the
+ * histogram's range (raise psra_config.tail_bins). */
 int psra_tail(psra_handle *h, const int64_t *values, int64_t n, const double *alphas,
               int32_t n_alpha, psra_tail_out *out, int64_t *hist, int32_t n_bins,
               int64_t bin_width);
+
+/* The device histogram as plain integers, for callers that shard the years over processes (one handle per process /
+ * GPU, torch.distributed or MPI between them): export the counts of this handle, sum them element-wise over the ranks,
+ * import the sums and call psra_tail(values = NULL) -- O(bins) bytes per rank instead of 8 B per year.
+ * meta[4] = {years, years with loss of load, years beyond the range, their ENS sum}; counts[0 .. *n_used) = bins up to
+ * the last non-empty one (n_used <= max_bins, else PSRA_E_OVERFLOW). */
+int psra_tail_hist_export(psra_handle *h, int64_t *counts, int64_t max_bins, int64_t *n_used, int64_t *meta);
+int psra_tail_hist_import(psra_handle *h, const int64_t *counts, int64_t n, const int64_t *meta);
 
 /* hourly-resampled MC with maintenance / LFU / energy-limited units: replaces run_detailed_mc
  * (tail_risk.jl:12-91) == run_monte_carlo (MCvsMarkovProcess.jl:210-284) ---------------------- */
@@ -287,8 +315,8 @@ typedef struct psra_area_summary {
 } psra_area_summary;
 
 /* Years [year0, year0+nyears) of experiment `seed`, independent years (each with its own Philox streams keyed
- * (seed; year, global unit index); init_mode as psra_seq_mc).  Replaces the handle's unit table (psra_set_system
- * is called with the flattened unit list); the load set by psra_set_load is not touched. */
+ * (seed; year, global unit index); init_mode as psra_seq_mc).  Self-contained: the system and load the handle holds
+ * from psra_set_system / psra_set_load are neither used nor changed. */
 int psra_multi_area_mc(psra_handle *h, const psra_area_system *sys, int32_t policy, int64_t year0,
                        int64_t nyears, uint64_t seed, int32_t init_mode, const psra_area_outputs *out,
                        psra_area_summary *summary);

@@ -53,6 +53,8 @@ end
 struct PsraConfig
     device::Int32; warps_per_block::Int32; seg_hours::Int32; blocks_per_sm::Int32
     reserved::NTuple{4,Int32}
+    ngpus::Int32; ev_cap::Int32; tail_bins::Int32
+    reserved2::NTuple{5,Int32}
 end
 struct PsraAreaSystem
     n_areas::Int32; n_units::Int32; n_hours::Int32; reserved::Int32
@@ -72,8 +74,16 @@ mutable struct PsraAreaSummary
     PsraAreaSummary() = new(0, ntuple(_ -> Int64(0), 8), ntuple(_ -> Int64(0), 8), 0, 0f0, 0)
 end
 
+# capacities and tie capacities must lie on the fixed-point grid (error otherwise); loads are ceiled onto it, which
+# keeps the reference's Float64 test `margin < 0` exact for whole-grid capacities (c < L <=> c < ceil(L))
 function fixed(x::AbstractVector{Float64}, scale::Float64)
-    return Int32.(round.(x .* scale))
+    v = x .* scale; r = round.(v)
+    all(abs.(v .- r) .<= 1e-6) || error("value not representable at fp_scale=$scale; choose a finer scale")
+    return Int32.(r)
+end
+function fixed_load(x::AbstractVector{Float64}, scale::Float64)
+    v = x .* scale; r = round.(v)
+    return Int32.(ifelse.(abs.(v .- r) .<= 1e-6, r, ceil.(v)))
 end
 
 """
@@ -81,7 +91,7 @@ end
 
 Same call and return value as AdequacyAssessmentII.jl:185-250: a vector of `(area, lole, eue)` named tuples.
 Years are independent (own Philox streams keyed (seed; year, unit)); MW values are converted to fixed point
-(`round(x * fp_scale)`).
+(capacities must lie on the grid; loads are ceiled onto it).
 """
 function run_fast_sequential_simulation(sys::System, policy::SupportPolicy, n_years::Int; seed::Integer=42,
                                         fp_scale::Float64=1.0, device::Integer=0)
@@ -99,12 +109,13 @@ function run_fast_sequential_simulation(sys::System, policy::SupportPolicy, n_ye
     loads = Int32[]                                     # [n_areas][H], row-major for C
     for area in sys.areas
         length(area.hourly_load) == H || error("all areas need load curves of the same length")
-        append!(loads, fixed(area.hourly_load, fp_scale))
+        append!(loads, fixed_load(area.hourly_load, fp_scale))
     end
     topo = fixed(vec(permutedims(sys.topology_matrix)), fp_scale)   # symmetric; row-major for C
 
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    cfg = Ref(PsraConfig(Int32(device), 0, 0, 0, (Int32(0), Int32(0), Int32(0), Int32(0))))
+    cfg = Ref(PsraConfig(Int32(device), 0, 0, 0, (Int32(0), Int32(0), Int32(0), Int32(0)), Int32(1), Int32(0), Int32(0),
+                         (Int32(0), Int32(0), Int32(0), Int32(0), Int32(0))))
     rc = ccall((:psra_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{PsraConfig}), h, cfg)
     rc == 0 || error("psra_create failed ($rc): no CUDA device / library? (there is no CPU fallback)")
     s = PsraAreaSummary()
@@ -132,25 +143,7 @@ function run_fast_sequential_simulation(sys::System, policy::SupportPolicy, n_ye
     return results
 end
 
-# AdequacyAssessmentII.jl:256-290
-function run_demo()
-    gens1 = [Generator("G1_$i", 400.0, 1000.0, 50.0) for i in 1:5]
-    load1 = 1000.0 .+ 500.0 .* sin.(range(0, 2π, length=8760))
-    gens2 = [Generator("G2_$i", 200.0, 900.0, 60.0) for i in 1:5]
-    load2 = 800.0 .+ 400.0 .* sin.(range(0, 2π, length=8760))
-    sys = System([Area(1, "Area_Rich", gens1, collect(load1)), Area(2, "Area_Poor", gens2, collect(load2))], [TieLine(1, 2, 200.0)])
-    res_iso = run_fast_sequential_simulation(sys, ISOLATED, 500)
-    res_int = run_fast_sequential_simulation(sys, INTERCONNECTED, 500)
-    println("\n=== FINAL COMPARISON (FAST METHOD) ===")
-    println("Policy          | Area       | LOLE (h/yr) | EUE (MWh/yr)")
-    println("-"^60)
-    for r in res_iso
-        @printf("ISOLATED        | %-10s | %10.2f  | %10.2f\n", r.area, r.lole, r.eue)
-    end
-    println("-"^60)
-    for r in res_int
-        @printf("INTERCONNECTED  | %-10s | %10.2f  | %10.2f\n", r.area, r.lole, r.eue)
-    end
-end
+# The reference's demo driver (AdequacyAssessmentII.jl:256-291, run_adequacy_assessmentII.jl) stays with the reference:
+# include this module instead of AdequacyAssessmentII.jl and its `run_demo` body works unchanged.
 
 end # module

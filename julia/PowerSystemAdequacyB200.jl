@@ -59,16 +59,19 @@ end
 struct PsraConfig
     device::Int32; warps_per_block::Int32; seg_hours::Int32; blocks_per_sm::Int32
     reserved::NTuple{4,Int32}
+    ngpus::Int32; ev_cap::Int32; tail_bins::Int32
+    reserved2::NTuple{5,Int32}
 end
 mutable struct PsraSeqSummary
     years::Int64; sum_lol_hours::Int64; sum_ens_fp::Int64; sum_entries::Int64; years_with_loss::Int64
     sum_lol_sq::UInt64; sum_ens_sq_lo::UInt64; sum_ens_sq_hi::UInt64; events::UInt64
-    kernel_ms::Float32; reserved::Int32
+    kernel_ms::Float32; redone::Int32
     PsraSeqSummary() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0f0, 0)
 end
 struct PsraSeqOutputs
     lol_hours::Ptr{UInt32}; ens_fp::Ptr{Int64}; entries::Ptr{UInt32}; fail_count::Ptr{UInt32}
     group_lol::Ptr{Int64}; group::Int32; keep_on_device::Int32; history::Ptr{Float64}
+    tail_hist::Int32; reserved::Int32
 end
 mutable struct PsraNonseqSummary
     samples::Int64; sum_lol_hours::Int64; sum_ens_fp::Int64; samples_with_loss::Int64
@@ -96,8 +99,16 @@ function check(e::Engine, rc::Cint)
     error("libpsra_b200 error $rc: $msg")
 end
 
-function Engine(; device::Integer=0)
-    cfg = Ref(PsraConfig(Int32(device), 0, 0, 0, (Int32(0), Int32(0), Int32(0), Int32(0))))
+"""
+    Engine(; device=0, ngpus=1)
+
+One libpsra_b200 handle.  `ngpus = G > 1` spans the devices `device .. device+G-1` of this process: the Monte Carlo
+calls shard their years / samples over them and combine the integer accumulators, per-hour failure counts and the ENS
+histogram with `ncclAllReduce` inside the library -- `run_sequential_mc(gens, load, years; engine=Engine(ngpus=8))`.
+"""
+function Engine(; device::Integer=0, ngpus::Integer=1)
+    z4 = (Int32(0), Int32(0), Int32(0), Int32(0)); z5 = (Int32(0), Int32(0), Int32(0), Int32(0), Int32(0))
+    cfg = Ref(PsraConfig(Int32(device), 0, 0, 0, z4, Int32(ngpus), Int32(0), Int32(0), z5))
     hp = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:psra_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{PsraConfig}), hp, cfg)
     e = Engine(hp[], 1.0)
@@ -114,13 +125,24 @@ end
 const _engine = Ref{Union{Nothing,Engine}}(nothing)
 default_engine() = (_engine[] === nothing && (_engine[] = Engine()); _engine[]::Engine)
 
-# Float64 MW -> int32 fixed point (round-half-even, like Julia's round())
-fixed(x::AbstractVector{Float64}, scale::Float64) = Int32.(round.(x .* scale))
+# Float64 MW -> int32 fixed point.  Capacities must lie on the grid (error otherwise: choose a finer fp_scale).
+function fixed(x::AbstractVector{Float64}, scale::Float64)
+    v = x .* scale; r = round.(v)
+    all(abs.(v .- r) .<= 1e-6) || error("capacity is not representable at fp_scale=$scale; choose a finer scale")
+    return Int32.(r)
+end
+# Loads: the reference tests `cap_avail < load` in Float64 (PowerSystemAdequacy.jl:192,253); with capacities on the
+# grid, c < L  <=>  c < ceil(L), so ceil keeps every loss-of-load hour exactly (LOLE / LOLF unbiased; the deficit is
+# over-stated by < 1 grid unit per loss hour -- a finer fp_scale shrinks that).  Loads on the grid are unchanged.
+function fixed_load(x::AbstractVector{Float64}, scale::Float64)
+    v = x .* scale; r = round.(v)
+    return Int32.(ifelse.(abs.(v .- r) .<= 1e-6, r, ceil.(v)))
+end
 
 function set_system!(e::Engine, gens::Vector{Generator}, load::LoadModel; fp_scale::Float64=1.0)
     cap = fixed([g.capacity for g in gens], fp_scale)
     mttf = [g.mttf for g in gens]; mttr = [g.mttr for g in gens]
-    ld = fixed(load.hourly_load, fp_scale)
+    ld = fixed_load(load.hourly_load, fp_scale)
     GC.@preserve cap mttf mttr ld begin
         check(e, ccall((:psra_set_system, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int32),
                        e.h, cap, mttf, mttr, Int32(length(cap))))
@@ -179,13 +201,14 @@ end
 "Sequential MC with the full index set (LOLE, EENS, LOLF = mean NLC, LOLD; Montecarlo_seq/seqMain.m:160-213)"
 function run_sequential_indices(gens::Vector{Generator}, load::LoadModel, years::Int; seed::Integer=42,
                                 year0::Integer=0, fp_scale::Float64=1.0, init_mode::Int32=PSRA_INIT_STATIONARY,
-                                years_per_chain::Integer=1, keep_on_device::Bool=false,
+                                years_per_chain::Integer=1, keep_on_device::Bool=false, tail_hist::Bool=false,
                                 engine::Engine=default_engine())
     set_system!(engine, gens, load; fp_scale=fp_scale)
     history = zeros(Float64, div(years, 10))          # running mean every 10 years, computed on the device
     s = PsraSeqSummary()
     GC.@preserve history begin
-        out = Ref(PsraSeqOutputs(C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, Int32(10), Int32(keep_on_device), pointer(history)))
+        out = Ref(PsraSeqOutputs(C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, Int32(10), Int32(keep_on_device), pointer(history),
+                                 Int32(tail_hist), Int32(0)))
         check(engine, ccall((:psra_seq_mc, LIB), Cint,
                             (Ptr{Cvoid}, Int64, Int64, UInt64, Int32, Int32, Ref{PsraSeqOutputs}, Ref{PsraSeqSummary}),
                             engine.h, year0, years, UInt64(seed), init_mode, Int32(years_per_chain), out, s))
@@ -196,7 +219,15 @@ function run_sequential_indices(gens::Vector{Generator}, load::LoadModel, years:
                              s.years_with_loss / n, s.events, s.kernel_ms, history)
 end
 
-"run_sequential_mc, PowerSystemAdequacy.jl:214-269 (history: running mean every 10 years)"
+"""
+run_sequential_mc, PowerSystemAdequacy.jl:214-269 (history: running mean every 10 years).
+
+Default semantics differ from the reference in one documented way (INTEGRATION.md section 4): the reference runs ONE
+chain that starts all-up and carries the unit states across all years (:223-224); the default here is independent
+years from the stationary law (`init_mode=PSRA_INIT_STATIONARY, years_per_chain=1`): the same expectation without the
+all-up start bias, and what lets the years shard over GPUs.  `init_mode=PSRA_INIT_ALL_UP, years_per_chain=years`
+reproduces the reference's chain.  `engine=Engine(ngpus=8)` uses eight GPUs from this one call.
+"""
 function run_sequential_mc(gens::Vector{Generator}, load::LoadModel, years::Int; kwargs...)
     t_start = time()
     r = run_sequential_indices(gens, load, years; kwargs...)
@@ -223,7 +254,7 @@ function unit_importance(gens::Vector{Generator}, load::LoadModel, years::Int; s
     return imp, cnt, idx
 end
 
-"VaR / CVaR of the per-year ENS kept on the device by run_sequential_indices(...; keep_on_device=true)"
+"VaR / CVaR of the per-year ENS of the last run_sequential_indices(...; tail_hist=true) (exact, from the device's ENS histogram: no per-year vector) or (...; keep_on_device=true) (radix select over the kept vector)"
 function tail_risk(alphas::Vector{Float64}=[0.95, 0.99]; engine::Engine=default_engine())
     outs = Vector{PsraTailOut}(undef, length(alphas))
     GC.@preserve alphas outs begin

@@ -12,4 +12,4 @@ from .api import (DetailedGenerator, SystemParams, run_detailed_mc, run_monte_ca
                   Engine, Generator, LoadModel, PsraError, ReliabilityResult, SequentialIndices,  # noqa: F401
                   compare_results, cumulative_series, export_results, unit_importance, evaluate_risk, indices_from_raw, run_analytical,
                   run_non_sequential_mc, run_sequential_mc,
-                  ISOLATED, INTERCONNECTED, AreaGenerator, TieLine, Area, System, run_fast_sequential_simulation, run_demo)
+                  ISOLATED, INTERCONNECTED, AreaGenerator, TieLine, Area, System, run_fast_sequential_simulation)

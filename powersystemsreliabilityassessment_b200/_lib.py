@@ -27,25 +27,28 @@ EXPORTS = [
     "psra_nonseq_eval_states", "psra_nonseq_eval_uniforms", "psra_copt", "psra_copt_indices",
     "psra_copt_indices_strict", "psra_fd_recursion", "psra_markov2", "psra_dtmc_capacity", "psra_tail", "psra_detailed_mc", "psra_detailed_eval_injected",
     "psra_multi_area_mc", "psra_failure_times", "psra_sampler_durations", "psra_seq_unit_importance",
+    "psra_tail_hist_export", "psra_tail_hist_import",
 ]
 
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("warps_per_block", C.c_int32), ("seg_hours", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("blocks_per_sm", C.c_int32), ("reserved", C.c_int32 * 4), ("ngpus", C.c_int32), ("ev_cap", C.c_int32),
+                ("tail_bins", C.c_int32), ("reserved2", C.c_int32 * 5)]
 
 
 class SeqSummary(C.Structure):
     _fields_ = [("years", C.c_int64), ("sum_lol_hours", C.c_int64), ("sum_ens_fp", C.c_int64),
                 ("sum_entries", C.c_int64), ("years_with_loss", C.c_int64), ("sum_lol_sq", C.c_uint64),
                 ("sum_ens_sq_lo", C.c_uint64), ("sum_ens_sq_hi", C.c_uint64), ("events", C.c_uint64),
-                ("kernel_ms", C.c_float), ("reserved", C.c_int32)]
+                ("kernel_ms", C.c_float), ("redone", C.c_int32)]
 
 
 class SeqOutputs(C.Structure):
     _fields_ = [("lol_hours", C.c_void_p), ("ens_fp", C.c_void_p), ("entries", C.c_void_p),
                 ("fail_count", C.c_void_p), ("group_lol", C.c_void_p), ("group", C.c_int32),
-                ("keep_on_device", C.c_int32), ("history", C.c_void_p)]
+                ("keep_on_device", C.c_int32), ("history", C.c_void_p), ("tail_hist", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class NonseqSummary(C.Structure):
@@ -139,6 +142,10 @@ def load():
     L.psra_sampler_durations.argtypes = [vp, C.c_float, vp, i64, vp, vp]
     L.psra_tail.restype = C.c_int
     L.psra_tail.argtypes = [vp, vp, i64, vp, i32, C.POINTER(TailOut), vp, i32, i64]
+    L.psra_tail_hist_export.restype = C.c_int
+    L.psra_tail_hist_export.argtypes = [vp, vp, i64, C.POINTER(i64), vp]
+    L.psra_tail_hist_import.restype = C.c_int
+    L.psra_tail_hist_import.argtypes = [vp, vp, i64, vp]
     L.psra_detailed_mc.restype = C.c_int
     L.psra_detailed_mc.argtypes = [vp, C.POINTER(DetailedSystem), vp, i32, dbl, i64, i64, u64, vp, vp, C.POINTER(C.c_float)]
     L.psra_multi_area_mc.restype = C.c_int

@@ -80,6 +80,7 @@ class SequentialIndices:
     cov_eens: float        # seqMain.m:183-186 CoV = std(ENS)/(mean*sqrt(n))
     events: int
     kernel_ms: float
+    redone: int = 0                            # chains the library replayed with the generic kernel (exact either way)
     lol_hours: Optional[np.ndarray] = None     # per-year vectors when requested
     ens: Optional[np.ndarray] = None
     entries: Optional[np.ndarray] = None
@@ -91,6 +92,34 @@ class SequentialIndices:
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _fixed_load(load_mw, scale: float, mode: str) -> np.ndarray:
+    """Hourly load in MW -> the fixed-point grid.  The reference tests `cap_avail < load` in Float64 (PSA.jl:192,253) and
+    the capacities are whole grid values here, so for a load L between two grid values the loss test is decided by
+    ceil(L): c < L  <=>  c < ceil(L).  mode:
+      "ceil"   (default) -- ceil to the grid: every loss-of-load hour of the Float64 comparison is kept exactly
+                            (LOLE / LOLF / durations unbiased); the deficit load - cap is then over-stated by less than
+                            one grid unit per loss hour (EENS bias < LOLE / fp_scale MWh per year) -- choose a finer
+                            fp_scale to shrink it, or feed loads that are whole grid values (no change at all);
+      "rint"             -- round to nearest: EENS unbiased to first order, but loss hours with a load within half a
+                            grid unit above a capacity level are missed (RTS-79: LOLE 9.3677 instead of 9.3941 h/yr);
+      "strict"           -- raise unless the load is representable exactly."""
+    v = np.asarray(load_mw, dtype=np.float64) * scale
+    r = np.rint(v)
+    if mode == "strict":
+        if not (np.abs(v - r) <= 1e-6).all():
+            raise ValueError(f"load is not representable at fp_scale={scale}; choose a finer scale")
+    elif mode == "ceil":
+        # at fp_scale = 1 this is the Float64 comparison itself (a load one ulp above a whole number does lose load at
+        # that capacity); a scale factor adds its own rounding error, forgiven up to a few ulps
+        tol = 0.0 if scale == 1.0 else 8.0 * np.finfo(np.float64).eps * np.abs(v)
+        r = np.where(np.abs(v - r) <= tol, r, np.ceil(v))
+    elif mode != "rint":
+        raise ValueError("load mode must be 'ceil', 'rint' or 'strict'")
+    if r.size and (r.min() < 0 or r.max() > 0x3fffffff):
+        raise ValueError(f"load out of the int32 fixed-point range at fp_scale={scale}")
+    return np.ascontiguousarray(r, dtype=np.int32)
 
 
 def _fixed(values, scale: float, what: str, strict: bool) -> np.ndarray:
@@ -109,15 +138,18 @@ class Engine:
 
     def __init__(self, device: int = 0, warps_per_block: int = 0, seg_hours: int = 0, blocks_per_sm: int = 0,
                  force_generic: bool = False, unpacked_words: bool = False, force_team: bool = False,
-                 static_blocks: int = 0):
+                 static_blocks: int = 0, ngpus: int = 1, ev_cap: int = 0, tail_bins: int = 0):
+        """ngpus > 1: the handle spans the devices device .. device + ngpus - 1 of this process; the Monte Carlo calls
+        shard their year / sample range over them and combine the integers with NCCL inside the library."""
         self._L = _lib.load()
         self._h = C.c_void_p()
         cfg = _lib.Config(device=device, warps_per_block=warps_per_block, seg_hours=seg_hours,
-                          blocks_per_sm=blocks_per_sm)
+                          blocks_per_sm=blocks_per_sm, ngpus=int(ngpus), ev_cap=int(ev_cap), tail_bins=int(tail_bins))
         cfg.reserved[0] = 1 if force_generic else 0
-        cfg.reserved[1] = 1 if unpacked_words else 0
+        cfg.reserved[1] = int(unpacked_words)      # 1: unpacked cross-check variants; 2: force seq_wide.cu's packed timeline
         cfg.reserved[2] = 1 if force_team else 0
         cfg.reserved[3] = int(static_blocks)
+        self.ngpus = max(1, int(ngpus))
         rc = self._L.psra_create(C.byref(self._h), C.byref(cfg))
         if rc != 0:
             msg = self._L.psra_last_error(self._h).decode() if self._h else "psra_create failed"
@@ -165,7 +197,7 @@ class Engine:
         out = (C.c_uint64 * 16)()
         self._check(self._L.psra_last_counters(self._h, out, 16))
         v = list(out)
-        return dict(waves=v[9], jobs=v[10], ahead_jobs=v[11], resolved_runs=v[12], pend_max=v[13], events=v[7])
+        return dict(waves=v[9], jobs=v[10], ahead_jobs=v[11], resolved_runs=v[12], pend_max=v[13], events=v[7], redone=v[14])
 
     # ---- system data
     def set_system(self, capacity_mw, mttf_h, mttr_h, fp_scale: float = 1.0, strict: bool = True):
@@ -176,21 +208,23 @@ class Engine:
         self.fp_scale = float(fp_scale)
         self.n_units = len(cap)
 
-    def set_load(self, load_mw, strict: bool = False):
-        load = _fixed(load_mw, self.fp_scale, "load", strict)
+    def set_load(self, load_mw, strict: bool = False, mode: Optional[str] = None):
+        """mode: see _fixed_load ("ceil" keeps the Float64 loss test exact; default).  strict=True == mode="strict"."""
+        load = _fixed_load(load_mw, self.fp_scale, mode or ("strict" if strict else "ceil"))
         self._check(self._L.psra_set_load(self._h, _ptr(load), len(load)))
         self.n_hours = len(load)
         return load
 
     def set_generators(self, gens: Sequence[Generator], load: LoadModel, fp_scale: float = 1.0,
-                       strict: bool = True):
+                       strict: bool = True, load_mode: str = "ceil"):
         self.set_system([g.capacity for g in gens], [g.mttf for g in gens], [g.mttr for g in gens],
                         fp_scale, strict)
-        return self.set_load(load.hourly_load, strict=False)
+        return self.set_load(load.hourly_load, mode=load_mode)
 
     # ---- sequential MC
-    def _seq_outputs(self, n, per_year, fail_count, group, keep, history=False):
+    def _seq_outputs(self, n, per_year, fail_count, group, keep, history=False, tail_hist=False):
         o = _lib.SeqOutputs()
+        o.tail_hist = 1 if tail_hist else 0
         bufs = {}
         if history:
             bufs["history"] = np.empty(n // history, dtype=np.float64)     # fully overwritten by the library
@@ -215,6 +249,7 @@ class Engine:
                    sum_ens_sq=(s.sum_ens_sq_hi << 64) | s.sum_ens_sq_lo, events=s.events)
         r = indices_from_raw(raw, self.fp_scale)
         r.kernel_ms = float(s.kernel_ms)
+        r.redone = int(s.redone)
         sc = self.fp_scale
         r.lol_hours = bufs.get("lol_hours")
         r.ens = None if "ens" not in bufs else bufs["ens"] / sc
@@ -228,10 +263,12 @@ class Engine:
 
     def seq_mc(self, years: int, seed: int = 42, year0: int = 0, init_mode: int = INIT_STATIONARY,
                years_per_chain: int = 1, per_year: bool = False, fail_count: bool = False,
-               group: int = 0, keep_on_device: bool = False, history: int = 0) -> SequentialIndices:
+               group: int = 0, keep_on_device: bool = False, history: int = 0, tail_hist: bool = False) -> SequentialIndices:
+        """tail_hist=True: the kernel also counts the years by their ENS (1 fixed-point MWh bins) on the device;
+        Engine.tail() then gives exact VaR / CVaR without any per-year vector."""
         if history and group and history != group:
             raise ValueError("history and group must use the same cadence")
-        o, bufs = self._seq_outputs(years, per_year, fail_count, group, keep_on_device, history)
+        o, bufs = self._seq_outputs(years, per_year, fail_count, group, keep_on_device, history, tail_hist)
         s = _lib.SeqSummary()
         self._check(self._L.psra_seq_mc(self._h, year0, years, seed, init_mode, years_per_chain,
                                         C.byref(o), C.byref(s)))
@@ -441,7 +478,7 @@ class Engine:
                       year0: int = 0, init_mode: int = INIT_STATIONARY, per_year: bool = False, fp_scale: float = 1.0,
                       strict: bool = True):
         """psra_multi_area_mc: loads[n_areas][H], topology[n_areas][n_areas] (System.topology_matrix).
-        Replaces the engine's unit table.  Returns dict(lole[A], eue[A], raw sums, optional per-year arrays)."""
+        Leaves the engine's own system / load alone.  Returns dict(lole[A], eue[A], raw sums, optional per-year arrays)."""
         ua = np.ascontiguousarray(unit_area, dtype=np.int32)
         capi = _fixed(cap, fp_scale, "capacity", strict)
         mf = np.ascontiguousarray(mttf, dtype=np.float64); mr = np.ascontiguousarray(mttr, dtype=np.float64)
@@ -449,7 +486,7 @@ class Engine:
         if ld.ndim != 2:
             raise ValueError("loads must be [n_areas][n_hours]")
         A, H = ld.shape
-        ldi = _fixed(ld.reshape(-1), fp_scale, "load", False)      # loads are rounded to the grid, like set_generators
+        ldi = _fixed_load(ld.reshape(-1), fp_scale, "ceil")        # like set_generators: the Float64 loss test stays exact
         topo = _fixed(np.asarray(topology, dtype=np.float64).reshape(-1), fp_scale, "tie capacity", strict)
         if len(topo) != A * A or not (len(ua) == len(capi) == len(mf) == len(mr)):
             raise ValueError("inconsistent multi-area system arrays")
@@ -463,7 +500,8 @@ class Engine:
         sm = _lib.AreaSummary()
         self._check(self._L.psra_multi_area_mc(self._h, C.byref(sys), int(policy), year0, years, seed, init_mode,
                                                C.byref(o), C.byref(sm)))
-        self.fp_scale = fp_scale
+        # the library leaves the handle's single-area system / load untouched (the call uses private tables), so the
+        # engine's unit count, hour count and scale still describe what set_system / set_load uploaded
         n = max(years, 1)
         sl = np.array(sm.sum_lol_hours[:A], dtype=np.int64); se = np.array(sm.sum_ens_fp[:A], dtype=np.int64)
         return dict(lole=sl / n, eue=se / n / fp_scale, sum_lol_hours=sl, sum_ens_fp=se, events=int(sm.events),
@@ -487,6 +525,26 @@ class Engine:
         res = [dict(alpha=float(a), var=o.var / sc, cvar=o.cvar / sc, n_tail=o.n_tail, x_lo=o.x_lo, x_hi=o.x_hi)
                for a, o in zip(al, outs)]
         return (res, hist[:n_bins]) if n_bins else res
+
+
+def _engine_tail_hist_export(self, max_bins: int = 1 << 24):
+    """ENS histogram of the last seq_mc(tail_hist=True) as (counts[int64], meta[4] = years, years with loss, years beyond
+    the range, their ENS sum): what ranks exchange (element-wise sum) for a cross-rank VaR / CVaR."""
+    counts = np.zeros(max_bins, dtype=np.int64)
+    meta = np.zeros(4, dtype=np.int64)
+    n = C.c_int64()
+    self._check(self._L.psra_tail_hist_export(self._h, _ptr(counts), max_bins, C.byref(n), _ptr(meta)))
+    return counts[:n.value].copy(), meta
+
+
+def _engine_tail_hist_import(self, counts, meta):
+    c = np.ascontiguousarray(counts, dtype=np.int64)
+    m = np.ascontiguousarray(meta, dtype=np.int64)
+    self._check(self._L.psra_tail_hist_import(self._h, _ptr(c) if c.size else None, c.size, _ptr(m)))
+
+
+Engine.tail_hist_export = _engine_tail_hist_export
+Engine.tail_hist_import = _engine_tail_hist_import
 
 
 def indices_from_raw(raw: dict, fp_scale: float = 1.0) -> SequentialIndices:
@@ -546,7 +604,12 @@ def run_sequential_mc(gens: Sequence[Generator], load: LoadModel, years: int, se
                       fp_scale: float = 1.0, init_mode: int = INIT_STATIONARY, years_per_chain: int = 1,
                       year0: int = 0, engine: Optional[Engine] = None, details: bool = False):
     """PSA.jl:214-269: history = running mean of LOLE every 10 years (:263-265).
-    year0 selects the shard [year0, year0+years) of the experiment `seed` (multi-GPU / resume);
+    Default semantics differ from the reference in one documented way: the reference runs
+    ONE chain that starts all-up and carries the unit states across all years (PSA.jl:223-224); the default here is
+    independent years from the stationary law (init_mode=INIT_STATIONARY, years_per_chain=1) -- the same expectation
+    without the all-up start bias, and what lets years shard over GPUs.  init_mode=INIT_ALL_UP, years_per_chain=years
+    is the reference's chain.  An engine created with ngpus=G shards the years over G devices inside the library.
+    year0 selects the shard [year0, year0+years) of the experiment `seed` (multi-process sharding / resume);
     details=True additionally returns the SequentialIndices (LOLF, LOLD, CIs, raw accumulators)."""
     eng = engine or default_engine()
     t0 = time.time()
@@ -643,24 +706,6 @@ def run_fast_sequential_simulation(sys: System, policy: int, n_years: int, seed:
     if verbose:
         print(f"Simulation completed in {time.time() - t0:.2f} seconds.")
     return [dict(area=a.name, lole=float(r["lole"][i]), eue=float(r["eue"][i])) for i, a in enumerate(sys.areas)]
-
-
-def run_demo(n_years: int = 500, engine: Optional[Engine] = None) -> str:
-    """AdequacyAssessmentII.jl:256-290: the two-area demo system, ISOLATED vs INTERCONNECTED, and its table."""
-    gens1 = [AreaGenerator(f"G1_{i}", 400.0, 1000.0, 50.0) for i in range(1, 6)]
-    gens2 = [AreaGenerator(f"G2_{i}", 200.0, 900.0, 60.0) for i in range(1, 6)]
-    x = np.linspace(0.0, 2.0 * np.pi, 8760)
-    sysm = System([Area(1, "Area_Rich", gens1, 1000.0 + 500.0 * np.sin(x)), Area(2, "Area_Poor", gens2, 800.0 + 400.0 * np.sin(x))],
-                  [TieLine(1, 2, 200.0)])
-    res_iso = run_fast_sequential_simulation(sysm, ISOLATED, n_years, engine=engine)
-    res_int = run_fast_sequential_simulation(sysm, INTERCONNECTED, n_years, engine=engine)
-    lines = ["", "=== FINAL COMPARISON (FAST METHOD) ===", "Policy          | Area       | LOLE (h/yr) | EUE (MWh/yr)", "-" * 60]
-    lines += ["ISOLATED        | %-10s | %10.2f  | %10.2f" % (r["area"], r["lole"], r["eue"]) for r in res_iso]
-    lines.append("-" * 60)
-    lines += ["INTERCONNECTED  | %-10s | %10.2f  | %10.2f" % (r["area"], r["lole"], r["eue"]) for r in res_int]
-    text = "\n".join(lines)
-    print(text)
-    return text
 
 
 def evaluate_risk(cum_prob, cum_freq, peak_load: float, installed_cap: float):

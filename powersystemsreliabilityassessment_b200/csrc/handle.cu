@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(HIST_THREADS) history_partial_kernel(const lon
 
 __global__ void __launch_bounds__(HIST_THREADS) history_scan_kernel(const long long *__restrict__ g, long long n, long long chunk,
                                                                     int block0, const long long *__restrict__ partial, int group,
-                                                                    double *__restrict__ out)
+                                                                    long long carry0, long long idx0, double *__restrict__ out)
 {
     __shared__ long long sh[HIST_THREADS / 32];
     __shared__ long long wtot[HIST_THREADS / 32];
     const int blk = block0 + (int)blockIdx.x;
     long long carry = 0;
     for (int b = threadIdx.x; b < blk; b += HIST_THREADS) carry += partial[b];
-    carry = hist_block_sum(carry, sh);
+    carry = hist_block_sum(carry, sh) + carry0;          // carry0 / idx0: what lies in front of this device's range (multi-GPU)
     const long long lo = (long long)blk * chunk, hi = min(n, lo + chunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long base = lo; base < hi; base += HIST_THREADS) {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(HIST_THREADS) history_scan_kernel(const long l
         __syncthreads();
         long long before = 0, total = 0;
         for (int w = 0; w < HIST_THREADS / 32; w++) { const long long t = wtot[w]; total += t; if (w < warp) before += t; }
-        if (i < hi) out[i] = (double)(carry + before + v) / ((double)group * (double)(i + 1));
+        if (i < hi) out[i] = (double)(carry + before + v) / ((double)group * (double)(idx0 + i + 1));
         carry += total;
     }
 }
@@ -128,7 +128,7 @@ int psra_history_range(psra_handle *h, const long long *d_group, int64_t nfull, 
     double *d_hist = (double *)h->d_hist;
     long long *d_part = (long long *)(d_hist + nfull);
     history_partial_kernel<<<(unsigned)(b1 - b0), HIST_THREADS, 0, stream>>>(d_group, nfull, chunk, (int)b0, d_part);
-    history_scan_kernel<<<(unsigned)(b1 - b0), HIST_THREADS, 0, stream>>>(d_group, nfull, chunk, (int)b0, d_part, group, d_hist);
+    history_scan_kernel<<<(unsigned)(b1 - b0), HIST_THREADS, 0, stream>>>(d_group, nfull, chunk, (int)b0, d_part, group, h->hist_carry0, h->hist_idx0, d_hist);
     PSRA_CUDA(h, cudaGetLastError());
     const int64_t g0 = b0 * chunk, g1 = std::min(nfull, b1 * chunk);
     PSRA_CUDA(h, cudaMemcpyAsync(history + g0, d_hist + g0, sizeof(double) * (size_t)(g1 - g0), cudaMemcpyDeviceToHost, stream));
@@ -197,16 +197,21 @@ extern "C" int psra_create(psra_handle **out, const psra_config *cfg)
     PSRA_CUDA(h, cudaEventCreate(&h->ev0));
     PSRA_CUDA(h, cudaEventCreate(&h->ev1));
     PSRA_CUDA(h, cudaMalloc(&h->d_acc, sizeof(unsigned long long) * ACC_COUNT));
+    PSRA_CUDA(h, cudaMalloc(&h->d_redo, sizeof(unsigned long long) * (1 + 4096)));
+    PSRA_CUDA(h, cudaMalloc(&h->d_red, sizeof(unsigned long long) * 32));
+    if (h->cfg.ngpus > 1) return psra_multi_create(h);
     return PSRA_OK;
 }
 
 extern "C" void psra_destroy(psra_handle *h)
 {
     if (!h) return;
+    psra_multi_destroy(h);
     cudaSetDevice(h->device);
     void *bufs[] = {h->d_cap, h->d_mttf, h->d_mttr, h->d_for_thr, h->d_for, h->d_load, h->d_lmax,
                     h->d_load_sorted, h->d_load_suffix, h->d_acc, h->d_lol, h->d_ens, h->d_ent, h->d_fail,
-                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order, h->d_hist, h->d_lol_tab, h->d_byte_tab, h->d_wide_tab};
+                    h->d_group, h->d_scratch, h->d_scratch2, h->d_order, h->d_hist, h->d_lol_tab, h->d_byte_tab, h->d_wide_tab,
+                    h->d_redo, h->d_tail_hist, h->d_tail_work, h->d_red};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -233,7 +238,9 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     double rate = 0.0;
     for (int u = 0; u < U; u++) {
         PSRA_REQUIRE(h, cap_fp[u] >= 0, "negative capacity");
-        PSRA_REQUIRE(h, mttf_h[u] > 0 && mttr_h[u] > 0, "MTTF / MTTR must be positive");
+        // upper bound: event times are 64-bit ticks of 2^-24 h and hour indices 32 bits (a duration is < 2^56 ticks)
+        PSRA_REQUIRE(h, mttf_h[u] > 0 && mttr_h[u] > 0 && mttf_h[u] <= 1.0e8 && mttr_h[u] <= 1.0e8,
+                     "MTTF / MTTR must be positive (at most 1e8 hours)");
         total += cap_fp[u];
         if (cap_fp[u] > max_unit) max_unit = cap_fp[u];
         rate += 2.0 / (mttf_h[u] + mttr_h[u]);
@@ -285,6 +292,11 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     h->max_unit_cap = max_unit;
     h->events_per_hour = rate;
     h->tab_valid = false;
+    h->hist_years = 0;
+    for (psra_handle *p : h->peers) {                    // multi-GPU handle: every device holds the system
+        const int rc = psra_set_system(p, cap_fp, mttf_h, mttr_h, n_units);
+        if (rc) return psra_fail(h, rc, "device %d: %s", p->device, p->err);
+    }
     return PSRA_OK;
 }
 
@@ -315,5 +327,9 @@ extern "C" int psra_set_load(psra_handle *h, const int32_t *load_fp, int32_t n_h
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     h->H = H; h->Wd = Wd; h->max_load = mx;
     h->tab_valid = false;
+    for (psra_handle *p : h->peers) {
+        const int rc = psra_set_load(p, load_fp, n_hours);
+        if (rc) return psra_fail(h, rc, "device %d: %s", p->device, p->err);
+    }
     return PSRA_OK;
 }

@@ -296,14 +296,36 @@ extern "C" int psra_multi_area_mc(psra_handle *h, const psra_area_system *sys, i
     for (int i = 0; i < A * A; i++) PSRA_REQUIRE(h, sys->topology_fp[i] >= 0 && sys->topology_fp[i] <= 0x3fffffff, "tie capacity out of range");
     memset(summary, 0, sizeof(*summary));
     summary->years = nyears; summary->n_areas = A;
-    int rc = psra_set_system(h, sys->cap_fp, sys->mttf_h, sys->mttr_h, U);      // units, sampler thresholds, unit order
-    if (rc) return rc;
+    int rc = PSRA_OK;
     if (nyears == 0) return PSRA_OK;
     PSRA_CUDA(h, cudaSetDevice(h->device));
 
-    // area data: [unit_area U][load A*Hpad][lmax A*Wd][topo A*A] in one scratch buffer
-    std::vector<int32_t> buf((size_t)U + (size_t)A * Hpad + (size_t)A * Wd + (size_t)A * A, 0);
+    // private tables of this call in one scratch buffer (the handle's own system and load -- psra_set_system /
+    // psra_set_load -- stay as they are): [unit_area U][load A*Hpad][lmax A*Wd][topo A*A][cap U][mttf U][mttr U]
+    // [FOR thresholds U][unit order U]; the sampler quantities are those of psra_set_system (binary32 means,
+    // floor(FOR 2^32), units ordered by decreasing transition rate)
+    std::vector<int32_t> buf((size_t)U + (size_t)A * Hpad + (size_t)A * Wd + (size_t)A * A + 5 * (size_t)U, 0);
     int32_t *b_area = buf.data(), *b_load = b_area + U, *b_lmax = b_load + (size_t)A * Hpad, *b_topo = b_lmax + (size_t)A * Wd;
+    int32_t *b_cap = b_topo + (size_t)A * A, *b_mttf = b_cap + U, *b_mttr = b_mttf + U, *b_thr = b_mttr + U, *b_order = b_thr + U;
+    {
+        int64_t total = 0;
+        for (int u = 0; u < U; u++) {
+            PSRA_REQUIRE(h, sys->cap_fp[u] >= 0, "negative capacity");
+            PSRA_REQUIRE(h, sys->mttf_h[u] > 0 && sys->mttr_h[u] > 0 && sys->mttf_h[u] <= 1.0e8 && sys->mttr_h[u] <= 1.0e8,
+                         "MTTF / MTTR must be positive (at most 1e8 hours)");
+            total += sys->cap_fp[u];
+            b_cap[u] = sys->cap_fp[u];
+            const float mf = (float)sys->mttf_h[u], mr = (float)sys->mttr_h[u];
+            memcpy(&b_mttf[u], &mf, 4); memcpy(&b_mttr[u], &mr, 4);
+            const double lam = 1.0 / sys->mttf_h[u], mu = 1.0 / sys->mttr_h[u];      // AdequacyAssessmentII.jl:15-26 rates
+            const double t = floor(lam / (lam + mu) * 4294967296.0);
+            const uint32_t thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
+            memcpy(&b_thr[u], &thr, 4);
+            b_order[u] = u;
+        }
+        PSRA_REQUIRE(h, total <= 0x3fffffff, "installed capacity exceeds the int32 fixed-point range");
+        std::stable_sort(b_order, b_order + U, [&](int32_t x, int32_t y) { return sys->mttf_h[x] + sys->mttr_h[x] < sys->mttf_h[y] + sys->mttr_h[y]; });
+    }
     for (int u = 0; u < U; u++) b_area[u] = sys->unit_area[u];
     for (int ar = 0; ar < A; ar++)
         for (int i = 0; i < H; i++) {
@@ -321,9 +343,12 @@ extern "C" int psra_multi_area_mc(psra_handle *h, const psra_area_system *sys, i
     a.A = A; a.U = U; a.H = H; a.Wd = Wd; a.policy = policy; a.init_mode = init_mode;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
     a.year0 = year0; a.nyears = nyears;
-    a.cap = h->d_cap; a.mttf = h->d_mttf; a.mttr = h->d_mttr; a.for_thr = h->d_for_thr; a.order = h->d_order;
     a.unit_area = (const int32_t *)h->d_scratch;
     a.load = a.unit_area + U; a.lmax = a.load + (size_t)A * Hpad; a.topo = a.lmax + (size_t)A * Wd;
+    a.cap = a.topo + (size_t)A * A;
+    a.mttf = reinterpret_cast<const float *>(a.cap + U); a.mttr = a.mttf + U;
+    a.for_thr = reinterpret_cast<const uint32_t *>(a.mttr + U);
+    a.order = reinterpret_cast<const int32_t *>(a.for_thr + U);
     a.acc = h->d_acc;
     const bool want_vec = out && (out->lol_hours || out->ens_fp);
     if (want_vec) {

@@ -342,7 +342,7 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
         if (out->cap_avail) PSRA_CUDA(h, cudaMemcpyAsync(out->cap_avail, a.cap_out, cap_bytes, cudaMemcpyDeviceToHost, h->stream));
         if (out->states)    PSRA_CUDA(h, cudaMemcpyAsync(out->states, a.states, st_bytes, cudaMemcpyDeviceToHost, h->stream));
         if (out->group_lol) PSRA_CUDA(h, cudaMemcpyAsync(out->group_lol, h->d_group, sizeof(long long) * (size_t)ngroups, cudaMemcpyDeviceToHost, h->stream));
-        if (out->history) {
+        if (out->history && !h->multi_defer) {
             rc = psra_history_to_host(h, h->d_group, n / a.group, a.group, out->history);
             if (rc) return rc;
         }
@@ -360,10 +360,17 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
     return PSRA_OK;
 }
 
+int psra_run_nonseq_range(psra_handle *h, long long i0, long long n, uint64_t seed, const psra_nonseq_outputs *out,
+                          psra_nonseq_summary *summary)
+{
+    return run_nonseq(h, NS_PHILOX, nullptr, i0, n, seed, out, summary);
+}
+
 extern "C" int psra_nonseq_mc(psra_handle *h, int64_t sample0, int64_t n, uint64_t seed,
                               const psra_nonseq_outputs *out, psra_nonseq_summary *summary)
 {
     if (!h) return PSRA_E_INVALID;
+    if (!h->peers.empty()) return psra_multi_nonseq_mc(h, sample0, n, seed, out, summary);
     return run_nonseq(h, NS_PHILOX, nullptr, sample0, n, seed, out, summary);
 }
 

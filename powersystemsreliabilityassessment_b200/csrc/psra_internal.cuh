@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "psra_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -63,6 +65,18 @@ struct psra_handle {
     void *d_scratch = nullptr; size_t scratch_cap = 0;   // inputs of injected paths, tail keys
     void *d_scratch2 = nullptr; size_t scratch2_cap = 0;
     void *d_hist = nullptr; size_t hist_cap = 0;         // convergence history + its scan partials
+    unsigned long long *d_redo = nullptr;                // [1 + PSRA_REDO_CAP] redo list of the sequential sampler kernels
+    // per-year ENS histogram kept for psra_tail (tail.cu): [tail_bins + 2] counts + beyond-range {count, sum}
+    unsigned long long *d_tail_hist = nullptr; int64_t tail_bins = 0;
+    int64_t hist_years = 0, hist_years_with_loss = 0;    // > 0: the histogram of the last psra_seq_mc call is valid
+    void *d_tail_work = nullptr; size_t tail_work_cap = 0;
+    // multi-GPU handle (psra_config.ngpus > 1, multi.cu): this handle is device 0 of the set, `peers` the others
+    std::vector<psra_handle *> peers;
+    void *nccl_comms = nullptr;                          // ncclComm_t[1 + peers.size()]
+    unsigned long long *d_red = nullptr;                 // [32] small all-reduce buffer (accumulators as 32-bit-safe limbs)
+    bool multi_defer = false;    // set on the devices of a multi-GPU call: leave the per-hour counts, the group sums and the
+                                 // ENS histogram on the device (the driver all-reduces / scans them)
+    long long hist_carry0 = 0, hist_idx0 = 0;            // running-mean scan: LOL hours / groups in front of this device's range
     unsigned long long last_acc[ACC_COUNT_MAX] = {0};   // accumulators of the last MC call (diagnostics)
 };
 
@@ -92,6 +106,24 @@ int psra_history_prepare(psra_handle *h, int64_t nfull);
 int psra_history_range(psra_handle *h, const long long *d_group, int64_t nfull, int group, int64_t b0, int64_t b1,
                        double *history, cudaStream_t stream);
 int psra_history_to_host(psra_handle *h, const long long *d_group, int64_t nfull, int group, double *history);
+// (re)allocate and zero the ENS histogram for the system currently set (tail.cu)
+int psra_tail_hist_prepare(psra_handle *h);
+// index of the last non-empty bin of the device histogram + 1 (0 = empty), synchronous (tail.cu)
+int psra_tail_hist_used(psra_handle *h, int64_t *used);
+// per-hour failure counts: (re)allocate and zero d_fail (seq_mc.cu)
+int psra_seq_prepare_fail(psra_handle *h);
+// the single-device engines behind psra_seq_mc / psra_nonseq_mc (seq_mc.cu, nonseq_mc.cu)
+int psra_run_seq_range(psra_handle *h, long long chain_base, long long nchains, int ypc, int init_mode, uint64_t seed,
+                       const psra_seq_outputs *out, psra_seq_summary *summary);
+int psra_run_nonseq_range(psra_handle *h, long long i0, long long n, uint64_t seed, const psra_nonseq_outputs *out,
+                          psra_nonseq_summary *summary);
+// multi-GPU driver (multi.cu)
+int psra_multi_create(psra_handle *h);
+void psra_multi_destroy(psra_handle *h);
+int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed, int32_t init_mode, int32_t ypc,
+                      const psra_seq_outputs *out, psra_seq_summary *summary);
+int psra_multi_nonseq_mc(psra_handle *h, int64_t sample0, int64_t n, uint64_t seed, const psra_nonseq_outputs *out,
+                         psra_nonseq_summary *summary);
 
 // ------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
@@ -130,7 +162,7 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
 }
 
 // E = -ln(u) of the draw x, u = (x | 1) / 2^32 -- sampler specification v2 (the CPU checker
-// oracle_neglog_u32 spells out the same sequence): a fixed sequence of integer operations and correctly rounded
+// spells out the same sequence): a fixed sequence of integer operations and correctly rounded
 // binary32 add / fma, reproducible bit for bit on any IEEE-754 machine.
 //   w = x | 1,  lz = clz(w),  u = w / 2^32 = m * 2^-k  with  k = lz + 1 (1..32)  and  m in [1, 2) truncated to 24 bits;
 //   t = m - 1.5 (exact),  R = P7(t) ~ -ln(1.5 + t) (Horner, seven fma; minimax on [-0.5, 0.5), |error| < 2.5e-7);
@@ -142,10 +174,15 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
 // e - 159 = -k is exact; fma(-k, -LN2, R) rounds the same real number as fma(k, LN2, R).
 // 14 instructions per draw (v1, the fdlibm-style reduction to [sqrt(1/2), sqrt(2)) with a degree-9 polynomial: 21).
 #define PSRA_LN2_F 0x1.62e430p-1f
-__device__ __forceinline__ float neglog_u32(uint32_t x)
+// `one_bits` = 0x3F800000 in a register the compiler cannot see through (asm volatile("" : "+r"(one_bits)) outside the
+// hot loop): with it the mantissa of m is ONE three-input LOP3, (fw & 0x007FFFFF) | one_bits -- with two immediates
+// ptxas emits two.  The overload without it is for code that is not register-bound / not hot.
+__device__ __forceinline__ float neglog_u32(uint32_t x, uint32_t one_bits)
 {
     const uint32_t fw = __float_as_uint(__uint2float_rz(x | 1u));
-    const float t = __fadd_rn(__uint_as_float((fw & 0x007FFFFFu) | 0x3F800000u), -1.5f);
+    uint32_t mb;
+    asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(mb) : "r"(fw), "r"(one_bits));
+    const float t = __fadd_rn(__uint_as_float(mb), -1.5f);
     float p = -0x1.578b02p-7f;
     p = __fmaf_rn(p, t, 0x1.1d506cp-6f);
     p = __fmaf_rn(p, t, -0x1.a7b9fep-6f);
@@ -157,6 +194,7 @@ __device__ __forceinline__ float neglog_u32(uint32_t x)
     const float nk = __fadd_rn(__uint_as_float(__funnelshift_r(fw, 0x00258000u, 23)), -8388767.0f);   // e - 159 = -k
     return __fmaf_rn(nk, -PSRA_LN2_F, p);
 }
+__device__ __forceinline__ float neglog_u32(uint32_t x) { return neglog_u32(x, 0x3F800000u); }
 
 // duration of one draw in ticks of 2^-24 h: RN_int64(max(mean_ticks * E, 1)), mean_ticks = mean * 2^24
 __device__ __forceinline__ unsigned long long dur_ticks(float mean_ticks, uint32_t x)
@@ -215,5 +253,5 @@ __device__ __forceinline__ void atomic_add_u128(unsigned long long *lo, unsigned
 // accumulator slots in d_acc
 enum {
     ACC_LOL = 0, ACC_ENS, ACC_ENT, ACC_YWL, ACC_LOL2, ACC_ENS2_LO, ACC_ENS2_HI, ACC_EVENTS,
-    ACC_OVERFLOW, ACC_WAVES, ACC_JOBS, ACC_OPT_JOBS, ACC_FLAGGED, ACC_PEND_MAX, ACC_COUNT = 32
+    ACC_OVERFLOW, ACC_WAVES, ACC_JOBS, ACC_OPT_JOBS, ACC_FLAGGED, ACC_PEND_MAX, ACC_REDO, ACC_COUNT = 32
 };

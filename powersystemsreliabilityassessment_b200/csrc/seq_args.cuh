@@ -5,6 +5,9 @@
 
 struct SeqArgs {
     int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves, pack_shift, static_blocks;
+    int wide_pack;          // seq_wide.cu: two hours per 32-bit timeline word
+    int redo_cap;           // capacity of the redo list
+    int group_phase;        // local year 0 of this launch is year `group_phase` of its history group (replays only)
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
     const int32_t *load; const int32_t *lmax;
     const int32_t *order;   // units sorted by decreasing transition rate (seq_wide.cu work queue)
@@ -17,7 +20,34 @@ struct SeqArgs {
     uint32_t *lol; long long *ens; uint32_t *ent; uint32_t *fail;
     unsigned long long *group_lol; unsigned long long *acc;
     unsigned long long *imp;   // [U] hours with loss of load in which the unit is DOWN (seq_mc.cu only), or nullptr
+    // redo list: redo[0] = number of chains a fast kernel handed back (event list full, packed timeline checksum),
+    // redo[1 + i] = their absolute chain indices; the host replays them with the generic kernel of seq_mc.cu
+    unsigned long long *redo;
+    // per-year ENS histogram (tail risk, tail_risk.jl:168-175 / seqMain.m:287): hist[e] = number of years whose ENS is
+    // e fixed-point MWh, 1 <= e < hist_bins (years without loss of load are not entered: their number is
+    // years - years_with_loss); hist[hist_bins] / hist[hist_bins + 1] = number / ENS sum of the years beyond the range
+    unsigned long long *hist;
+    long long hist_bins;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void seq_redo_push(const SeqArgs &a, long long chain)
+{
+    const unsigned long long i = atomicAdd(&a.redo[0], 1ull);
+    if (i < (unsigned long long)a.redo_cap) a.redo[1 + i] = (unsigned long long)chain;
+}
+
+// one year with loss of load into the ENS histogram
+__device__ __forceinline__ void seq_hist_add(const SeqArgs &a, long long ens)
+{
+    if (!a.hist) return;
+    if ((unsigned long long)ens < (unsigned long long)a.hist_bins) atomicAdd(&a.hist[ens], 1ull);
+    else {
+        atomicAdd(&a.hist[a.hist_bins], 1ull);
+        atomicAdd(&a.hist[a.hist_bins + 1], (unsigned long long)ens);
+    }
+}
+#endif
 
 // duration of one sampler draw in ticks of 2^-24 h (DESIGN.md "Sampler"): mean_ticks = mean * 2^24
 // in binary32, D = max(1, RN_int64(mean_ticks * E)).  All event-time arithmetic on ticks is exact.
@@ -38,7 +68,7 @@ void seq_team_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t 
 #define SEQ_TEAM_WARPS 8
 
 // seq_wide.cu
-size_t seq_wide_smem_bytes(int Wd);
+size_t seq_wide_smem_bytes(int Wd, bool pack);
 int seq_wide_threads();
-cudaError_t seq_wide_prepare(size_t smem, int *blocks_per_sm);
+cudaError_t seq_wide_prepare(bool disc, bool pack, size_t smem, int threads, int *blocks_per_sm);
 void seq_wide_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);

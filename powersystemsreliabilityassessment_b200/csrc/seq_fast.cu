@@ -45,7 +45,7 @@
 
 struct FastWarpSmem {                  // per-warp scratch that precedes the event lists
     unsigned long long t_run[32];      // time (ticks) of the last generated event of each unit
-    unsigned long long acc[8];         // per-warp accumulators (lane 0): lol, ens, entries, years with loss, lol^2, ens^2 lo/hi
+    unsigned long long acc[8];         // per-warp accumulators (lane 0): lol, ens, entries, years with loss, lol^2, ens^2 lo/hi, state transitions
     unsigned int diag[8];              // waves, jobs, ahead jobs, flagged runs, max list depth
     unsigned char jobmap[32];
 };
@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
         for (int y = 0; y < n_ypc; y++) {
             unsigned int lolh = 0, entries = 0;
             long long ens_lane = 0;
+            bool year_bad = false;        // warp-uniform
             for (int seg = 0; seg < n_seg; seg++, ring ^= 1) {
                 const int seg_h0 = kTwo ? seg * seg_slots : 0;
                 const int seg_h1 = kTwo ? min(a.H, seg_h0 + seg_slots) : a.H;
@@ -549,8 +550,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
                 }
                 if (lane == 0) ws->diag[4] = max(ws->diag[4], (unsigned int)max(cnt_cur, cnt_nxt));
                 bool list_ok = true;
-                if (cnt_cur > ev_cap || cnt_nxt > ev_cap) {      // reported as PSRA_E_OVERFLOW: choose a shorter segment
-                    if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 3ull);
+                if (cnt_cur > ev_cap || cnt_nxt > ev_cap) {
+                    // the event list is full.  Single segment (a chain = one year): the year goes to the redo list and the
+                    // host replays it with the generic kernel; ring variant: the host repeats the whole call with the
+                    // generic kernel (the earlier years of the chain are already in the sums)
+                    if constexpr (kTwo) { if (lane == 0) atomicExch(&a.acc[ACC_OVERFLOW], 3ull); }
+                    else year_bad = true;
                     cnt_cur = min(cnt_cur, ev_cap); cnt_nxt = min(cnt_nxt, ev_cap);
                     list_ok = false;                             // the links may be garbage: do not walk the lists
                 }
@@ -669,11 +674,21 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
             long long ens = 0;
             if (lolh) ens = warp_sum_ll(ens_lane);
             const long long yi = kTwo ? cl * a.ypc + y : cl;
-            if (lane == 0) {
+            // state transitions of the year (one REDUX): a year that goes to the redo list is counted by its replay
+            {
+                const unsigned int ev_year = __reduce_add_sync(0xffffffffu, n_events);
+                n_events = 0u;
+                if (!year_bad && lane == 0) ws->acc[7] += ev_year;
+            }
+            if (year_bad) {
+                if (lane == 0) seq_redo_push(a, (long long)chain);
+                lolh = 0;
+            } else if (lane == 0) {
                 if (a.lol) a.lol[yi] = lolh;
                 if (a.ens) a.ens[yi] = ens;
                 if (a.ent) a.ent[yi] = entries;
                 if (a.group_lol && lolh) atomicAdd(&a.group_lol[yi / a.group], (unsigned long long)lolh);
+                if (lolh) seq_hist_add(a, ens);
             }
             if (lolh && lane == 0) {             // a year without loss of load adds nothing (ENS and entries are 0 as well)
                 ws->acc[0] += lolh; ws->acc[1] += (unsigned long long)ens; ws->acc[2] += entries;
@@ -689,10 +704,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS(kTwo), 1) seq_fast_kernel(con
         __syncwarp();
     }
 
-    unsigned long long ev = n_events;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) ev += __shfl_xor_sync(0xffffffffu, ev, d);
     if (lane == 0) {
+        const unsigned long long ev = ws->acc[7];
         if (ws->acc[0]) atomicAdd(&a.acc[ACC_LOL], ws->acc[0]);
         if (ws->acc[1]) atomicAdd(&a.acc[ACC_ENS], ws->acc[1]);
         if (ws->acc[2]) atomicAdd(&a.acc[ACC_ENT], ws->acc[2]);

@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
                 if (a.lol) a.lol[yi] = lolh;
                 if (a.ens) a.ens[yi] = ens;
                 if (a.ent) a.ent[yi] = entries;
-                if (a.group_lol && lolh) atomicAdd(&a.group_lol[yi / a.group], (unsigned long long)lolh);
+                if (a.group_lol && lolh) atomicAdd(&a.group_lol[(yi + a.group_phase) / a.group], (unsigned long long)lolh);
+                if (lolh) seq_hist_add(a, ens);
             }
             acc_lol += lolh; acc_ens += ens; acc_ent += entries;
             acc_ywl += lolh ? 1 : 0;
@@ -351,6 +352,48 @@ __global__ void __launch_bounds__(512, 1) seq_mc_kernel(const SeqArgs a)
 }
 
 // ------------------------------------------------------------------------------- host side
+#define PSRA_REDO_CAP 4096
+
+// launch geometry of the generic kernel of this file (injected durations, systems the sampler kernels do not take,
+// replays of the redo list)
+struct GenericGeom { int seg_words, nseg, persist, wpb; size_t smem; };
+
+static GenericGeom generic_geom(const psra_handle *h, int ypc, bool want_imp, int wpb_cfg)
+{
+    GenericGeom g{};
+    const bool one_unit = h->U <= 32;
+    g.seg_words = h->Wd;
+    if (one_unit) {
+        if (h->cfg.seg_hours > 0) g.seg_words = std::max(1, std::min(h->Wd, (h->cfg.seg_hours + 31) / 32));
+        else g.seg_words = std::max(1, std::min(h->Wd, (1120 + 31) / 32));
+    }
+    g.nseg = (h->Wd + g.seg_words - 1) / g.seg_words;
+    g.persist = (!one_unit && (ypc > 1 || g.nseg > 1)) ? 1 : 0;
+    auto smem_for = [&](int w) -> size_t {
+        size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
+        b += (size_t)w * (sizeof(int32_t) * (size_t)g.seg_words * 32 + sizeof(uint32_t) * (size_t)g.seg_words);
+        if (g.persist) b += 8 + (size_t)w * h->U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
+        if (want_imp) b += sizeof(uint32_t) * (size_t)w * g.seg_words;       // loss-of-load bitmaps
+        return b;
+    };
+    g.wpb = std::max(1, std::min(16, wpb_cfg > 0 ? wpb_cfg : 16));
+    while (g.wpb > 1 && smem_for(g.wpb) > h->smem_optin) g.wpb--;
+    g.smem = smem_for(g.wpb);
+    return g;
+}
+
+int psra_seq_prepare_fail(psra_handle *h)
+{
+    if (h->fail_cap < h->Wd * 32) {
+        if (h->d_fail) cudaFree(h->d_fail);
+        h->d_fail = nullptr; h->fail_cap = 0;
+        PSRA_CUDA(h, cudaMalloc(&h->d_fail, sizeof(uint32_t) * (size_t)h->Wd * 32));
+        h->fail_cap = h->Wd * 32;
+    }
+    PSRA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(uint32_t) * (size_t)h->Wd * 32, h->stream));
+    return PSRA_OK;
+}
+
 static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, long long chain_base,
                    long long nchains, int ypc, int init_mode, uint64_t seed, const psra_seq_outputs *out,
                    psra_seq_summary *summary, uint64_t *imp_out = nullptr)
@@ -364,6 +407,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     memset(summary, 0, sizeof(*summary));
     const long long nyears = nchains * ypc;
     summary->years = nyears;
+    h->kept_n = 0;
+    h->hist_years = 0;
     if (nyears == 0) return PSRA_OK;
 
     const bool one_unit = h->U <= 32;
@@ -387,8 +432,10 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     a.chain_base = chain_base; a.nchains = nchains;
     a.acc = h->d_acc;
     a.load16 = load16 ? 1 : 0;
+    a.redo = h->d_redo; a.redo_cap = PSRA_REDO_CAP;
 
     // launch geometry: segment length and warps per block under the shared-memory budget
+    const GenericGeom gg = generic_geom(h, ypc, imp_out != nullptr, h->cfg.warps_per_block);
     int seg_words = h->Wd;
     if (team) {
         // whole year in one segment when its int32 timeline stays below 40 KB, else 1760-hour segments
@@ -396,31 +443,32 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         seg_words = std::max(1, std::min(h->Wd, (seg_hours + 31) / 32));
     }
     // seq_fast.cu: event lists sized 1.75x the expected transitions of a segment (+ initial draws + slack:
-    // > 15 standard deviations for RTS-79; an overflow is reported as PSRA_E_OVERFLOW, never silent);
+    // > 15 standard deviations for RTS-79; a chain whose list overflows goes to the redo list);
     // by default the whole year is one segment unless that list would exceed 2048 entries
     auto ev_cap_for = [&](int sw) -> int {
+        if (h->cfg.ev_cap > 0) return (std::max(256, h->cfg.ev_cap) + 31) & ~31;     // cross-checks of the redo path
         const double e = h->events_per_hour * sw * 32.0 + h->U;
         const long long c = std::max(512ll, (long long)(1.75 * e) + 64);     // >= 1 static block + a few waves of 128 slots
         return (int)((c + 31) & ~31ll);
     };
     if (one_unit) {
-        if (h->cfg.seg_hours > 0) seg_words = std::max(1, std::min(h->Wd, (h->cfg.seg_hours + 31) / 32));
-        else if (!fast) seg_words = std::max(1, std::min(h->Wd, (1120 + 31) / 32));
+        if (!fast) seg_words = gg.seg_words;
+        else if (h->cfg.seg_hours > 0) seg_words = std::max(1, std::min(h->Wd, (h->cfg.seg_hours + 31) / 32));
         // event entries hold an 11-bit list link and a 14-bit hour: bound the list and the segment length
         if (fast) { while (seg_words > 1 && (ev_cap_for(seg_words) > 2016 || seg_words > 512)) seg_words = (seg_words + 1) / 2; }
     }
     a.seg_words = seg_words;
     a.nseg = (h->Wd + seg_words - 1) / seg_words;
-    a.persist = (!one_unit && !team && (ypc > 1 || a.nseg > 1)) ? 1 : 0;
+    a.persist = (!one_unit && !team) ? gg.persist : 0;
     a.pend_cap = seq_team_pend_cap(h->U);
     a.two_halves = (a.nseg > 1 || ypc > 1) ? 1 : 0;
     a.ev_cap = ev_cap_for(seg_words);
     // seq_fast.cu single-segment mode: the word's sum and negative sum share one int32 (sum + 2^K * neg) when
     // |sum| <= installed capacity < 2^(K-1) and neg > -2^(31-K).  A list of ev_cap entries holds at most
     // (ev_cap + U) / 2 + 1 down events (the events of a unit alternate), so the bound below makes a silent
-    // overflow impossible: the list overflow (PSRA_E_OVERFLOW) would trigger first.
+    // overflow impossible: the list overflow (redo list) would trigger first.
     a.pack_shift = 0;
-    if (fast && !a.two_halves && !h->cfg.reserved[1]) {
+    if (fast && !a.two_halves && h->cfg.reserved[1] != 1) {
         int K = 2;
         while ((1ll << (K - 1)) <= h->total_cap) K++;
         const long long worst = ((long long)(a.ev_cap + h->U) / 2 + 1) * (long long)h->max_unit_cap;
@@ -428,6 +476,15 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     }
     if (fast && a.ev_cap > 2016)
         return psra_fail(h, PSRA_E_INVALID, "unit transition rate too high for the sampler kernel (%d events per 32-hour word)", a.ev_cap);
+    // seq_wide.cu: two hours per timeline word (int16 halves) when a single hour cannot plausibly move the capacity
+    // by 2^14 fixed-point units -- at least 8 + 4 x (expected events per hour) same-direction events of the largest
+    // unit would have to meet in one hour.  A year in which an hour's net change does leave +-2^14 is caught by the
+    // kernel (range test of every half, end-of-year checksum) and replayed with the int32 timeline.
+    // psra_config.reserved[1]: 1 = never, 2 = always (cross-checks of the redo path)
+    a.wide_pack = 0;
+    if (wide && h->cfg.reserved[1] != 1 && h->max_unit_cap > 0 &&
+        (h->cfg.reserved[1] == 2 || 16384.0 / (double)h->max_unit_cap >= 8.0 + 4.0 * h->events_per_hour))
+        a.wide_pack = 1;
     // seq_fast.cu single-segment mode: the first blocks of every unit are generated lane = unit without any scheduling.
     // Their number: about 0.7 x the mean demand E[blocks] = (1 + 2 H / (MTTF + MTTR) + 1) / 4 per unit (3 for RTS-79;
     // a simulation of the scheduler puts the optimum of cost = 250 static + 425 per wave there), at least 1
@@ -444,24 +501,21 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads(a.two_halves != 0) / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
         if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16, a.pack_shift != 0);
-        if (wide) return seq_wide_smem_bytes(h->Wd);
+        if (wide) return seq_wide_smem_bytes(h->Wd, a.wide_pack != 0);
         if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words, a.two_halves != 0);
-        size_t b = sizeof(int32_t) * ((size_t)h->Wd * 32 + h->Wd);
-        b += (size_t)w * (sizeof(int32_t) * (size_t)seg_words * 32 + sizeof(uint32_t) * (size_t)seg_words);
-        if (a.persist) b += 8 + (size_t)w * a.U * (sizeof(double) + sizeof(int) + sizeof(uint32_t));
-        if (imp_out) b += sizeof(uint32_t) * (size_t)w * seg_words;       // loss-of-load bitmaps
-        return b;
+        return gg.smem;
     };
     if (team) {
         wpb = SEQ_TEAM_WARPS;
         if (wide) {
             // block size of seq_wide.cu: 4 warps measured best from 64 to 1024 units (scripts/sweep_wide_units.py: +10-18 %
-            // over 6 warps at 96-320 units, equal at 1024; 5 blocks per SM either way); psra_config.warps_per_block overrides
+            // over 6 warps at 96-320 units, equal at 1024); psra_config.warps_per_block overrides (at most 4)
             const int wmax = seq_wide_threads() / 32;
             wpb = h->cfg.warps_per_block > 0 ? std::min(wmax, h->cfg.warps_per_block) : std::min(wmax, 4);
         }
     }
-    while (wpb > 1 && smem_for(wpb) > h->smem_optin) wpb--;
+    if (!fast && !team) wpb = gg.wpb;
+    while (fast && wpb > 1 && smem_for(wpb) > h->smem_optin) wpb--;
     const size_t smem = smem_for(wpb);
     if (smem > h->smem_optin)
         return psra_fail(h, PSRA_E_INVALID, "system too large for the shared-memory timeline (%zu B needed, %zu B available)",
@@ -481,16 +535,15 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         if (rc) return rc;
         a.lol = h->d_lol; a.ens = (long long *)h->d_ens; a.ent = h->d_ent;
     }
-    h->kept_n = 0;
     if (out && out->fail_count) {
-        if (h->fail_cap < h->Wd * 32) {
-            if (h->d_fail) cudaFree(h->d_fail);
-            h->d_fail = nullptr; h->fail_cap = 0;
-            PSRA_CUDA(h, cudaMalloc(&h->d_fail, sizeof(uint32_t) * (size_t)h->Wd * 32));
-            h->fail_cap = h->Wd * 32;
-        }
-        PSRA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(uint32_t) * (size_t)h->Wd * 32, h->stream));
+        int rc = psra_seq_prepare_fail(h);
+        if (rc) return rc;
         a.fail = h->d_fail;
+    }
+    if (out && out->tail_hist) {
+        int rc = psra_tail_hist_prepare(h);
+        if (rc) return rc;
+        a.hist = (unsigned long long *)h->d_tail_hist; a.hist_bins = h->tail_bins;
     }
     long long ngroups = 0;
     if (out && (out->group_lol || out->history)) {
@@ -509,6 +562,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         a.group = 1;
     }
     PSRA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * ACC_COUNT, h->stream));
+    PSRA_CUDA(h, cudaMemsetAsync(h->d_redo, 0, sizeof(unsigned long long), h->stream));
     if (imp_out) {
         int rc = psra_reserve(h, &h->d_scratch2, &h->scratch2_cap, sizeof(unsigned long long) * (size_t)h->U);
         if (rc) return rc;
@@ -523,7 +577,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (fast) {
         PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, a.two_halves != 0, a.pack_shift != 0, smem, wpb * 32, &bps));
     } else if (wide) {
-        PSRA_CUDA(h, seq_wide_prepare(smem, &bps));
+        PSRA_CUDA(h, seq_wide_prepare(a.disc != 0, a.wide_pack != 0, smem, wpb * 32, &bps));
     } else if (team) {
         PSRA_CUDA(h, seq_team_prepare(smem, &bps));
     } else {
@@ -540,7 +594,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     // up to PSRA_MAX_CHUNKS launches whose group ranges are whole history-scan blocks: the scan and the read-back
     // of a finished range run on stream2 while the next launch computes (the history is 8 B per `group` years --
     // 8 MB for 10^7 RTS-79 years -- and would otherwise be a serial tail of the call).
-    const int64_t nfull = (out && out->history) ? nyears / a.group : 0;
+    const bool defer = h->multi_defer;     // device of a multi-GPU call: history, failure counts and histogram stay here
+    const int64_t nfull = (out && out->history && !defer) ? nyears / a.group : 0;
     int nlaunch = 1;
     long long chunk_chains = nchains;
     int64_t hblock = 0, hblocks_per_launch = 0;
@@ -551,10 +606,10 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         const int64_t hblocks = (nfull + hblock - 1) / hblock;
         // a launch must cover whole scan blocks: hblock groups = hblock * group years = whole chains
         if (!injected && nyears >= (1ll << 20) && (hblock * a.group) % ypc == 0 && hblocks >= 2 * PSRA_MAX_CHUNKS) {
-            nlaunch = PSRA_MAX_CHUNKS;
-            hblocks_per_launch = (hblocks + nlaunch - 1) / nlaunch;
+            hblocks_per_launch = (hblocks + PSRA_MAX_CHUNKS - 1) / PSRA_MAX_CHUNKS;
             chunk_chains = hblocks_per_launch * hblock * a.group / ypc;
-            nlaunch = (int)((nchains + chunk_chains - 1) / chunk_chains);
+            // the last launch also takes the years behind the last full group (nyears % group of them)
+            nlaunch = (int)std::min<long long>(PSRA_MAX_CHUNKS, (nchains + chunk_chains - 1) / chunk_chains);
         }
     }
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -562,7 +617,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         SeqArgs b = a;
         const long long c0 = (long long)c * chunk_chains;
         b.chain_base = a.chain_base + c0;
-        b.nchains = std::min(chunk_chains, nchains - c0);
+        b.nchains = (c == nlaunch - 1) ? nchains - c0 : chunk_chains;
         const long long y0 = c0 * ypc;
         if (a.lol) b.lol = a.lol + y0;
         if (a.ens) b.ens = a.ens + y0;
@@ -581,12 +636,61 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));
 
     unsigned long long acc[ACC_COUNT];
+    unsigned long long n_redo = 0;
     if (nlaunch > 1) {
         // scan + read back the history range of every launch as soon as that launch has finished
         for (int c = 0; c < nlaunch; c++) {
             PSRA_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_chunk[c], 0));
-            int rc = psra_history_range(h, h->d_group, nfull, a.group, c * hblocks_per_launch, (c + 1) * hblocks_per_launch,
-                                        out->history, h->stream2);
+            int rc = psra_history_range(h, h->d_group, nfull, a.group, c * hblocks_per_launch,
+                                        c == nlaunch - 1 ? INT64_MAX / 2 : (c + 1) * hblocks_per_launch, out->history, h->stream2);
+            if (rc) return rc;
+        }
+    }
+    // chains the sampler kernels handed back (event list of seq_fast.cu full, checksum of seq_wide.cu's packed timeline):
+    // replay each with a kernel that has no such limit, into the same accumulators and output slots.  Rare by
+    // construction (see ev_cap_for / wide_pack above), so one small launch per chain is fine.
+    PSRA_CUDA(h, cudaMemcpyAsync(&n_redo, h->d_redo, sizeof(n_redo), cudaMemcpyDeviceToHost, h->stream));
+    PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (n_redo > PSRA_REDO_CAP)
+        return psra_fail(h, PSRA_E_OVERFLOW, "%llu chains overflowed the fast sequential kernel (redo list holds %d): "
+                         "set a shorter psra_config.seg_hours", n_redo, PSRA_REDO_CAP);
+    if (n_redo > 0) {
+        std::vector<unsigned long long> list((size_t)n_redo);
+        PSRA_CUDA(h, cudaMemcpy(list.data(), h->d_redo + 1, sizeof(unsigned long long) * (size_t)n_redo, cudaMemcpyDeviceToHost));
+        SeqArgs b = a;
+        b.redo = nullptr;
+        size_t smem_r = 0; int threads_r = 0;
+        if (wide) {
+            b.wide_pack = 0;
+            smem_r = seq_wide_smem_bytes(h->Wd, false); threads_r = wpb * 32;
+            int dummy = 0;
+            PSRA_CUDA(h, seq_wide_prepare(b.disc != 0, false, smem_r, threads_r, &dummy));
+        } else {
+            b.seg_words = gg.seg_words; b.nseg = gg.nseg; b.persist = gg.persist;
+            smem_r = gg.smem; threads_r = 32;
+            const GenericGeom g1 = generic_geom(h, ypc, false, 1);
+            smem_r = g1.smem;
+            PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+        }
+        for (unsigned long long i = 0; i < n_redo; i++) {
+            const long long cl = (long long)list[(size_t)i] - a.chain_base;
+            if (cl < 0 || cl >= nchains) return psra_fail(h, PSRA_E_CUDA, "internal error: redo list entry out of range");
+            SeqArgs r = b;
+            r.chain_base = a.chain_base + cl; r.nchains = 1;
+            const long long y0 = cl * ypc;
+            if (a.lol) r.lol = a.lol + y0;
+            if (a.ens) r.ens = a.ens + y0;
+            if (a.ent) r.ent = a.ent + y0;
+            if (a.group_lol) r.group_lol = a.group_lol + y0 / a.group;
+            // group_lol is indexed by (local year) / group: keep the phase of the year inside its group
+            r.group_phase = (int)(y0 % a.group);
+            if (wide) seq_wide_launch(r, 1u, threads_r, smem_r, h->stream);
+            else kern<<<1u, threads_r, smem_r, h->stream>>>(r);
+            PSRA_CUDA(h, cudaGetLastError());
+        }
+        if (nfull > 0 && nlaunch > 1) {      // the overlapped history scan ran before the replays: scan again
+            PSRA_CUDA(h, cudaStreamSynchronize(h->stream2));
+            int rc = psra_history_range(h, h->d_group, nfull, a.group, 0, INT64_MAX / 2, out->history, h->stream);
             if (rc) return rc;
         }
     }
@@ -596,7 +700,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         if (out->lol_hours) PSRA_CUDA(h, cudaMemcpyAsync(out->lol_hours, h->d_lol, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
         if (out->ens_fp)    PSRA_CUDA(h, cudaMemcpyAsync(out->ens_fp, h->d_ens, sizeof(int64_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
         if (out->entries)   PSRA_CUDA(h, cudaMemcpyAsync(out->entries, h->d_ent, sizeof(uint32_t) * (size_t)nyears, cudaMemcpyDeviceToHost, h->stream));
-        if (out->fail_count) PSRA_CUDA(h, cudaMemcpyAsync(out->fail_count, h->d_fail, sizeof(uint32_t) * (size_t)h->H, cudaMemcpyDeviceToHost, h->stream));
+        if (out->fail_count && !defer) PSRA_CUDA(h, cudaMemcpyAsync(out->fail_count, h->d_fail, sizeof(uint32_t) * (size_t)h->H, cudaMemcpyDeviceToHost, h->stream));
         if (out->group_lol) PSRA_CUDA(h, cudaMemcpyAsync(out->group_lol, h->d_group, sizeof(long long) * (size_t)ngroups, cudaMemcpyDeviceToHost, h->stream));
         if (nfull > 0 && nlaunch == 1) {
             int rc = psra_history_range(h, h->d_group, nfull, a.group, 0, INT64_MAX / 2, out->history, h->stream);
@@ -616,15 +720,34 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     summary->sum_ens_sq_lo = acc[ACC_ENS2_LO];
     summary->sum_ens_sq_hi = acc[ACC_ENS2_HI];
     summary->events = acc[ACC_EVENTS];
+    summary->redone = (int32_t)n_redo;
     memcpy(h->last_acc, acc, sizeof(acc));
+    h->last_acc[ACC_REDO] = n_redo;
     if (want_vec && out->keep_on_device) h->kept_n = nyears;
-    if (acc[ACC_OVERFLOW] == 3ull)
+    if (a.hist) { h->hist_years = nyears; h->hist_years_with_loss = (int64_t)acc[ACC_YWL]; }
+    if (acc[ACC_OVERFLOW] == 3ull) {
+        // seq_fast.cu, ring variant (several segments per year or multi-year chains): a segment's event list was full.
+        // Never fail for that (the reference loop cannot, PSA.jl:230-266): repeat the call with the generic kernel.
+        if (fast && !h->cfg.reserved[0]) {
+            h->cfg.reserved[0] = 1;
+            const int rc = run_seq(h, injected, h_dur, K, chain_base, nchains, ypc, init_mode, seed, out, summary, imp_out);
+            h->cfg.reserved[0] = 0;
+            if (rc == PSRA_OK) { summary->redone = (int32_t)std::min<long long>(nchains, 0x7fffffff); h->last_acc[ACC_REDO] = (unsigned long long)nchains; }
+            return rc;
+        }
         return psra_fail(h, PSRA_E_OVERFLOW, "event list of a timeline segment overflowed (%d entries): set a shorter psra_config.seg_hours", a.ev_cap);
+    }
     if (acc[ACC_OVERFLOW] == 2ull)
         return psra_fail(h, PSRA_E_OVERFLOW, "internal error: pending-event list overflow in the sequential kernel");
     if (acc[ACC_OVERFLOW])
         return psra_fail(h, PSRA_E_OVERFLOW, "injected durations exhausted: a unit needed more than K=%d draws", K);
     return PSRA_OK;
+}
+
+int psra_run_seq_range(psra_handle *h, long long chain_base, long long nchains, int ypc, int init_mode, uint64_t seed,
+                       const psra_seq_outputs *out, psra_seq_summary *summary)
+{
+    return run_seq(h, false, nullptr, 0, chain_base, nchains, ypc, init_mode, seed, out, summary);
 }
 
 extern "C" int psra_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed, int32_t init_mode,
@@ -637,6 +760,7 @@ extern "C" int psra_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64
                  "year0 and nyears must be multiples of years_per_chain");
     PSRA_REQUIRE(h, (init_mode & ~PSRA_DISC_MATLAB) == PSRA_INIT_ALL_UP || (init_mode & ~PSRA_DISC_MATLAB) == PSRA_INIT_STATIONARY,
                  "unknown init_mode");
+    if (!h->peers.empty()) return psra_multi_seq_mc(h, year0, nyears, seed, init_mode, years_per_chain, out, summary);
     return run_seq(h, false, nullptr, 0, year0 / years_per_chain, nyears / years_per_chain, years_per_chain,
                    init_mode, seed, out, summary);
 }

@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, 3) seq_team_kernel(const SeqA
                     if (a.ens) a.ens[yi] = ens;
                     if (a.ent) a.ent[yi] = entries;
                     if (a.group_lol && lolh) atomicAdd(&a.group_lol[yi / a.group], (unsigned long long)lolh);
+                    if (lolh) seq_hist_add(a, ens);
                 }
                 acc_lol += lolh; acc_ens += ens; acc_ent += entries;
                 acc_ywl += lolh ? 1 : 0;

@@ -23,16 +23,39 @@ def test_library_exports_every_declared_symbol():
     assert L.psra_version() == 1001
 
 
-def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.Config) == 32
-    assert ctypes.sizeof(_lib.SeqSummary) == 80
-    assert ctypes.sizeof(_lib.SeqOutputs) == 56
-    assert ctypes.sizeof(_lib.NonseqSummary) == 64
-    assert ctypes.sizeof(_lib.NonseqOutputs) == 56
-    assert ctypes.sizeof(_lib.TailOut) == 40
-    assert ctypes.sizeof(_lib.DetailedSystem) == 48
-    assert ctypes.sizeof(_lib.AreaSystem) == 64 and ctypes.sizeof(_lib.AreaOutputs) == 16
-    assert ctypes.sizeof(_lib.AreaSummary) == 8 + 2 * 8 * _lib.MAX_AREAS + 16
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors against the header itself: a C program compiled from include/psra_b200.h prints sizeof and
+    the offset of every field; both must agree with _lib.py (the Julia structs in julia/*.jl list the same fields in
+    the same order, checked by name below)."""
+    import subprocess
+    pairs = [("psra_config", _lib.Config), ("psra_seq_summary", _lib.SeqSummary), ("psra_seq_outputs", _lib.SeqOutputs),
+             ("psra_nonseq_summary", _lib.NonseqSummary), ("psra_nonseq_outputs", _lib.NonseqOutputs),
+             ("psra_tail_out", _lib.TailOut), ("psra_detailed_system", _lib.DetailedSystem),
+             ("psra_area_system", _lib.AreaSystem), ("psra_area_outputs", _lib.AreaOutputs),
+             ("psra_area_summary", _lib.AreaSummary)]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "psra_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            src.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ['  return 0;', '}']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    assert ctypes.sizeof(_lib.Config) == 64 and ctypes.sizeof(_lib.SeqOutputs) == 64
+    # Julia mirrors: same field names in the same order (Julia is not installed here; this is the mechanical part)
+    jl = open(os.path.join(ROOT, "julia/PowerSystemAdequacyB200.jl")).read()
+    for jname, cls in (("PsraConfig", _lib.Config), ("PsraSeqSummary", _lib.SeqSummary), ("PsraSeqOutputs", _lib.SeqOutputs),
+                       ("PsraNonseqSummary", _lib.NonseqSummary), ("PsraNonseqOutputs", _lib.NonseqOutputs), ("PsraTailOut", _lib.TailOut)):
+        body = re.search(r"struct %s\n(.*?)\nend" % jname, jl, re.S).group(1)
+        names = re.findall(r"([a-z_0-9]+)::", body)
+        assert names == [f for f, _ in cls._fields_], jname
 
 
 def test_no_cpu_fallback():
@@ -68,6 +91,30 @@ def test_fixed_point_conversion():
     assert list(api._fixed([1.3, 2.5, 3.5], 1.0, "x", False)) == [1, 2, 4]     # rint = half-even
     with pytest.raises(ValueError):
         api._fixed([-1.0], 1.0, "x", False)
+
+
+def test_load_goes_onto_the_grid_without_changing_the_loss_test():
+    """PSA.jl:192,253: cap_avail < load in Float64.  For whole-grid capacities c < L <=> c < ceil(L): the default load
+    conversion is ceil (values on the grid untouched), so LOL hours of the Float64 comparison survive exactly."""
+    L = np.array([1530.76977, 1439.0, 1370.00000004, 2850.0, 0.2])
+    assert list(api._fixed_load(L, 1.0, "ceil")) == [1531, 1439, 1371, 2850, 1]
+    assert list(api._fixed_load(L, 1.0, "rint")) == [1531, 1439, 1370, 2850, 0]
+    assert list(api._fixed_load([0.3, 1530.76977, 0.7], 10.0, "ceil")) == [3, 15308, 7]      # 0.3 * 10 = 3.0000000000000004
+    with pytest.raises(ValueError):
+        api._fixed_load(L, 1.0, "strict")
+    rng = np.random.default_rng(0)
+    load = rng.uniform(900.0, 2900.0, 5000)
+    caps = np.where(rng.random(5000) < 0.5, np.floor(load), rng.integers(0, 3406, 5000)).astype(np.float64)   # half of them just below the load
+    assert np.array_equal(caps < load, caps < api._fixed_load(load, 1.0, "ceil"))
+    assert not np.array_equal(caps < load, caps < api._fixed_load(load, 1.0, "rint"))
+    # the analytical LOLE of the ceil-ed RTS-79 curve is the float-load value (9.3941), not the rint one (9.3677)
+    from oracle import oracle as O
+    from powersystemsreliabilityassessment_b200 import rts79
+    cap, mttf, mttr = rts79.units()
+    q = (1 / mttf) / (1 / mttf + 1 / mttr)
+    lo_f, _, _ = O.analytical(cap, q, rts79.load_curve_mw(), 1.0)
+    lo_c, _, _ = O.analytical(cap, q, api._fixed_load(rts79.load_curve_mw(), 1.0, "ceil").astype(np.float64), 1.0)
+    assert abs(lo_f - 9.3941103566) < 1e-9 and abs(lo_c - lo_f) < 1e-12
 
 
 def test_indices_from_raw():
