@@ -54,13 +54,13 @@ typedef struct psra_config {
     int32_t blocks_per_sm;    /* 0 = as many as fit */
     int32_t reserved[4];      /* reserved[0] != 0: force the generic sequential kernel (seq_mc.cu) also
                                  for systems of <= 32 units (cross-checks; the default picks seq_fast.cu);
-                                 reserved[1] == 1: seq_fast.cu keeps the word sums unpacked, seq_wide.cu keeps one hour
-                                 per timeline word; == 2: seq_wide.cu packs two hours per word whatever the unit sizes
-                                 (cross-checks of the redo path);
+                                 reserved[1] == 1: seq_fast.cu keeps the word sums unpacked (cross-checks);
                                  reserved[2] != 0: systems of > 32 units use seq_team.cu also where seq_wide.cu
                                  applies (cross-checks);
                                  reserved[3] > 0: number of statically scheduled Philox blocks per unit in
-                                 seq_fast.cu's single-segment mode (0 = chosen from the expected demand) */
+                                 seq_fast.cu's single-segment mode (0 = chosen from the expected demand); for
+                                 seq_wide.cu: k moves the static-phase threshold to (k - 16) / 8 standard deviations
+                                 below the expected demand (0 = 0.5) */
     int32_t ngpus;            /* 0 / 1: one device.  G > 1: the handle spans the devices device .. device + G - 1 of this
                                  process; psra_seq_mc / psra_nonseq_mc split their year / sample range over them
                                  (contiguous shards keyed on the global index, so the integers do not depend on G) and
@@ -110,7 +110,7 @@ typedef struct psra_seq_summary {
     uint64_t events;            /* state transitions simulated (diagnostic) */
     float    kernel_ms;         /* CUDA-event time of the kernel(s) of this call (multi-GPU: the slowest device) */
     int32_t  redone;            /* chains a fast kernel handed back and the library replayed with the generic kernel
-                                   (event list full / packed-timeline checksum); results are exact either way */
+                                   (event list of a warp full); results are exact either way */
 } psra_seq_summary;
 
 typedef struct psra_seq_outputs {       /* all optional (NULL = not wanted) */

@@ -264,20 +264,24 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
         PSRA_CUDA(h, cudaMalloc(&h->d_mttr, sizeof(float) * U));
         PSRA_CUDA(h, cudaMalloc(&h->d_for_thr, sizeof(uint32_t) * U));
         PSRA_CUDA(h, cudaMalloc(&h->d_for, sizeof(double) * U));
-        PSRA_CUDA(h, cudaMalloc(&h->d_order, sizeof(int32_t) * U));
-        PSRA_CUDA(h, cudaMalloc(&h->d_wide_tab, sizeof(uint4) * U));
+        PSRA_CUDA(h, cudaMalloc(&h->d_order, sizeof(int32_t) * ((U + 31) & ~31)));      // padded to whole groups of 32 (seq_wide.cu)
+        PSRA_CUDA(h, cudaMalloc(&h->d_wide_tab, sizeof(uint4) * ((U + 31) & ~31)));
     }
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_cap, cap_fp, sizeof(int32_t) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_mttf, mf.data(), sizeof(float) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_mttr, mr.data(), sizeof(float) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_for_thr, thr.data(), sizeof(uint32_t) * U, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaMemcpyAsync(h->d_for, q.data(), sizeof(double) * U, cudaMemcpyHostToDevice, h->stream));
-    std::vector<int32_t> order(U);
+    const int Upad = (U + 31) & ~31;
+    std::vector<int32_t> order(Upad, 0);
     for (int u = 0; u < U; u++) order[u] = u;
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return mttf_h[x] + mttr_h[x] < mttf_h[y] + mttr_h[y]; });
-    PSRA_CUDA(h, cudaMemcpyAsync(h->d_order, order.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, h->stream));
+    std::stable_sort(order.begin(), order.begin() + U, [&](int32_t x, int32_t y) { return mttf_h[x] + mttr_h[x] < mttf_h[y] + mttr_h[y]; });
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_order, order.data(), sizeof(int32_t) * Upad, cudaMemcpyHostToDevice, h->stream));
+    h->cycle_sorted.assign(U, 0.0);
+    for (int k = 0; k < U; k++) h->cycle_sorted[k] = mttf_h[order[k]] + mttr_h[order[k]];
     // one 16-byte record per queue position for seq_wide.cu (the means already in ticks: a power-of-two scaling, exact)
-    std::vector<uint4> wtab(U);
+    // (positions U .. Upad - 1: capacity 0; the kernel keeps their events out of the year)
+    std::vector<uint4> wtab(Upad, make_uint4(0u, 0x4B800000u, 0x4B800000u, 0u));
     for (int k = 0; k < U; k++) {
         const int u = order[k];
         const float mup = mf[u] * 16777216.0f, mdn = mr[u] * 16777216.0f;
@@ -285,7 +289,7 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
         memcpy(&bu, &mup, 4); memcpy(&bd, &mdn, 4);
         wtab[k] = make_uint4((uint32_t)cap_fp[u], bu, bd, thr[u]);
     }
-    PSRA_CUDA(h, cudaMemcpyAsync(h->d_wide_tab, wtab.data(), sizeof(uint4) * U, cudaMemcpyHostToDevice, h->stream));
+    PSRA_CUDA(h, cudaMemcpyAsync(h->d_wide_tab, wtab.data(), sizeof(uint4) * Upad, cudaMemcpyHostToDevice, h->stream));
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     h->U = U;
     h->total_cap = total;

@@ -39,8 +39,9 @@ struct psra_handle {
     float *d_mttf = nullptr;         // [U] binary32 means used by the sampler
     float *d_mttr = nullptr;
     uint32_t *d_for_thr = nullptr;   // [U] floor(FOR * 2^32)
-    int32_t *d_order = nullptr;      // [U] unit indices, most transitions per hour first
-    uint4 *d_wide_tab = nullptr;     // [U] in that order: {capacity, bits of mttf * 2^24, bits of mttr * 2^24, FOR threshold} (seq_wide.cu)
+    int32_t *d_order = nullptr;      // [U padded to 32] unit indices, most transitions per hour first
+    uint4 *d_wide_tab = nullptr;     // [U padded to 32] in that order: {capacity, bits of mttf * 2^24, bits of mttr * 2^24, FOR threshold} (seq_wide.cu)
+    std::vector<double> cycle_sorted;   // [U] MTTF + MTTR in hours, in that order (host copy: static block counts of seq_wide.cu)
     double *d_for = nullptr;         // [U] FOR in FP64 (injected-uniform path, PSA.jl:183)
     // load (device)
     int H = 0;

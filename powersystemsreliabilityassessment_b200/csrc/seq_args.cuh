@@ -5,7 +5,7 @@
 
 struct SeqArgs {
     int U, H, Wd, seg_words, nseg, ypc, init_mode, K, group, persist, load16, disc, pend_cap, ev_cap, two_halves, pack_shift, static_blocks;
-    int wide_pack;          // seq_wide.cu: two hours per 32-bit timeline word
+    uint8_t wide_sblk[64];  // seq_wide.cu: statically scheduled Philox blocks per unit, for every group of 32 queue positions
     int redo_cap;           // capacity of the redo list
     int group_phase;        // local year 0 of this launch is year `group_phase` of its history group (replays only)
     const int32_t *cap; const float *mttf; const float *mttr; const uint32_t *for_thr;
@@ -20,7 +20,7 @@ struct SeqArgs {
     uint32_t *lol; long long *ens; uint32_t *ent; uint32_t *fail;
     unsigned long long *group_lol; unsigned long long *acc;
     unsigned long long *imp;   // [U] hours with loss of load in which the unit is DOWN (seq_mc.cu only), or nullptr
-    // redo list: redo[0] = number of chains a fast kernel handed back (event list full, packed timeline checksum),
+    // redo list: redo[0] = number of chains a fast kernel handed back (event list of seq_fast.cu full),
     // redo[1 + i] = their absolute chain indices; the host replays them with the generic kernel of seq_mc.cu
     unsigned long long *redo;
     // per-year ENS histogram (tail risk, tail_risk.jl:168-175 / seqMain.m:287): hist[e] = number of years whose ENS is
@@ -68,7 +68,8 @@ void seq_team_launch(const SeqArgs &a, unsigned grid, size_t smem, cudaStream_t 
 #define SEQ_TEAM_WARPS 8
 
 // seq_wide.cu
-size_t seq_wide_smem_bytes(int Wd, bool pack);
-int seq_wide_threads();
-cudaError_t seq_wide_prepare(bool disc, bool pack, size_t smem, int threads, int *blocks_per_sm);
+#define SEQ_WIDE_MAX_UNITS 2048
+size_t seq_wide_smem_bytes(int Wd, int U, int nwarps);
+int seq_wide_max_warps();
+cudaError_t seq_wide_prepare(bool disc, size_t smem, int threads, int *blocks_per_sm);
 void seq_wide_launch(const SeqArgs &a, unsigned grid, int threads, size_t smem, cudaStream_t stream);

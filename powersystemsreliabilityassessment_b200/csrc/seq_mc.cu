@@ -420,7 +420,8 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     PSRA_REQUIRE(h, !imp_out || one_unit || ypc == 1, "unit importance for more than 32 units needs years_per_chain = 1");
     // seq_wide.cu: one block per year with a lane-level work queue over the units, when the whole year is one
     // shared-memory timeline (independent years, no explicit segment length); seq_team.cu covers the rest
-    const bool wide = team && ypc == 1 && h->cfg.seg_hours == 0 && h->Wd * 32 <= 10240 && !h->cfg.reserved[2];
+    const bool wide = team && ypc == 1 && h->cfg.seg_hours == 0 && h->Wd * 32 <= 10240 && !h->cfg.reserved[2] &&
+                      h->U <= SEQ_WIDE_MAX_UNITS;
     SeqArgs a{};
     a.U = h->U; a.H = h->H; a.Wd = h->Wd; a.ypc = ypc; a.init_mode = init_mode & ~PSRA_DISC_MATLAB; a.K = K;
     a.disc = (!injected && (init_mode & PSRA_DISC_MATLAB)) ? 1 : 0;
@@ -476,15 +477,24 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     }
     if (fast && a.ev_cap > 2016)
         return psra_fail(h, PSRA_E_INVALID, "unit transition rate too high for the sampler kernel (%d events per 32-hour word)", a.ev_cap);
-    // seq_wide.cu: two hours per timeline word (int16 halves) when a single hour cannot plausibly move the capacity
-    // by 2^14 fixed-point units -- at least 8 + 4 x (expected events per hour) same-direction events of the largest
-    // unit would have to meet in one hour.  A year in which an hour's net change does leave +-2^14 is caught by the
-    // kernel (range test of every half, end-of-year checksum) and replayed with the int32 timeline.
-    // psra_config.reserved[1]: 1 = never, 2 = always (cross-checks of the redo path)
-    a.wide_pack = 0;
-    if (wide && h->cfg.reserved[1] != 1 && h->max_unit_cap > 0 &&
-        (h->cfg.reserved[1] == 2 || 16384.0 / (double)h->max_unit_cap >= 8.0 + 4.0 * h->events_per_hour))
-        a.wide_pack = 1;
+    // seq_wide.cu: Philox blocks per unit that are generated without any scheduling (static phase), one count per group
+    // of 32 queue positions (the units are sorted by transition rate, so a group's units have about the same demand).
+    // A unit with m = 2 H / (MTTF + MTTR) expected transitions needs ceil((m' + 2) / 4) blocks, m' ~ m +- sqrt(m); a
+    // static block costs ~140 warp-instructions per 32 units, a queued one ~200, so block b is worth scheduling
+    // statically when it is needed with probability >= ~0.7: B = floor((m + 2 - 0.5 sqrt(m)) / 4), at least 1
+    // (block 0 holds the initial state).  psra_config.reserved[3] = k > 0 moves the 0.5 to (k - 16) / 8 (sweeps).
+    if (wide) {
+        const double theta = h->cfg.reserved[3] > 0 ? (h->cfg.reserved[3] - 16) / 8.0 : 0.5;
+        const int ngroups = (h->U + 31) / 32;
+        for (int g = 0; g < ngroups; g++) {
+            int B = 255;
+            for (int k = g * 32; k < std::min(h->U, g * 32 + 32); k++) {
+                const double m = 2.0 * h->H / h->cycle_sorted[(size_t)k];
+                B = std::min(B, (int)std::floor((m + 2.0 - theta * std::sqrt(m)) / 4.0));
+            }
+            a.wide_sblk[g] = (uint8_t)std::max(1, std::min(255, B));
+        }
+    }
     // seq_fast.cu single-segment mode: the first blocks of every unit are generated lane = unit without any scheduling.
     // Their number: about 0.7 x the mean demand E[blocks] = (1 + 2 H / (MTTF + MTTR) + 1) / 4 per unit (3 for RTS-79;
     // a simulation of the scheduler puts the optimum of cost = 250 static + 425 per wave there), at least 1
@@ -501,7 +511,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     wpb = std::max(1, std::min(fast ? seq_fast_max_threads(a.two_halves != 0) / 32 : 16, wpb));
     auto smem_for = [&](int w) -> size_t {
         if (fast) return seq_fast_smem_bytes(h->Wd, seg_words, w, a.ev_cap, a.two_halves != 0, load16, a.pack_shift != 0);
-        if (wide) return seq_wide_smem_bytes(h->Wd, a.wide_pack != 0);
+        if (wide) return seq_wide_smem_bytes(h->Wd, h->U, w);
         if (team) return seq_team_smem_bytes(h->U, h->Wd, seg_words, a.two_halves != 0);
         return gg.smem;
     };
@@ -510,7 +520,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         if (wide) {
             // block size of seq_wide.cu: 4 warps measured best from 64 to 1024 units (scripts/sweep_wide_units.py: +10-18 %
             // over 6 warps at 96-320 units, equal at 1024); psra_config.warps_per_block overrides (at most 4)
-            const int wmax = seq_wide_threads() / 32;
+            const int wmax = seq_wide_max_warps();
             wpb = h->cfg.warps_per_block > 0 ? std::min(wmax, h->cfg.warps_per_block) : std::min(wmax, 4);
         }
     }
@@ -577,7 +587,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (fast) {
         PSRA_CUDA(h, seq_fast_prepare(a.disc != 0, a.two_halves != 0, a.pack_shift != 0, smem, wpb * 32, &bps));
     } else if (wide) {
-        PSRA_CUDA(h, seq_wide_prepare(a.disc != 0, a.wide_pack != 0, smem, wpb * 32, &bps));
+        PSRA_CUDA(h, seq_wide_prepare(a.disc != 0, smem, wpb * 32, &bps));
     } else if (team) {
         PSRA_CUDA(h, seq_team_prepare(smem, &bps));
     } else {
@@ -646,9 +656,9 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
             if (rc) return rc;
         }
     }
-    // chains the sampler kernels handed back (event list of seq_fast.cu full, checksum of seq_wide.cu's packed timeline):
+    // chains the sampler kernels handed back (event list of seq_fast.cu full):
     // replay each with a kernel that has no such limit, into the same accumulators and output slots.  Rare by
-    // construction (see ev_cap_for / wide_pack above), so one small launch per chain is fine.
+    // construction (see ev_cap_for above), so one small launch per chain is fine.
     PSRA_CUDA(h, cudaMemcpyAsync(&n_redo, h->d_redo, sizeof(n_redo), cudaMemcpyDeviceToHost, h->stream));
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     if (n_redo > PSRA_REDO_CAP)
@@ -661,10 +671,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         b.redo = nullptr;
         size_t smem_r = 0; int threads_r = 0;
         if (wide) {
-            b.wide_pack = 0;
-            smem_r = seq_wide_smem_bytes(h->Wd, false); threads_r = wpb * 32;
-            int dummy = 0;
-            PSRA_CUDA(h, seq_wide_prepare(b.disc != 0, false, smem_r, threads_r, &dummy));
+            smem_r = smem; threads_r = wpb * 32;
         } else {
             b.seg_words = gg.seg_words; b.nseg = gg.nseg; b.persist = gg.persist;
             smem_r = gg.smem; threads_r = 32;

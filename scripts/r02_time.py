@@ -6,16 +6,19 @@ import numpy as np
 from powersystemsreliabilityassessment_b200 import Engine, rts79
 
 c5 = rts79.synthetic_system(32, 37.0)
-for name, kw in (("wide packed", dict()), ("wide int32", dict(unpacked_words=True)), ("wide packed bps6", dict(blocks_per_sm=6)),
-                 ("wide packed bps7", dict(blocks_per_sm=7)), ("wide packed 3 warps", dict(warps_per_block=3)),
-                 ("wide packed 2 warps", dict(warps_per_block=2))):
+variants = [("wide default", dict())] + [(f"wide theta {(k - 16) / 8:+.3f}", dict(static_blocks=k)) for k in (8, 12, 16, 18, 24, 32, 48)] + \
+           [(f"wide {w} warps", dict(warps_per_block=w)) for w in (2, 3, 5, 6, 7, 8)] + [("wide bps4", dict(blocks_per_sm=4)), ("wide 6 warps bps3", dict(warps_per_block=6, blocks_per_sm=3))]
+if len(sys.argv) > 1 and sys.argv[1] == "short":
+    variants = variants[:1]
+if len(sys.argv) > 1 and sys.argv[1] == "warps":
+    variants = [v for v in variants if "warps" in v[0] or "default" in v[0] or "bps" in v[0]]
+for name, kw in variants:
     with Engine(**kw) as e:
         e.set_system(c5[0], c5[1], c5[2]); e.set_load(c5[3])
         e.seq_mc(20_000, seed=1)
-        best = None
         for n in (200_000, 1_000_000):
             r = e.seq_mc(n, seed=42)
-            print(f"{name:24s} {n:8d} yr  {r.kernel_ms:9.2f} ms  {n / r.kernel_ms * 1e3 / 1e6:7.3f} M yr/s  LOLE {r.lole:.4f}  redone {r.redone}  {e.last_counters()}", flush=True)
+            print(f"{name:24s} {n:8d} yr  {r.kernel_ms:9.2f} ms  {n / r.kernel_ms * 1e3 / 1e6:7.3f} M yr/s  LOLE {r.lole:.4f}  {e.last_counters()}", flush=True)
 
 cap, mttf, mttr = rts79.units()
 load = rts79.load_curve_int()

@@ -1,5 +1,5 @@
 """Round-2 features of the sequential path, every one through the C ABI against the CPU oracle:
-packed seq_wide.cu timeline + checksum / redo list, non-fatal event-list overflow of seq_fast.cu, the in-kernel
+static / queue phases of seq_wide.cu, non-fatal event-list overflow of seq_fast.cu, the in-kernel
 ENS histogram and the one-launch VaR / CVaR from its counts (tail_risk.jl:168-175, seqMain.m:287; SURVEY a-12),
 histogram exchange for cross-process sharding, the history launch plan at its chunk boundary, the lossless
 Float64-load rule (PSA.jl:192,253) and the self-contained multi-area call."""
@@ -22,47 +22,38 @@ def _same(a, b):
         assert a.raw[k] == b.raw[k], k
 
 
-def test_wide_packed_timeline_equals_int32_timeline_and_oracle(engine):
-    """seq_wide.cu keeps two hours per timeline word by default (config 5); the int32 timeline (unpacked_words) and the
-    oracle's literal loop give the same integers, with and without the MATLAB discretisation, for a ragged hour count."""
-    cap, mttf, mttr, load = rts79.synthetic_system(32, 37.0)
-    with Engine(unpacked_words=True) as un:
-        for H in (8736, 8736 - 45):
-            engine.set_system(cap, mttf, mttr); engine.set_load(load[:H])
-            un.set_system(cap, mttf, mttr); un.set_load(load[:H])
-            for disc in (0, DISC_MATLAB):
-                a = engine.seq_mc(200, seed=5, year0=40, init_mode=1 | disc, per_year=True, fail_count=True, group=10)
-                b = un.seq_mc(200, seed=5, year0=40, init_mode=1 | disc, per_year=True, fail_count=True, group=10)
-                _same(a, b)
-                assert np.array_equal(a.fail_count, b.fail_count) and np.array_equal(a.group_lol, b.group_lol)
-                assert a.redone == 0 and b.redone == 0 and a.lol_hours.sum() > 0
+def test_wide_static_and_queue_phases_give_the_oracle_integers(engine):
+    """seq_wide.cu generates the first blocks of every unit in a static lane = unit phase and the rest from per-warp
+    to-do queues.  The split (psra_config.reserved[3]: from "one static block" to "almost everything static") and the
+    block size must not change a single integer: oracle's literal loop, with and without the MATLAB discretisation,
+    ragged hour count, unit counts that are not multiples of 32 (padding lanes) and config 5."""
+    rng = np.random.default_rng(5)
+    cases = []
+    c5 = rts79.synthetic_system(32, 37.0)
+    cases.append((c5[0], c5[1], c5[2], c5[3][:8736 - 45], 6))
+    for U in (33, 70, 200):
+        k = (U + 31) // 32
+        s = rts79.synthetic_system(k, 1.05 * U / 32.0)
+        pick = np.sort(rng.choice(32 * k, U, replace=False))
+        cases.append((s[0][pick], s[1][pick] * rng.uniform(0.5, 1.5, U), s[2][pick], s[3], 12))
+    for cap, mttf, mttr, load, ny in cases:
         engine.set_system(cap, mttf, mttr); engine.set_load(load)
-        r = engine.seq_mc(10, seed=77, year0=3, per_year=True)
-        lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 77, 3, 10, 1, 1)
-        assert np.array_equal(r.lol_hours.astype(np.float64), lol) and np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), ens)
-        assert np.array_equal(r.entries.astype(np.float64), ent)
-
-
-def test_wide_packed_checksum_sends_overflowing_years_to_the_redo_list():
-    """Units of 9000 fixed-point MW: two same-direction events in one hour leave the accepted range of the packed
-    timeline's int16 halves, four wrap them (the packed variant is forced on here; the host would not choose it for such
-    a system).  The kernel must catch every such year (range test, end-of-year checksum) and the library replays it
-    with the int32 timeline: integers identical to the int32 kernel and to the oracle, redone > 0."""
-    rng = np.random.default_rng(12)
-    U = 48
-    cap = np.full(U, 9000.0); mttf = rng.uniform(150.0, 300.0, U); mttr = rng.uniform(40.0, 80.0, U)
-    load = rng.integers(280_000, 400_000, 2016).astype(np.int32)
-    with Engine(unpacked_words=2) as pk, Engine(unpacked_words=True) as un:      # 2 = force the packed timeline
-        for e in (pk, un):
-            e.set_system(cap, mttf, mttr); e.set_load(load)
-        a = pk.seq_mc(400, seed=3, per_year=True, fail_count=True, group=10, history=10)
-        b = un.seq_mc(400, seed=3, per_year=True, fail_count=True, group=10, history=10)
-        assert a.redone > 0 and b.redone == 0
-        _same(a, b)
-        assert np.array_equal(a.fail_count, b.fail_count) and np.array_equal(a.group_lol, b.group_lol)
-        assert np.array_equal(a.history, b.history)
-        lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 3, 0, 24, 1, 1)
-        assert np.array_equal(a.lol_hours[:24].astype(np.float64), lol) and np.array_equal(a.raw["ens_fp_vector"][:24].astype(np.float64), ens)
+        for disc in (0, DISC_MATLAB):
+            ref = engine.seq_mc(ny * 8, seed=5, year0=40, init_mode=(0 if disc else 1) | disc, per_year=True, fail_count=True, group=10)
+            assert ref.lol_hours.sum() > 0
+            if disc:
+                lol, ens, ent = O.seq_matlab_philox(cap, mttf, mttr, load.astype(np.float64), 5, 40, ny)
+            else:
+                lol, ens, ent = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 5, 40, ny, 1, 1)
+            assert np.array_equal(ref.lol_hours[:ny].astype(np.float64), lol) and np.array_equal(ref.entries[:ny].astype(np.float64), ent)
+            assert np.array_equal(ref.raw["ens_fp_vector"][:ny].astype(np.float64), ens)
+            for kw in (dict(static_blocks=1), dict(static_blocks=56), dict(static_blocks=8, warps_per_block=1),
+                       dict(warps_per_block=3), dict(warps_per_block=2, blocks_per_sm=1), dict(force_team=True)):
+                with Engine(**kw) as v:
+                    v.set_system(cap, mttf, mttr); v.set_load(load)
+                    b = v.seq_mc(ny * 8, seed=5, year0=40, init_mode=(0 if disc else 1) | disc, per_year=True, fail_count=True, group=10)
+                _same(ref, b)
+                assert np.array_equal(ref.fail_count, b.fail_count) and np.array_equal(ref.group_lol, b.group_lol)
 
 
 def test_fast_kernel_event_list_overflow_is_replayed_not_fatal(rts):
@@ -83,7 +74,9 @@ def test_fast_kernel_event_list_overflow_is_replayed_not_fatal(rts):
         assert small.tail(None) == ref.tail(None)
         # ring variant: three-year chains
         l3, e3, n3 = O.seq_philox(cap, mttf, mttr, load.astype(np.float64), 21, 0, 8, 3, 0)
-        c = small.seq_mc(24, seed=21, init_mode=0, years_per_chain=3, per_year=True)
+        with Engine(ev_cap=448) as tiny:       # the ring keeps one list per year-long segment: below the ~ 500 events of a year
+            tiny.set_system(cap, mttf, mttr); tiny.set_load(load)
+            c = tiny.seq_mc(24, seed=21, init_mode=0, years_per_chain=3, per_year=True)
         assert c.redone > 0
         assert np.array_equal(c.lol_hours.astype(np.float64), l3) and np.array_equal(c.raw["ens_fp_vector"].astype(np.float64), e3)
         assert np.array_equal(c.entries.astype(np.float64), n3)

@@ -223,9 +223,9 @@ def test_statistics_match_analytical_rts79(engine, rts):
 def test_fixed_point_scale_int32_timeline(engine, rts):
     """fp_scale = 16: installed capacity 54 480 and peak load 45 600 exceed int16, so the sampler kernel
     takes its int32 timeline / int32 load-curve variant; ENS is then in 1/16 MWh."""
-    load = np.rint(16 * rts["load_mw"]).astype(np.int32)
     engine.set_system(rts["cap"], rts["mttf"], rts["mttr"], fp_scale=16.0)
-    engine.set_load(rts["load_mw"])
+    load = engine.set_load(rts["load_mw"])                     # the grid values the library uses (ceil rule, api._fixed_load)
+    assert np.abs(load - 16 * rts["load_mw"]).max() < 1.0 and (load >= 16 * rts["load_mw"] - 1e-9).all()
     r = engine.seq_mc(96, seed=321, init_mode=1, per_year=True)
     lol, ens, ent = O.seq_philox(16 * rts["cap"], rts["mttf"], rts["mttr"], load.astype(np.float64), 321, 0, 96, 1, 1)
     assert np.array_equal(r.lol_hours.astype(np.float64), lol)
