@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports this module.
-Parity status: deterministic functions pinned by SURVEY.md section 8c known answers
-(tests/test_oracle.py); the reference's Monte Carlo streams are unpinned (Julia RNG).
+Parity status: pinned by SURVEY.md section 8c known answers (tests/test_oracle.py) and by vectors the reference's
+own source text produces when transliterated line by line (oracle/jl_transliterate.py, tests/golden/ref_*.npz,
+tests/test_reference_pin.py); the reference's Monte Carlo random streams themselves are irreproducible (unseeded Julia RNG).
 """
 from __future__ import annotations
 

@@ -9,12 +9,23 @@
  * MATLAB; neither runtime exists in this image, so the reference itself cannot be
  * compiled or run here (no oracle/_ref).  Every function below restates, line by line,
  * the arithmetic of the cited reference lines in plain C (FP64, no FMA contraction,
- * same operation order).  Pinning: the deterministic functions are checked against the
- * known-answer values derived in SURVEY.md section 8c / BASELINE.md section 3 (classic
- * RTS-79 HL1 LOLE 9.394 h/yr, the script demos' printed values) in tests/test_oracle.py.
- * The Monte Carlo streams of the reference (Julia's unpinned default RNG) cannot be
- * reproduced: MC parity is "unpinned by the reference" and is established through
- * injected duration / state matrices instead.
+ * same operation order).  Pinning:
+ *   (1) known answers: the deterministic functions against the values derived in SURVEY.md
+ *       section 8c / BASELINE.md section 3 (classic RTS-79 HL1 LOLE 9.394 h/yr, the script
+ *       demos' printed values), tests/test_oracle.py;
+ *   (2) the reference's own source text: run_sequential_mc / run_non_sequential_mc /
+ *       add_unit_convolution / run_analytical are cut out of the reference checkout and
+ *       transliterated line by line into Python (oracle/jl_transliterate.py; the three
+ *       `-log(rand())/rate` draws of PSA.jl:224,243,246 read from per-unit lists, rand() of
+ *       PSA.jl:183 replayed from a recorded matrix); the vectors they produce are committed
+ *       (tests/golden/ref_*.npz, scripts/make_reference_golden.py) and this file reproduces
+ *       them bit for bit (tests/test_reference_pin.py), as does an independent naive
+ *       transcription (oracle/psa_literal.py);
+ *   (3) not done here: Julia itself.  tools/patched_reference.jl runs the same three
+ *       substitutions in a real Julia for whoever has one.
+ * The Monte Carlo STREAMS of the reference (Julia's unversioned default RNG, never seeded)
+ * cannot be reproduced by anyone; parity of the sampler paths is per trial on injected
+ * duration / state / uniform matrices.
  *
  * All citations are path:line under /root/reference/GeneratingAdequacy unless a
  * directory is given.  PSA.jl = PowerSystemAdequacy.jl.

@@ -53,3 +53,55 @@ def test_nonsequential_samples_golden(engine, rts):
     assert np.array_equal(r["lol_hours"].astype(np.float64), g["lol"])
     assert np.array_equal(r["ens"].astype(np.float64), g["eue"])
     assert np.array_equal(r["states"].reshape(256, -1), g["states"])
+
+
+# ---- vectors produced by the reference's own source text (scripts/make_reference_golden.py, oracle/jl_transliterate.py)
+def _ref(name):
+    return np.load(os.path.join(G, f"ref_{name}.npz"))
+
+
+@pytest.mark.parametrize("case", ["rts79_int", "small"])
+def test_reference_text_sequential_vectors_integer_load(engine, case):
+    """run_sequential_mc of PSA.jl:214-269 (transliterated from the reference text, the three draws injected) against
+    psra_seq_eval_injected: every year's LOL hours and ENS, the history and the indices, bit for bit."""
+    g = _ref("seq_" + case)
+    years = len(g["lole"])
+    engine.set_system(g["cap"], g["mttf"], g["mttr"]); engine.set_load(g["load"], strict=True)
+    r = engine.seq_eval_injected(g["dur"][None, :, :], years_per_chain=years, group=10)
+    assert np.array_equal(r.lol_hours.astype(np.float64), g["lole"]) and g["lole"].sum() > 0
+    assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), g["eue"])
+    hist = np.cumsum(r.group_lol[:years // 10]) / (10.0 * np.arange(1, years // 10 + 1))
+    assert np.array_equal(hist, g["history"])
+    assert r.lole == float(g["lole_hours_yr"]) and r.eens == float(g["eue_mwh_yr"])
+
+
+def test_reference_text_sequential_vectors_fractional_load(engine):
+    """The RTS-79 curve in MW (fractional): the library puts the load on the integer grid with ceil, which keeps every
+    loss-of-load hour of the Float64 comparison (c < L <=> c < ceil(L)); the deficit is over-stated by < 1 MW per hour."""
+    g = _ref("seq_rts79_mw")
+    years = len(g["lole"])
+    engine.set_system(g["cap"], g["mttf"], g["mttr"]); engine.set_load(g["load"])
+    r = engine.seq_eval_injected(g["dur"][None, :, :], years_per_chain=years)
+    assert np.array_equal(r.lol_hours.astype(np.float64), g["lole"]) and g["lole"].sum() > 0
+    over = r.raw["ens_fp_vector"].astype(np.float64) - g["eue"]
+    assert (over >= 0).all() and (over < np.maximum(g["lole"], 1e-300)).all()
+
+
+def test_reference_text_non_sequential_vectors(engine):
+    g = _ref("nonseq_rts79_mw")
+    engine.set_system(g["cap"], g["mttf"], g["mttr"]); engine.set_load(g["load"])
+    r = engine.nonseq_eval_uniforms(g["r"], group=100)
+    assert np.array_equal(r["lol_hours"].astype(np.float64), g["lole"])
+    over = r["ens"].astype(np.float64) - g["eue"]
+    assert (over >= -1e-9).all() and (over < np.maximum(g["lole"], 1e-300) + 1e-9).all()
+    hist = np.cumsum(r["group_lol"]) / (100.0 * np.arange(1, 4))
+    assert np.array_equal(hist, g["history"])
+
+
+@pytest.mark.parametrize("step", [10, 7])
+def test_reference_text_analytical_vectors(engine, step):
+    g = _ref(f"analytical_step{step}")
+    probs = engine.copt(g["cap"], g["for_rate"], float(g["step"]))
+    assert np.array_equal(probs, g["probs"])                                  # bit-identical FP64 COPT
+    lole, eue = engine.copt_indices(probs, float(g["step"]), float(g["cap"].sum()), g["load"])
+    assert abs(lole - float(g["lole"])) <= 1e-9 * lole and abs(eue - float(g["eue"])) <= 1e-9 * eue

@@ -1,0 +1,150 @@
+"""Pins the CPU oracle to the reference's own source text (CPU only).
+
+tests/golden/ref_*.npz were produced by executing run_sequential_mc / run_non_sequential_mc / add_unit_convolution /
+run_analytical of GeneratingAdequacy/PowerSystemAdequacy.jl, cut out of the reference checkout and transliterated line by
+line into Python (oracle/jl_transliterate.py; generator: scripts/make_reference_golden.py).  Here
+  * the C oracle (oracle/psra_oracle.c) and the independent hand transcription (oracle/psa_literal.py) must reproduce
+    those vectors bit for bit -- everywhere, also on the GPU box where /root/reference does not exist;
+  * when /root/reference exists, the vectors are re-derived from its text and must equal the committed ones, and the
+    three draws that tools/patched_reference.jl / the transliteration substitute sit on PSA.jl:224,243,246, once each.
+The CUDA path is held to the same vectors in tests/test_gpu_golden.py."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import jl_transliterate as J
+from oracle import oracle as O
+from oracle import psa_literal as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+have_ref = os.path.exists(os.path.join(REF, J.PSA_REL))
+SEQ_CASES = ("rts79_int", "rts79_mw", "small")
+
+
+def _g(name):
+    return np.load(os.path.join(G, f"ref_{name}.npz"))
+
+
+def _history(lole, every):
+    c = np.cumsum(lole)
+    k = np.arange(every, len(lole) + 1, every)
+    return c[k - 1] / k
+
+
+@pytest.mark.parametrize("case", SEQ_CASES)
+def test_c_oracle_reproduces_the_reference_sequential_loop(case):
+    g = _g("seq_" + case)
+    years = len(g["lole"])
+    lol, eue, ent, used = O.seq_literal(g["cap"], g["load"], years, g["dur"])
+    assert np.array_equal(lol, g["lole"]) and np.array_equal(eue, g["eue"])          # Float64, bit for bit
+    assert lol.sum() > 0 and used.max() < g["dur"].shape[1]
+    assert np.array_equal(_history(lol, 10), g["history"])                           # PSA.jl:264-266
+    assert lol.sum() / years == float(g["lole_hours_yr"])
+    tot = 0.0
+    for e in eue:
+        tot += e                                                                     # cum_eue += year_eue, in order
+    assert tot / years == float(g["eue_mwh_yr"])
+
+
+@pytest.mark.parametrize("case", SEQ_CASES)
+def test_hand_transcription_reproduces_the_reference_sequential_loop(case):
+    g = _g("seq_" + case)
+    years = len(g["lole"])
+    lole, eue, nlc, hist = L.sequential_mc(list(g["cap"]), list(g["load"]), years, [list(r) for r in g["dur"]])
+    assert lole == list(g["lole"]) and eue == list(g["eue"]) and hist == list(g["history"])
+    # deficit entries (calnlc.m) of the transcription == the C oracle's count
+    _, _, ent, _ = O.seq_literal(g["cap"], g["load"], years, g["dur"])
+    assert nlc == list(ent.astype(int))
+
+
+def test_c_oracle_and_transcription_reproduce_the_reference_non_sequential_loop():
+    g = _g("nonseq_rts79_mw")
+    q = (1.0 / g["mttf"]) / ((1.0 / g["mttf"]) + (1.0 / g["mttr"]))                  # PSA.jl:32-37
+    assert np.array_equal(q, g["for_rate"])
+    lol, eue, _ = O.nonseq_literal(g["cap"], q, g["load"], g["r"])
+    assert np.array_equal(lol, g["lole"]) and np.array_equal(eue, g["eue"])
+    assert np.array_equal(_history(lol, 100), g["history"]) and lol.sum() / len(lol) == float(g["lole_hours_yr"])
+    l2, e2, h2 = L.non_sequential_mc(list(g["cap"]), list(q), list(g["load"]), [list(r) for r in g["r"]])
+    assert l2 == list(g["lole"]) and e2 == list(g["eue"]) and h2 == list(g["history"])
+
+
+@pytest.mark.parametrize("step", [10, 7])
+def test_c_oracle_reproduces_the_reference_analytical_engine(step):
+    g = _g(f"analytical_step{step}")
+    lole, eue, probs = O.analytical(g["cap"], g["for_rate"], g["load"], float(g["step"]))
+    assert np.array_equal(probs, g["probs"])                                         # COPT, bit for bit
+    # the transliteration sums sequentially where Julia sums pairwise: the indices agree to rounding, bar 1e-9
+    assert abs(lole - float(g["lole"])) <= 1e-12 * lole and abs(eue - float(g["eue"])) <= 1e-12 * eue
+
+
+def test_random_systems_oracle_vs_transcription():
+    """20 seeded random systems: the C oracle and the hand transcription agree on every year (injected durations and
+    injected uniforms) -- two restatements written independently of each other."""
+    rng = np.random.default_rng(77)
+    for _ in range(20):
+        U = int(rng.integers(1, 12)); H = int(rng.integers(5, 200)); years = int(rng.integers(1, 25))
+        cap = rng.integers(1, 80, U).astype(np.float64)
+        mttf = rng.uniform(3.0, 300.0, U); mttr = rng.uniform(0.5, 40.0, U)
+        load = np.round(rng.uniform(0.3, 1.0, H) * cap.sum(), int(rng.integers(0, 3)))
+        K = int(4 * years * H / 3.0) + 16
+        dur = np.empty((U, K))
+        for u in range(U):
+            dur[u, 0::2] = rng.exponential(mttf[u], len(dur[u, 0::2]))
+            dur[u, 1::2] = rng.exponential(mttr[u], len(dur[u, 1::2]))
+        dur[:, 3::4] *= rng.choice([1.0, 1e-2])
+        dur = np.maximum(dur, 1e-9)
+        lol, eue, ent, _ = O.seq_literal(cap, load, years, dur)
+        a, b, c, _ = L.sequential_mc(list(cap), list(load), years, [list(r) for r in dur])
+        assert a == list(lol) and b == list(eue) and c == list(ent.astype(int))
+        q = (1.0 / mttf) / ((1.0 / mttf) + (1.0 / mttr))
+        r = rng.random((40, U))
+        nl, ne, _ = O.nonseq_literal(cap, q, load, r)
+        a, b, _ = L.non_sequential_mc(list(cap), list(q), list(load), [list(x) for x in r])
+        assert a == list(nl) and b == list(ne)
+
+
+def test_calnlc_and_matlab_sampling_transcriptions():
+    assert L.calnlc([1, 1, 0, 1, 0, 0, 1]) == 3 and L.calnlc([0, 0, 0]) == 0 and L.calnlc([0, 1, 1, 1]) == 1   # calnlc.m:22-34
+    # seq_mcsampling.m:40-74: -450 ln(0.5) = 311.9 -> UP for 312 h; -50 ln(0.9) = 5.27 -> DOWN for 6 h from hour 313
+    s, used = L.matlab_unit_series(450.0, 50.0, 400, [0.5, 0.9, 0.01, 0.3])
+    assert sum(s) == 6 and s[312:318] == [1] * 6 and s[311] == 0 and used == 3
+
+
+# ------------------------------------------------------------------------------------ needs the reference checkout
+@pytest.mark.skipif(not have_ref, reason="/root/reference is not present (GPU box)")
+def test_substitutions_hit_exactly_the_three_draws_of_the_reference():
+    src = J.load_reference(REF)
+    _, hit = J.apply_substitutions(src, J.SEQ_DRAW_SUBSTITUTIONS)
+    assert hit == [224, 243, 246]
+    # tools/patched_reference.jl performs the same three replacements on a real Julia
+    tool = open(os.path.join(ROOT, "tools", "patched_reference.jl"), encoding="utf-8").read()
+    olds = re.findall(r'must_replace\(src, "([^"]+)"', tool)
+    assert olds[:3] == [s[1] for s in J.SEQ_DRAW_SUBSTITUTIONS]
+    lines = src.split("\n")
+    for (line_no, old, _) in J.SEQ_DRAW_SUBSTITUTIONS:
+        assert src.count(old) == 1 and old in lines[line_no - 1]
+    assert olds[3] == J.SEQ_RECORD_SUBSTITUTION[0] and src.count(olds[3]) == 1
+
+
+@pytest.mark.skipif(not have_ref, reason="/root/reference is not present (GPU box)")
+def test_committed_vectors_are_what_the_reference_text_produces():
+    src = J.load_reference(REF)
+    sha = hashlib.sha256(src.encode("utf-8")).hexdigest()
+    g = _g("seq_small")
+    assert str(g["reference_sha256"]) == sha
+    res, lole, eue, hit = J.reference_sequential(src, g["cap"], g["mttf"], g["mttr"], g["load"], len(g["lole"]), g["dur"])
+    assert hit == [224, 243, 246] and lole == list(g["lole"]) and eue == list(g["eue"])
+    assert res.convergence_history == list(g["history"]) and res.method == "Sequential MC"
+    g = _g("nonseq_rts79_mw")
+    res, lole, eue, q = J.reference_non_sequential(src, g["cap"], g["mttf"], g["mttr"], g["load"], 100, g["r"][:100].reshape(-1))
+    assert lole == list(g["lole"][:100]) and eue == list(g["eue"][:100]) and q == list(g["for_rate"])
+    g = _g("analytical_step10")
+    res, probs, _ = J.reference_analytical(src, g["cap"], g["mttf"], g["mttr"], g["load"], 10.0)
+    assert probs == list(g["probs"]) and res.lole_hours_yr == float(g["lole"]) and res.eue_mwh_yr == float(g["eue"])
+    # the known answers of SURVEY.md 8c / BASELINE.md section 3 come out of the reference text
+    assert abs(res.lole_hours_yr - 9.420474608) < 1e-8 and abs(res.eue_mwh_yr - 1177.243237) < 1e-5
