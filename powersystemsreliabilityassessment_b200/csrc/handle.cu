@@ -115,6 +115,15 @@ int psra_history_prepare(psra_handle *h, int64_t nfull)
 {
     if (nfull <= 0) return PSRA_OK;
     const int64_t chunk = psra_history_block(h, nfull), blocks = (nfull + chunk - 1) / chunk;
+    const size_t pin = sizeof(double) * (size_t)nfull;
+    if (h->pin_cap < pin) {
+        if (h->h_pin) cudaFreeHost(h->h_pin);
+        h->h_pin = nullptr; h->pin_cap = 0;
+        const size_t want = std::max(pin + pin / 4, (size_t)1 << 20);
+        PSRA_CUDA(h, cudaHostAlloc(&h->h_pin, want, cudaHostAllocDefault));
+        h->pin_cap = want;
+    }
+    h->pin_pending.clear();
     return psra_reserve(h, &h->d_hist, &h->hist_cap, sizeof(double) * (size_t)nfull + sizeof(long long) * (size_t)blocks);
 }
 
@@ -131,7 +140,23 @@ int psra_history_range(psra_handle *h, const long long *d_group, int64_t nfull, 
     history_scan_kernel<<<(unsigned)(b1 - b0), HIST_THREADS, 0, stream>>>(d_group, nfull, chunk, (int)b0, d_part, group, h->hist_carry0, h->hist_idx0, d_hist);
     PSRA_CUDA(h, cudaGetLastError());
     const int64_t g0 = b0 * chunk, g1 = std::min(nfull, b1 * chunk);
-    PSRA_CUDA(h, cudaMemcpyAsync(history + g0, d_hist + g0, sizeof(double) * (size_t)(g1 - g0), cudaMemcpyDeviceToHost, stream));
+    const size_t slot = h->pin_pending.size();
+    if (slot >= sizeof(h->ev_pin) / sizeof(h->ev_pin[0]))
+        return psra_fail(h, PSRA_E_CUDA, "internal error: too many staged history ranges");
+    double *pin = (double *)h->h_pin + g0;
+    PSRA_CUDA(h, cudaMemcpyAsync(pin, d_hist + g0, sizeof(double) * (size_t)(g1 - g0), cudaMemcpyDeviceToHost, stream));
+    PSRA_CUDA(h, cudaEventRecord(h->ev_pin[slot], stream));
+    h->pin_pending.push_back({history + g0, pin, sizeof(double) * (size_t)(g1 - g0), h->ev_pin[slot]});
+    return PSRA_OK;
+}
+
+int psra_history_drain(psra_handle *h)
+{
+    for (const psra_handle::PinCopy &c : h->pin_pending) {
+        PSRA_CUDA(h, cudaEventSynchronize(c.ev));
+        memcpy(c.dst, c.src, c.bytes);
+    }
+    h->pin_pending.clear();
     return PSRA_OK;
 }
 
@@ -140,7 +165,9 @@ int psra_history_to_host(psra_handle *h, const long long *d_group, int64_t nfull
     if (nfull <= 0) return PSRA_OK;
     int rc = psra_history_prepare(h, nfull);
     if (rc) return rc;
-    return psra_history_range(h, d_group, nfull, group, 0, INT64_MAX / 2, history, h->stream);
+    rc = psra_history_range(h, d_group, nfull, group, 0, INT64_MAX / 2, history, h->stream);
+    if (rc) return rc;
+    return psra_history_drain(h);
 }
 
 extern "C" int psra_version(void) { return PSRA_VERSION; }
@@ -194,6 +221,7 @@ extern "C" int psra_create(psra_handle **out, const psra_config *cfg)
     PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     for (int i = 0; i < PSRA_MAX_CHUNKS; i++) PSRA_CUDA(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    for (int i = 0; i < PSRA_MAX_CHUNKS + 2; i++) PSRA_CUDA(h, cudaEventCreateWithFlags(&h->ev_pin[i], cudaEventDisableTiming));
     PSRA_CUDA(h, cudaEventCreate(&h->ev0));
     PSRA_CUDA(h, cudaEventCreate(&h->ev1));
     PSRA_CUDA(h, cudaMalloc(&h->d_acc, sizeof(unsigned long long) * ACC_COUNT));
@@ -217,6 +245,8 @@ extern "C" void psra_destroy(psra_handle *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < PSRA_MAX_CHUNKS; i++) if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+    for (int i = 0; i < PSRA_MAX_CHUNKS + 2; i++) if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -239,7 +269,7 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     for (int u = 0; u < U; u++) {
         PSRA_REQUIRE(h, cap_fp[u] >= 0, "negative capacity");
         // upper bound: event times are 64-bit ticks of 2^-24 h and hour indices 32 bits (a duration is < 2^56 ticks)
-        PSRA_REQUIRE(h, mttf_h[u] > 0 && mttr_h[u] > 0 && mttf_h[u] <= 1.0e8 && mttr_h[u] <= 1.0e8,
+        PSRA_REQUIRE(h, mttf_h[u] > 0 && mttr_h[u] > 0 && mttf_h[u] <= PSRA_MAX_MEAN_HOURS && mttr_h[u] <= PSRA_MAX_MEAN_HOURS,
                      "MTTF / MTTR must be positive (at most 1e8 hours)");
         total += cap_fp[u];
         if (cap_fp[u] > max_unit) max_unit = cap_fp[u];

@@ -184,6 +184,33 @@ static int first_error(psra_handle *h, const std::vector<int> &rc)
     return PSRA_OK;
 }
 
+// Running-mean history of a multi-device call: every device scans its groups (carry = LOL hours of the devices in front of
+// it) and stages them through its pinned buffer; one host thread per device, so the scans, the link transfers and the host
+// copies into the caller's buffer run side by side.
+static int multi_history(psra_handle *h, const std::vector<long long> &idx0, const std::vector<long long> &nf,
+                         const std::vector<long long> &carry, long long group, double *history)
+{
+    const int G = n_devices(h);
+    std::vector<int> rc((size_t)G, PSRA_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) {
+        if (nf[(size_t)g] <= 0) continue;
+        th.emplace_back([&, g]() {
+            psra_handle *d = device_of(h, g);
+            int r = PSRA_OK;
+            if (cudaSetDevice(d->device) != cudaSuccess) r = psra_fail(d, PSRA_E_CUDA, "cudaSetDevice failed");
+            d->hist_carry0 = carry[(size_t)g]; d->hist_idx0 = idx0[(size_t)g];
+            if (r == PSRA_OK) r = psra_history_prepare(d, nf[(size_t)g]);
+            if (r == PSRA_OK) r = psra_history_range(d, d->d_group, nf[(size_t)g], (int)group, 0, INT64_MAX / 2, history + idx0[(size_t)g], d->stream);
+            if (r == PSRA_OK) r = psra_history_drain(d);
+            d->hist_carry0 = 0; d->hist_idx0 = 0;
+            rc[(size_t)g] = r;
+        });
+    }
+    for (auto &t : th) t.join();
+    return first_error(h, rc);
+}
+
 int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t seed, int32_t init_mode, int32_t ypc,
                       const psra_seq_outputs *out, psra_seq_summary *summary)
 {
@@ -238,6 +265,10 @@ int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t se
             rc[(size_t)g] = r;
         });
     }
+    // While the devices compute, this thread touches every page of the caller's history buffer (a fresh allocation costs
+    // a page fault per 4 KB at its first write: ~2 ms per 10 MB, which would otherwise sit behind the kernels; the buffer
+    // is an output that the call overwrites completely).
+    if (out && out->history && nyears / group > 0) memset(out->history, 0, sizeof(double) * (size_t)(nyears / group));
     for (auto &t : th) t.join();
     int e = first_error(h, rc);
     if (e) return e;
@@ -285,21 +316,17 @@ int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t se
     if (out && out->history) {
         const long long nfull = nyears / group;
         long long carry = 0;
+        std::vector<long long> hi0((size_t)G), hnf((size_t)G), hcarry((size_t)G);
         for (int g = 0; g < G; g++) {
-            psra_handle *d = device_of(h, g);
-            const long long idx0 = c0[(size_t)g] * ypc / group;
+            hi0[(size_t)g] = c0[(size_t)g] * ypc / group;
             const long long ng = (cn[(size_t)g] * ypc + group - 1) / group;
-            const long long nf = std::max(0ll, std::min(ng, nfull - idx0));
-            if (nf > 0) {
-                PSRA_CUDA(h, cudaSetDevice(d->device));
-                d->hist_carry0 = carry; d->hist_idx0 = idx0;
-                int r = psra_history_prepare(d, nf);
-                if (r == PSRA_OK) r = psra_history_range(d, d->d_group, nf, (int)group, 0, INT64_MAX / 2, out->history + idx0, d->stream);
-                d->hist_carry0 = 0; d->hist_idx0 = 0;
-                if (r) return g == 0 ? r : psra_fail(h, r, "device %d: %s", d->device, d->err);
-            }
+            hnf[(size_t)g] = std::max(0ll, std::min(ng, nfull - hi0[(size_t)g]));
+            hcarry[(size_t)g] = carry;
             carry += sums[(size_t)g].sum_lol_hours;
         }
+        e = multi_history(h, hi0, hnf, hcarry, group, out->history);
+        if (e) return e;
+        PSRA_CUDA(h, cudaSetDevice(h->device));
     }
     e = sync_all(h);
     if (e) return e;
@@ -373,6 +400,7 @@ int psra_multi_nonseq_mc(psra_handle *h, int64_t sample0, int64_t n, uint64_t se
             d->multi_defer = false;
         });
     }
+    if (out && out->history && n / group > 0) memset(out->history, 0, sizeof(double) * (size_t)(n / group));   // see psra_multi_seq_mc
     for (auto &t : th) t.join();
     int e = first_error(h, rc);
     if (e) return e;
@@ -397,21 +425,17 @@ int psra_multi_nonseq_mc(psra_handle *h, int64_t sample0, int64_t n, uint64_t se
     if (out && out->history) {
         const long long nfull = n / group;
         long long carry = 0;
+        std::vector<long long> hi0((size_t)G), hnf((size_t)G), hcarry((size_t)G);
         for (int g = 0; g < G; g++) {
-            psra_handle *d = device_of(h, g);
-            const long long idx0 = i0[(size_t)g] / group;
+            hi0[(size_t)g] = i0[(size_t)g] / group;
             const long long ng = (cn[(size_t)g] + group - 1) / group;
-            const long long nf = std::max(0ll, std::min(ng, nfull - idx0));
-            if (nf > 0) {
-                PSRA_CUDA(h, cudaSetDevice(d->device));
-                d->hist_carry0 = carry; d->hist_idx0 = idx0;
-                int r = psra_history_prepare(d, nf);
-                if (r == PSRA_OK) r = psra_history_range(d, d->d_group, nf, (int)group, 0, INT64_MAX / 2, out->history + idx0, d->stream);
-                d->hist_carry0 = 0; d->hist_idx0 = 0;
-                if (r) return g == 0 ? r : psra_fail(h, r, "device %d: %s", d->device, d->err);
-            }
+            hnf[(size_t)g] = std::max(0ll, std::min(ng, nfull - hi0[(size_t)g]));
+            hcarry[(size_t)g] = carry;
             carry += sums[(size_t)g].sum_lol_hours;
         }
+        e = multi_history(h, hi0, hnf, hcarry, group, out->history);
+        if (e) return e;
+        PSRA_CUDA(h, cudaSetDevice(h->device));
     }
     e = sync_all(h);
     if (e) return e;

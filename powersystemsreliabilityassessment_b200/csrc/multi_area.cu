@@ -311,7 +311,7 @@ extern "C" int psra_multi_area_mc(psra_handle *h, const psra_area_system *sys, i
         int64_t total = 0;
         for (int u = 0; u < U; u++) {
             PSRA_REQUIRE(h, sys->cap_fp[u] >= 0, "negative capacity");
-            PSRA_REQUIRE(h, sys->mttf_h[u] > 0 && sys->mttr_h[u] > 0 && sys->mttf_h[u] <= 1.0e8 && sys->mttr_h[u] <= 1.0e8,
+            PSRA_REQUIRE(h, sys->mttf_h[u] > 0 && sys->mttr_h[u] > 0 && sys->mttf_h[u] <= PSRA_MAX_MEAN_HOURS && sys->mttr_h[u] <= PSRA_MAX_MEAN_HOURS,
                          "MTTF / MTTR must be positive (at most 1e8 hours)");
             total += sys->cap_fp[u];
             b_cap[u] = sys->cap_fp[u];

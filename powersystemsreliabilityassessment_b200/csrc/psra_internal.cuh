@@ -17,6 +17,8 @@
 #define PSRA_VERSION 1001
 
 #define ACC_COUNT_MAX 32
+// largest MTTF / MTTR: event times are 64-bit ticks of 2^-24 h and hour indices 32 bits (a duration is < 2^56 ticks)
+#define PSRA_MAX_MEAN_HOURS 1.0e8
 #define PSRA_MAX_CHUNKS 8
 struct psra_handle {
     int device = 0;
@@ -66,6 +68,12 @@ struct psra_handle {
     void *d_scratch = nullptr; size_t scratch_cap = 0;   // inputs of injected paths, tail keys
     void *d_scratch2 = nullptr; size_t scratch2_cap = 0;
     void *d_hist = nullptr; size_t hist_cap = 0;         // convergence history + its scan partials
+    // pinned staging of the history read-back: device -> pinned at link speed, then a host memcpy into the caller's
+    // (pageable) buffer; a pageable cudaMemcpyAsync is staged by the driver at a fraction of that and blocks the host
+    void *h_pin = nullptr; size_t pin_cap = 0;
+    struct PinCopy { void *dst; const void *src; size_t bytes; cudaEvent_t ev; };
+    std::vector<PinCopy> pin_pending;
+    cudaEvent_t ev_pin[PSRA_MAX_CHUNKS + 2] = {nullptr};
     unsigned long long *d_redo = nullptr;                // [1 + PSRA_REDO_CAP] redo list of the sequential sampler kernels
     // per-year ENS histogram kept for psra_tail (tail.cu): [tail_bins + 2] counts + beyond-range {count, sum}
     unsigned long long *d_tail_hist = nullptr; int64_t tail_bins = 0;
@@ -107,6 +115,8 @@ int psra_history_prepare(psra_handle *h, int64_t nfull);
 int psra_history_range(psra_handle *h, const long long *d_group, int64_t nfull, int group, int64_t b0, int64_t b1,
                        double *history, cudaStream_t stream);
 int psra_history_to_host(psra_handle *h, const long long *d_group, int64_t nfull, int group, double *history);
+// wait for the staged ranges of psra_history_range (in issue order) and copy them into the caller's buffer
+int psra_history_drain(psra_handle *h);
 // (re)allocate and zero the ENS histogram for the system currently set (tail.cu)
 int psra_tail_hist_prepare(psra_handle *h);
 // index of the last non-empty bin of the device histogram + 1 (0 = empty), synchronous (tail.cu)
@@ -178,11 +188,17 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
 // `one_bits` = 0x3F800000 in a register the compiler cannot see through (asm volatile("" : "+r"(one_bits)) outside the
 // hot loop): with it the mantissa of m is ONE three-input LOP3, (fw & 0x007FFFFF) | one_bits -- with two immediates
 // ptxas emits two.  The overload without it is for code that is not register-bound / not hot.
+// Round 2 note: I2FP here and the F2I.S64 of ticks_rn run on the XU pipe (16 lanes per SM); with four of each per Philox
+// block they cost more than their instruction count (seq_wide.cu without the F2I.S64: +20 %, without the I2FP: +12 %).
+// Computing both on the FP64 pipe instead (w as the double 2^52 + w minus 2^52; P widened to a double plus 2^52 + 2^51) is
+// bit-exact -- verified over all 2^32 draws -- but slower on B200 (DADD is a low-rate instruction: seq_fast -4.5 %, seq_wide
+// -9.5 %), and an integer-only RN_int64 needs ~10 instructions; both were dropped.
 __device__ __forceinline__ float neglog_u32(uint32_t x, uint32_t one_bits)
 {
     const uint32_t fw = __float_as_uint(__uint2float_rz(x | 1u));
     uint32_t mb;
     asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(mb) : "r"(fw), "r"(one_bits));
+    const float nk = __fadd_rn(__uint_as_float(__funnelshift_r(fw, 0x00258000u, 23)), -8388767.0f);   // e - 159 = -k
     const float t = __fadd_rn(__uint_as_float(mb), -1.5f);
     float p = -0x1.578b02p-7f;
     p = __fmaf_rn(p, t, 0x1.1d506cp-6f);
@@ -192,15 +208,20 @@ __device__ __forceinline__ float neglog_u32(uint32_t x, uint32_t one_bits)
     p = __fmaf_rn(p, t, 0x1.c72898p-3f);
     p = __fmaf_rn(p, t, -0x1.555536p-1f);
     p = __fmaf_rn(p, t, -0x1.9f324cp-2f);
-    const float nk = __fadd_rn(__uint_as_float(__funnelshift_r(fw, 0x00258000u, 23)), -8388767.0f);   // e - 159 = -k
     return __fmaf_rn(nk, -PSRA_LN2_F, p);
 }
 __device__ __forceinline__ float neglog_u32(uint32_t x) { return neglog_u32(x, 0x3F800000u); }
 
 // duration of one draw in ticks of 2^-24 h: RN_int64(max(mean_ticks * E, 1)), mean_ticks = mean * 2^24
+// RN_int64(P) of a tick duration (1 <= P < 2^56: the host bounds the means, psra_set_system)
+__device__ __forceinline__ unsigned long long ticks_rn(float P)
+{
+    return (unsigned long long)__float2ll_rn(P);
+}
+
 __device__ __forceinline__ unsigned long long dur_ticks(float mean_ticks, uint32_t x)
 {
-    return (unsigned long long)__float2ll_rn(fmaxf(__fmul_rn(mean_ticks, neglog_u32(x)), 1.0f));
+    return ticks_rn(fmaxf(__fmul_rn(mean_ticks, neglog_u32(x)), 1.0f));
 }
 
 // MATLAB next-event discretisation (Montecarlo_seq/seq_mcsampling.m:52-60): time to failure rounded to

@@ -655,6 +655,10 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
                                         c == nlaunch - 1 ? INT64_MAX / 2 : (c + 1) * hblocks_per_launch, out->history, h->stream2);
             if (rc) return rc;
         }
+        // host side of the read-back: copy every staged range into the caller's buffer as soon as it has arrived, while the
+        // later launches still compute
+        int rc = psra_history_drain(h);
+        if (rc) return rc;
     }
     // chains the sampler kernels handed back (event list of seq_fast.cu full):
     // replay each with a kernel that has no such limit, into the same accumulators and output slots.  Rare by
@@ -716,6 +720,10 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     }
     if (nlaunch > 1) PSRA_CUDA(h, cudaStreamSynchronize(h->stream2));
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    {
+        int rc = psra_history_drain(h);      // ranges staged after the launches (single launch, re-scan after replays)
+        if (rc) return rc;
+    }
     float ms = 0.f;
     PSRA_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     summary->kernel_ms = ms;
@@ -820,7 +828,7 @@ extern "C" int psra_sampler_durations(psra_handle *h, float mean_h, const uint32
 {
     if (!h) return PSRA_E_INVALID;
     PSRA_REQUIRE(h, draws && n >= 1 && (ticks || e_bits), "null argument / empty input");
-    PSRA_REQUIRE(h, mean_h > 0.0f && mean_h < 1.0e9f, "mean duration must be positive (hours)");
+    PSRA_REQUIRE(h, mean_h > 0.0f && mean_h <= (float)PSRA_MAX_MEAN_HOURS, "mean duration must be positive (at most 1e8 hours)");
     PSRA_CUDA(h, cudaSetDevice(h->device));
     int rc = psra_reserve(h, &h->d_scratch, &h->scratch_cap, (size_t)n * (sizeof(uint32_t) * 2 + sizeof(uint64_t)));
     if (rc) return rc;

@@ -96,7 +96,7 @@ __device__ __forceinline__ void wide_scatter(uint32_t tl_s, uint32_t dummy_s, ui
 template <bool kDisc>
 __device__ __forceinline__ unsigned long long wide_dur(float mean_ticks, uint32_t x, bool up_state, uint32_t one_bits)
 {
-    unsigned long long t = (unsigned long long)__float2ll_rn(fmaxf(__fmul_rn(mean_ticks, neglog_u32(x, one_bits)), 1.0f));
+    unsigned long long t = ticks_rn(fmaxf(__fmul_rn(mean_ticks, neglog_u32(x, one_bits)), 1.0f));
     if constexpr (kDisc) t = ((t + (up_state ? (1ull << 23) : ((1ull << 24) - 1ull))) >> 24) << 24;
     return t;
 }
