@@ -271,6 +271,32 @@ def bench_configs(P, rts79, sharding, eng, dev, rank, world, seed, sm_count, sm_
                      seq_wall_ms=(t1 - t0) * 1e3, tail_wall_ms=(t2 - t1) * 1e3,
                      var95_mwh=tail[0]["var"], cvar95_mwh=tail[0]["cvar"], var99_mwh=tail[1]["var"], cvar99_mwh=tail[1]["cvar"],
                      per_year_vectors_in_hbm=0, method="1 MWh bins counted in the MC kernel; one launch over the bins (csrc/tail.cu)")
+
+    # ---- the rows SURVEY.md section 8 marks "next": hourly-resampled detailed MC (tail_risk.jl:12-91, its 6-unit system) and
+    #      the multi-area simulation (AdequacyAssessmentII.jl demo: 2 areas x 5 units, one 200 MW tie), kernel times
+    import math
+    dg = [P.DetailedGenerator("Nuclear", 400.0, 0.02, 4), P.DetailedGenerator("Coal_A", 300.0, 0.04, 3),
+          P.DetailedGenerator("Coal_B", 300.0, 0.04, 3), P.DetailedGenerator("Gas", 150.0, 0.05, 2),
+          P.DetailedGenerator("Hydro_ELU", 200.0, 0.01, 2, 200.0 * 50.0), P.DetailedGenerator("Old_56", 56.0, 0.10, 0)]
+    rng = np.random.default_rng(7); hh = np.arange(1, 8761)
+    base = np.maximum(0.0, 750.0 + 300.0 * np.sin((hh - 2000) / 8760 * 2 * math.pi) + 50.0 * rng.standard_normal(8760))
+    P.schedule_maintenance(dg, [base[(w - 1) * 168:min(w * 168, 8760)].max() for w in range(1, 53)])
+    eng.detailed_mc(dg, base, base.max() * 0.05, 20_000, seed=seed)
+    yl, _, ms = eng.detailed_mc(dg, base, base.max() * 0.05, 2_000_000, seed=seed)
+    out["f1_detailed_mc"] = dict(years=2_000_000, kernel_ms=ms, years_per_s=2e6 / (ms * 1e-3), hour_steps_per_s=2e6 * 8760 / (ms * 1e-3),
+                                 mean_lole=float(yl.mean()), kernel="detailed_mc_kernel (csrc/detailed_mc.cu)")
+    ua = np.array([0] * 5 + [1] * 5); acap = np.array([400.0] * 5 + [200.0] * 5)
+    amttf = np.array([1000.0] * 5 + [900.0] * 5); amttr = np.array([50.0] * 5 + [60.0] * 5)
+    xx = np.linspace(0.0, 2.0 * np.pi, 8760)
+    loads = np.stack([np.rint(1000.0 + 500.0 * np.sin(xx)), np.rint(800.0 + 400.0 * np.sin(xx))])
+    topo = np.array([[0.0, 200.0], [200.0, 0.0]])
+    out["f3_multi_area"] = {}
+    for pol, name in ((0, "isolated"), (1, "interconnected")):
+        eng.multi_area_mc(ua, acap, amttf, amttr, loads, topo, pol, 2000, seed=seed)
+        m = eng.multi_area_mc(ua, acap, amttf, amttr, loads, topo, pol, 1_000_000, seed=seed)
+        out["f3_multi_area"][name] = dict(years=1_000_000, kernel_ms=m["kernel_ms"], years_per_s=1e6 / (m["kernel_ms"] * 1e-3),
+                                          lole=[float(v) for v in np.atleast_1d(m["lole"])], eue=[float(v) for v in np.atleast_1d(m["eue"])])
+    eng.set_system(cap, mttf, mttr); eng.set_load(load)
     return out
 
 
@@ -373,6 +399,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms, ksum_ms = t.tolist()
+    live = eng.last_counters()            # counters the kernel itself kept during the last timed launch (this run, not a profile)
     ms_per_step = dev_ms / args.steps
     value = world * Y * args.steps / (dev_ms * 1e-3)
 
@@ -463,6 +490,11 @@ def main():
                          "alg_warp_inst_per_year": w_warp, "events_per_year": events,
                          "peak_source": f"{sm_count} SMs x 4 issue/clk x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json)",
                          "ncu_issue_active_pct": prof.get("issue_active_pct"),
+                         "ncu_warp_inst_per_year": prof.get("warp_inst_per_year"),
+                         "live_counters_per_year": {"philox_blocks": live["jobs"] / Y, "generation_waves": live["waves"] / Y,
+                                                    "state_transitions": live["events"] / Y, "words_resolved_hour_by_hour": live["resolved_runs"] / Y,
+                                                    "note": "kept by the kernel in this run; the ncu_* fields are constants of the "
+                                                            "committed profile named in traffic_source"},
                          "traffic_source": prof.get("source"),
                          "hbm": {"achieved": (prof.get("dram_bytes_per_launch") or 0.0) / k_s / 1e9, "peak": peaks.get("hbm_gbs"),
                                  "unit": "GB/s", "frac": (prof.get("dram_bytes_per_launch") or 0.0) / k_s / 1e9 / float(peaks.get("hbm_gbs") or 6547.5)},

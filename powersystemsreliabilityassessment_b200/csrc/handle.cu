@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <new>
+#include <thread>
 #include <vector>
 
 #include <algorithm>
@@ -252,6 +253,25 @@ extern "C" void psra_destroy(psra_handle *h)
     delete h;
 }
 
+// run `fn(peer)` for every peer device of a multi-GPU handle on its own host thread (uploads with their synchronisation
+// are ~0.15 ms per device when done one after the other)
+template <typename F>
+static int for_each_peer(psra_handle *h, F fn)
+{
+    if (h->peers.empty()) return PSRA_OK;
+    std::vector<int> rc(h->peers.size(), PSRA_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < h->peers.size(); i++) th.emplace_back([&, i]() { rc[i] = fn(h->peers[i]); });
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < rc.size(); i++)
+        if (rc[i]) {
+            char msg[400];
+            snprintf(msg, sizeof(msg), "%.390s", h->peers[i]->err);
+            return psra_fail(h, rc[i], "device %d: %s", h->peers[i]->device, msg);
+        }
+    return cudaSetDevice(h->device) == cudaSuccess ? PSRA_OK : psra_fail(h, PSRA_E_CUDA, "cudaSetDevice failed");
+}
+
 extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const double *mttf_h,
                                const double *mttr_h, int32_t n_units)
 {
@@ -327,11 +347,8 @@ extern "C" int psra_set_system(psra_handle *h, const int32_t *cap_fp, const doub
     h->events_per_hour = rate;
     h->tab_valid = false;
     h->hist_years = 0;
-    for (psra_handle *p : h->peers) {                    // multi-GPU handle: every device holds the system
-        const int rc = psra_set_system(p, cap_fp, mttf_h, mttr_h, n_units);
-        if (rc) return psra_fail(h, rc, "device %d: %s", p->device, p->err);
-    }
-    return PSRA_OK;
+    // multi-GPU handle: every device holds the system
+    return for_each_peer(h, [&](psra_handle *p) { return psra_set_system(p, cap_fp, mttf_h, mttr_h, n_units); });
 }
 
 extern "C" int psra_set_load(psra_handle *h, const int32_t *load_fp, int32_t n_hours)
@@ -361,9 +378,5 @@ extern "C" int psra_set_load(psra_handle *h, const int32_t *load_fp, int32_t n_h
     PSRA_CUDA(h, cudaStreamSynchronize(h->stream));
     h->H = H; h->Wd = Wd; h->max_load = mx;
     h->tab_valid = false;
-    for (psra_handle *p : h->peers) {
-        const int rc = psra_set_load(p, load_fp, n_hours);
-        if (rc) return psra_fail(h, rc, "device %d: %s", p->device, p->err);
-    }
-    return PSRA_OK;
+    return for_each_peer(h, [&](psra_handle *p) { return psra_set_load(p, load_fp, n_hours); });
 }
