@@ -16,10 +16,12 @@ Rules (Julia subset used by PSA.jl:67-269):
   for i in a:b / for x in xs / for (i, x) in enumerate(xs)   -> range(a, b + 1) / same / enumerate(xs, 1)
   if / elseif / else / while / end          -> if: / elif: / else: / while: / (block closed by indentation)
   `if c; stmt; end` on one line             -> if c: stmt
-  x[i] (1-based)                            -> x[(i) - 1]
+  x[i], a[i, j], x[r], x[end] (1-based)     -> the same on JArr, a 1-based array class; [..] displays -> JArr([..])
   c ? a : b                                 -> (a if c else b)
-  &&, ||, true, false, push!(v, x), trues(n), zeros(n), Float64[], T[...]   -> and, or, True, False, v.append(x), ...
-  a .* b                                    -> jl_bmul(a, b)
+  &&, ||, !x, true, false, nothing, x -> e, push!(v, x), f!(..)   -> and, or, not x, True, False, None, lambda x: e, v.append(x), f_b(..)
+  a .* b, a .- b, x[r] .-= c, x ./= c       -> jl_bmul(a, b), jl_bsub(a, b), jl_bsub_at(x, r, c), jl_bdiv_all(x, c)
+  a:b as a value                            -> jl_range(a, b)
+  push!(v, (k = x, ...)) (named tuple)      -> v.append(dict(k=x, ...))
   g.lambda                                  -> g.lambda_               (Python keyword)
   println(...), @printf(...)                -> pass
 Arithmetic is IEEE binary64 in both languages; `log` is the platform libm (compare durations, not uniforms, across
@@ -82,46 +84,72 @@ def _split_comment(line: str) -> Tuple[str, str]:
     return line, ""
 
 
-_RANGE = re.compile(r"\bin\s+([\w.]+(?:\([^()]*\))?|\([^()]*\)):([\w.]+(?:\([^()]*\))?|\([^()]*\))")
-_INDEX = re.compile(r"(?<![\w\]])([A-Za-z_][\w.]*)\[([^\[\]]+)\]")
+_RANGE_FOR = re.compile(r"\bin\s+([\w.]+(?:\([^()]*\))?|\([^()]*\)):([\w.]+(?:\([^()]*\))?|\([^()]*\))")
+_RANGE_VAL = re.compile(r"(?<![\w\])])(\b[\w.]+|\([^()]*\)):(\([^()]*\)|[\w.]+(?:\([^()]*\))?)")
+
+
+def _wrap_array_displays(code: str) -> str:
+    """`[a, b]` / `[f(i) for i in r]` that is NOT an index (not preceded by a name, `]` or `)`) -> JArr([...])."""
+    out = []
+    stack = []                       # True for array displays, False for index brackets
+    prev = ""
+    for ch in code:
+        if ch == "[":
+            is_display = not (prev.isalnum() or prev in "_])")
+            stack.append(is_display)
+            out.append("JArr([" if is_display else "[")
+        elif ch == "]" and stack:
+            out.append("])" if stack.pop() else "]")
+        else:
+            out.append(ch)
+        if not ch.isspace():
+            prev = ch
+    return "".join(out)
 
 
 def _expr(code: str) -> str:
-    code = re.sub(r"\bFloat64\[\]", "[]", code)
-    code = re.sub(r"\b(?:Float64|Int)\[", "[", code)
+    code = re.sub(r"\b(?:Float64|Int)\[", "[", code)                           # typed array display
+    code = re.sub(r"push!\(\s*([\w.]+)\s*,\s*\(\s*(\w+)\s*=(?!=)", r"\1.append(dict(\2=", code)     # named tuple -> dict
+    code = re.sub(r"push!\(\s*([\w.]+)\s*,\s*", r"\1.append(", code)
+    code = re.sub(r"\b(\w+)!\(", r"\1_b(", code)                                # fill!(..) -> fill_b(..), popfirst! ...
     code = code.replace("&&", " and ").replace("||", " or ")
+    code = re.sub(r"===\s*nothing", " is None", code)
+    code = re.sub(r"(?<![\w=!<>])!(?!=)", " not ", code)
     code = re.sub(r"\btrue\b", "True", code)
     code = re.sub(r"\bfalse\b", "False", code)
+    code = re.sub(r"\bnothing\b", "None", code)
     code = re.sub(r"\.lambda\b", ".lambda_", code)
-    code = re.sub(r"push!\(\s*([\w.]+)\s*,\s*(.+)\)\s*$", r"\1.append(\2)", code)
-    code = re.sub(r"([\w.]+(?:\([^()]*\))?)\s*\.\*\s*([\w.]+(?:\([^()]*\))?)", r"jl_bmul(\1, \2)", code)
+    code = re.sub(r"\b(\w+)\s*->\s*", r"lambda \1: ", code)
+    code = re.sub(r"([\w.]+)\[end\]", r"\1[length(\1)]", code)
+    # broadcasting
+    code = re.sub(r"^([\w.]+)\[(.+)\]\s*\.-=\s*(.+)$", r"jl_bsub_at(\1, \2, \3)", code)
+    code = re.sub(r"^([\w.]+)\s*\./=\s*(.+)$", r"jl_bdiv_all(\1, \2)", code)
+    code = re.sub(r"([\w.]+(?:\[[^\[\]]*\])?(?:\([^()]*\))?)\s*\.\*\s*([\w.]+(?:\[[^\[\]]*\])?(?:\([^()]*\))?)", r"jl_bmul(\1, \2)", code)
+    code = re.sub(r"([\w.]+(?:\[[^\[\]]*\])?)\s*\.-\s*([\w.]+(?:\[[^\[\]]*\])?)", r"jl_bsub(\1, \2)", code)
     code = re.sub(r"for\s+\((\w+)\s*,\s*(\w+)\)\s+in\s+enumerate\(([^()]+)\)", r"for (\1, \2) in enumerate(\3, 1)", code)
-    code = _RANGE.sub(lambda m: f"in range({m.group(1)}, ({m.group(2)}) + 1)", code)
-    # 1-based indexing (comprehensions / array literals start with `[` after an operator or `=`, never after a name)
-    code = _INDEX.sub(_index_repl, code)
+    code = _RANGE_FOR.sub(lambda m: f"in range({m.group(1)}, ({m.group(2)}) + 1)", code)
+    # a range used as a value: `window = a:(b)`, `x[a:(b)]`
+    if not re.match(r"^\s*(for|if|elif|while)\b", code):
+        code = _RANGE_VAL.sub(lambda m: f"jl_range({m.group(1)}, {m.group(2)})", code)
+    code = _wrap_array_displays(code)
     # ternary (one per statement in the subset)
-    m = re.match(r"^(\s*[\w.\[\]() -]+\s*=\s*)(.+?)\s\?\s(.+?)\s:\s(.+)$", code)
-    if m:
+    m = re.match(r"^(\s*(?:return\s+|[\w.\[\]() -]+\s*=\s*))(.+?)\s\?\s(.+?)\s:\s(.+)$", code)
+    if m and "lambda" not in m.group(1):
         code = f"{m.group(1)}(({m.group(3)}) if ({m.group(2)}) else ({m.group(4)}))"
     return code
 
 
-def _index_repl(m: "re.Match[str]") -> str:
-    inner = m.group(2)
-    if inner.endswith(") - 1") and inner.startswith("("):     # already rewritten
-        return m.group(0)
-    return f"{m.group(1)}[({inner}) - 1]"
-
-
 def transliterate(jl: str) -> str:
     """Julia function text (subset above) -> Python source of the same function."""
-    # join continuation lines (a statement whose code part ends with a binary operator or an opening bracket / comma)
+    # join continuation lines (a statement whose code part ends with a binary operator, an opening bracket or a comma)
     raw = jl.split("\n")
     joined: List[str] = []
     for line in raw:
         code, _ = _split_comment(line)
-        if joined and re.search(r"[+\-*/,(]\s*$", _split_comment(joined[-1])[0]) and code.strip():
+        if joined and re.search(r"(?:[+\-*/,(=]|&&|\|\|)\s*$", _split_comment(joined[-1])[0]) and code.strip():
             joined[-1] = _split_comment(joined[-1])[0].rstrip() + " " + code.strip()
+        elif joined and code.strip().startswith(")") and _split_comment(joined[-1])[0].count("(") > _split_comment(joined[-1])[0].count(")"):
+            joined[-1] = _split_comment(joined[-1])[0].rstrip() + code.strip()
         else:
             joined.append(line)
     out: List[str] = []
@@ -134,10 +162,10 @@ def transliterate(jl: str) -> str:
             continue
         if stmt == "end":
             continue
-        m = re.match(r"^function\s+(\w+)\((.*)\)\s*$", stmt)
+        m = re.match(r"^function\s+(\w+)(!?)\((.*)\)\s*$", stmt)
         if m:
-            args = re.sub(r"::[\w.]+(\{[^{}]*\})?", "", m.group(2)).replace(";", ",")
-            out.append(f"{indent}def {m.group(1)}({_expr(args)}):")
+            args = re.sub(r"::[\w.]+(\{[^{}]*\})?", "", m.group(3)).replace(";", ",")
+            out.append(f"{indent}def {m.group(1)}{'_b' if m.group(2) else ''}({_expr(args)}):")
             continue
         if re.match(r"^(println|@printf|print)\b", stmt):
             out.append(indent + "pass")
@@ -161,6 +189,49 @@ def transliterate(jl: str) -> str:
 
 
 # ----------------------------------------------------------------------------------------------- prelude
+class JArr:
+    """Julia Vector / Matrix: 1-based, `a[i]`, `a[i, j]`, `a[r]` with a range r (a copy, as in Julia)."""
+
+    def __init__(self, items=()):
+        self.v = list(items)
+
+    def __len__(self):
+        return len(self.v)
+
+    def __iter__(self):
+        return iter(self.v)
+
+    def __getitem__(self, k):
+        if isinstance(k, tuple):
+            return self.v[k[0] - 1].v[k[1] - 1]
+        if isinstance(k, range):
+            return JArr(self.v[i - 1] for i in k)
+        return self.v[k - 1]
+
+    def __setitem__(self, k, x):
+        if isinstance(k, tuple):
+            self.v[k[0] - 1].v[k[1] - 1] = x
+        else:
+            self.v[k - 1] = x
+
+    def append(self, x):
+        self.v.append(x)
+
+    def __eq__(self, o):
+        return list(self) == list(o)
+
+    def tolist(self):
+        return [x.tolist() if isinstance(x, JArr) else x for x in self.v]
+
+
+def jarr(x):
+    """numpy / list (1-D or 2-D) -> JArr of Python floats."""
+    try:
+        return JArr(jarr(r) for r in x) if hasattr(x[0], "__len__") else JArr(float(t) for t in x)
+    except (IndexError, TypeError):
+        return JArr(x)
+
+
 class _Struct:
     _fields: Tuple[str, ...] = ()
 
@@ -171,9 +242,69 @@ class _Struct:
             setattr(self, k, v)
 
 
+def _zeros(*a):
+    dims = [int(x) for x in a if not isinstance(x, type)]
+    zero = 0 if (a and a[0] is int) else 0.0
+    if len(dims) == 2:
+        return JArr(JArr([zero] * dims[1]) for _ in range(dims[0]))
+    return JArr([zero] * dims[0])
+
+
+def _copy(x):
+    return JArr(_copy(t) if isinstance(t, JArr) else t for t in x)
+
+
+def _findfirst(f, v):
+    for i, x in enumerate(v, 1):
+        if f(x):
+            return i
+    return None
+
+
+def _bsub_at(x, r, c):
+    for i in r:
+        x[i] = x[i] - c
+
+
+def _bdiv_all(x, c):
+    for i in range(1, len(x) + 1):
+        x[i] = x[i] / c
+
+
+def _sum(x, *rest):
+    s = None
+    for v in x:
+        s = v if s is None else s + v
+    return 0.0 if s is None else s
+
+
+def _cumsum(v):
+    out, s = [], 0.0
+    for i, x in enumerate(v):
+        s = x if i == 0 else s + x
+        out.append(s)
+    return JArr(out)
+
+
+def base_prelude(rand: Callable[[], float], randn: Callable[[], float] = None) -> Dict[str, object]:
+    """Julia Base functions of the subset (arrays are JArr, 1-based)."""
+    return dict(
+        JArr=JArr, rand=rand, randn=randn, log=math.log, time=_time.time, length=len, isempty=lambda v: len(v) == 0,
+        maximum=max, minimum=min, max=max, min=min, zeros=_zeros, trues=lambda n: JArr([True] * int(n)),
+        fill=lambda v, n: JArr([v] * int(n)), fill_b=lambda x, v: [x.__setitem__(i, v) for i in range(1, len(x) + 1)] and None,
+        Int=int, Float64=float, ceil=math.ceil, floor=math.floor, round=round, abs=abs, div=lambda a, b: int(a) // int(b),
+        Inf=float("inf"), sum=_sum, cumsum=_cumsum, reverse=lambda v: JArr(reversed(list(v))), copy=_copy,
+        findfirst=_findfirst, isnothing=lambda x: x is None, popfirst_b=lambda q: q.v.pop(0), all=lambda f, v: all(f(x) for x in v),
+        sort=lambda x, by=None, rev=False: JArr(sorted(x, key=by, reverse=rev)),
+        jl_bmul=lambda a, b: JArr(x * y for x, y in zip(a, b)), jl_bsub=lambda a, b: JArr(x - y for x, y in zip(a, b)),
+        jl_bsub_at=_bsub_at, jl_bdiv_all=_bdiv_all, jl_range=lambda a, b: range(int(a), int(b) + 1),
+        enumerate=enumerate, range=range, dict=dict,
+    )
+
+
 def prelude(rand: Callable[[], float]) -> Dict[str, object]:
-    """Names the transliterated functions may use: Julia Base functions of the subset and the reference's structs
-    (field lists as at PSA.jl:20-58; the derived Generator fields come from the transliterated outer constructor)."""
+    """base_prelude + the structs of PowerSystemAdequacy.jl (field lists as at PSA.jl:20-58; the derived Generator
+    fields come from the transliterated outer constructor)."""
 
     class Generator(_Struct):
         _fields = ("id", "capacity", "mttf", "mttr", "lambda_", "mu", "for_rate")
@@ -187,26 +318,9 @@ def prelude(rand: Callable[[], float]) -> Dict[str, object]:
     class COPT(_Struct):
         _fields = ("capacity_outage", "probability")
 
-    def cumsum(v):
-        out, s = [], 0.0
-        for i, x in enumerate(v):
-            s = x if i == 0 else s + x
-            out.append(s)
-        return out
-
-    def jl_sum(x, *rest):
-        s = None
-        for v in x:
-            s = v if s is None else s + v
-        return 0.0 if s is None else s
-
-    return dict(
-        Generator=Generator, LoadModel=LoadModel, ReliabilityResult=ReliabilityResult, COPT=COPT,
-        rand=rand, log=math.log, time=_time.time, length=len, isempty=lambda v: len(v) == 0, maximum=max,
-        zeros=lambda n: [0.0] * int(n), trues=lambda n: [True] * int(n), Int=int, ceil=math.ceil, floor=math.floor,
-        round=round, abs=abs, sum=jl_sum, cumsum=cumsum, reverse=lambda v: list(reversed(v)),
-        jl_bmul=lambda a, b: [x * y for x, y in zip(a, b)], enumerate=enumerate, range=range,
-    )
+    env = base_prelude(rand)
+    env.update(Generator=Generator, LoadModel=LoadModel, ReliabilityResult=ReliabilityResult, COPT=COPT)
+    return env
 
 
 def load_reference(ref_root: str = "/root/reference") -> str:
@@ -261,9 +375,10 @@ def reference_sequential(src: str, cap, mttf, mttr, load, years: int, durations)
     make = env["Generator"]                                   # now the transliterated outer constructor (4 arguments)
     struct7 = prelude(no_rand)["Generator"]
     env["Generator"] = struct7                                # ... which calls the 7-field struct
-    gens = [make(i + 1, float(cap[i]), float(mttf[i]), float(mttr[i])) for i in range(len(cap))]
-    lm = env["LoadModel"]([float(x) for x in load], max(float(x) for x in load))
+    gens = JArr(make(i + 1, float(cap[i]), float(mttf[i]), float(mttr[i])) for i in range(len(cap)))
+    lm = env["LoadModel"](jarr(load), max(float(x) for x in load))
     res = env["run_sequential_mc"](gens, lm, int(years))
+    res.convergence_history = list(res.convergence_history)
     return res, inj.lole, inj.eue, hit
 
 
@@ -278,9 +393,10 @@ def reference_non_sequential(src: str, cap, mttf, mttr, load, iterations: int, u
     compile_functions(patched, [("Generator", 0), ("run_non_sequential_mc", 0)], env)
     make = env["Generator"]
     env["Generator"] = prelude(lambda: 0.0)["Generator"]
-    gens = [make(i + 1, float(cap[i]), float(mttf[i]), float(mttr[i])) for i in range(len(cap))]
-    lm = env["LoadModel"]([float(x) for x in load], max(float(x) for x in load))
+    gens = JArr(make(i + 1, float(cap[i]), float(mttf[i]), float(mttr[i])) for i in range(len(cap)))
+    lm = env["LoadModel"](jarr(load), max(float(x) for x in load))
     res = env["run_non_sequential_mc"](gens, lm, int(iterations))
+    res.convergence_history = list(res.convergence_history)
     return res, inj.lole, inj.eue, [g.for_rate for g in gens]
 
 
@@ -300,7 +416,127 @@ def reference_analytical(src: str, cap, mttf, mttr, load, step_size: float):
     env["add_unit_convolution"] = spy
     make = env["Generator"]
     env["Generator"] = prelude(lambda: 0.0)["Generator"]
-    gens = [make(i + 1, float(cap[i]), float(mttf[i]), float(mttr[i])) for i in range(len(cap))]
-    lm = env["LoadModel"]([float(x) for x in load], max(float(x) for x in load))
+    gens = JArr(make(i + 1, float(cap[i]), float(mttf[i]), float(mttr[i])) for i in range(len(cap)))
+    lm = env["LoadModel"](jarr(load), max(float(x) for x in load))
     res = env["run_analytical"](gens, lm, step_size=float(step_size))
     return res, list(tables[-1].probability), [g.for_rate for g in gens]
+
+
+# ------------------------------------------------------------------ the "next" rows: other files of GeneratingAdequacy/
+MULTI_AREA_REL = "GeneratingAdequacy/AdequacyAssessmentII.jl"
+TAIL_RISK_REL = "GeneratingAdequacy/tail_risk.jl"
+COMPREHENSIVE_REL = "GeneratingAdequacy/generating_adequacy_comprehensive.jl"
+
+# run_fast_sequential_simulation draws its two durations at AdequacyAssessmentII.jl:210,213 (and the initial one in the
+# Generator constructor, :25); injected per generator exactly like the three draws of run_sequential_mc
+MULTI_AREA_DRAW_SUBSTITUTIONS: Tuple[Tuple[int, str, str], ...] = (
+    (210, "g.time_to_transition += -log(rand()) * g.mttr", "g.time_to_transition += PSRA_INJ_next(g)"),
+    (213, "g.time_to_transition += -log(rand()) * g.mttf", "g.time_to_transition += PSRA_INJ_next(g)"),
+)
+
+
+def load_text(ref_root: str, rel: str) -> str:
+    with open(f"{ref_root}/{rel}", "r", encoding="utf-8") as f:
+        return f.read()
+
+
+def _multi_area_env(rand):
+    class Generator(_Struct):
+        _fields = ("id", "capacity", "mttf", "mttr", "current_state", "time_to_transition")
+
+    class Area(_Struct):
+        _fields = ("id", "name", "generators", "hourly_load")
+
+    class System(_Struct):
+        _fields = ("areas", "tie_lines", "topology_matrix")
+
+    env = base_prelude(rand)
+    env.update(Generator=Generator, Area=Area, System=System, ISOLATED=0, INTERCONNECTED=1)
+    return env
+
+
+def reference_solve_curtailment(src: str, topology, margins, policy: int):
+    """solve_curtailment_fast (AdequacyAssessmentII.jl:73-179), transliterated, text unchanged."""
+    env = _multi_area_env(lambda: 0.0)
+    compile_functions(src, [("solve_curtailment_fast", 0)], env)
+    sys_ = env["System"](JArr([]), JArr([]), jarr(topology))
+    return list(env["solve_curtailment_fast"](sys_, jarr(margins), int(policy)))
+
+
+def reference_multi_area_year(src: str, unit_area, cap, mttf, mttr, loads, topology, policy: int, durations):
+    """run_fast_sequential_simulation (AdequacyAssessmentII.jl:185-250, transliterated) for ONE year of all-up generators
+    whose durations come from per-unit lists (durations[u][0] = the initial time to failure of :25).  Returns
+    (hours with curtailment per area, curtailed energy per area, substitution lines hit)."""
+    patched, hit = apply_substitutions(src, MULTI_AREA_DRAW_SUBSTITUTIONS)
+
+    def no_rand():
+        raise RuntimeError("run_fast_sequential_simulation consumed rand() although its draws are injected")
+
+    env = _multi_area_env(no_rand)
+    used = {}
+
+    def nxt(g):
+        u = int(g.id)
+        used[u] = used.get(u, 0) + 1
+        return float(durations[u][used[u]])
+
+    env["PSRA_INJ_next"] = nxt
+    compile_functions(patched, [("solve_curtailment_fast", 0), ("run_fast_sequential_simulation", 0)], env)
+    n_areas = len(loads)
+    areas = []
+    for a in range(n_areas):
+        gens = JArr(env["Generator"](u, float(cap[u]), float(mttf[u]), float(mttr[u]), True, float(durations[u][0]))
+                    for u in range(len(cap)) if int(unit_area[u]) == a)
+        areas.append(env["Area"](a + 1, f"area{a + 1}", gens, jarr(loads[a])))
+    sys_ = env["System"](JArr(areas), JArr([]), jarr(topology))
+    res = env["run_fast_sequential_simulation"](sys_, int(policy), 1)
+    return [r["lole"] for r in res], [r["eue"] for r in res], hit
+
+
+def _detailed_env(rand, randn):
+    class Generator(_Struct):
+        _fields = ("name", "capacity", "for_rate", "maintenance_weeks", "energy_limit", "effective_q", "scheduled_outage_start",
+                   "history_q")
+
+    class COPT(_Struct):
+        _fields = ("capacity_outage", "probability")
+
+    env = base_prelude(rand, randn)
+    env.update(Generator=Generator, COPT=COPT)
+    return env
+
+
+def reference_schedule_maintenance(src_comprehensive: str, cap, maintenance_weeks, weekly_peaks):
+    """schedule_maintenance! (generating_adequacy_comprehensive.jl:86-112), transliterated; returns the start weeks."""
+    env = _detailed_env(lambda: 0.0, lambda: 0.0)
+    compile_functions(src_comprehensive, [("schedule_maintenance!", 0)], env)
+    gens = JArr(env["Generator"](f"g{i}", float(cap[i]), 0.0, int(maintenance_weeks[i]), float("inf"), 0.0, 0, JArr([]))
+                for i in range(len(cap)))
+    env["schedule_maintenance_b"](gens, jarr(weekly_peaks))
+    return [int(g.scheduled_outage_start) for g in gens]
+
+
+def reference_detailed_mc(src_tail: str, cap, for_rate, maint_start, maint_weeks, energy_limit, base_load, lfu_sigma_percent,
+                          n_years: int, unif, norm):
+    """run_detailed_mc (tail_risk.jl:12-91), transliterated, text unchanged.  unif[year][hour][unit] / norm[year][hour] are
+    replayed in the reference's own consumption order: rand() is only called for a unit that is NOT on maintenance in that
+    hour (tail_risk.jl:39-44), randn() once per hour (:60)."""
+    U, H = len(cap), len(base_load)
+
+    def uniform_stream():
+        for y in range(n_years):
+            for h in range(1, H + 1):
+                week = (h - 1) // 168 + 1
+                for u in range(U):
+                    if maint_start[u] <= week < maint_start[u] + maint_weeks[u]:
+                        continue
+                    yield float(unif[y][h - 1][u])
+
+    us = uniform_stream()
+    ns = (float(norm[y][h]) for y in range(n_years) for h in range(H))
+    env = _detailed_env(lambda: next(us), lambda: next(ns))
+    compile_functions(src_tail, [("run_detailed_mc", 0)], env)
+    gens = JArr(env["Generator"](f"g{i}", float(cap[i]), float(for_rate[i]), int(maint_weeks[i]), float(energy_limit[i]),
+                                 float(for_rate[i]), int(maint_start[i]), JArr([])) for i in range(U))
+    yl, hf = env["run_detailed_mc"](gens, jarr(base_load), float(lfu_sigma_percent), int(n_years))
+    return list(yl), list(hf)

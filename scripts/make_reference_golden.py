@@ -70,3 +70,86 @@ for step in (10.0, 7.0):
 for k, v in cases.items():
     np.savez_compressed(os.path.join(out, f"ref_{k}.npz"), reference_sha256=np.array(sha), **v)
 print("reference text sha256", sha)
+
+# ====================================================================== the "next" rows (other reference files)
+from oracle import oracle as O
+
+sha_ma = hashlib.sha256(J.load_text(ref_root, J.MULTI_AREA_REL).encode()).hexdigest()
+src_ma = J.load_text(ref_root, J.MULTI_AREA_REL)
+src_tail = J.load_text(ref_root, J.TAIL_RISK_REL)
+src_comp = J.load_text(ref_root, J.COMPREHENSIVE_REL)
+more = {}
+
+# --- solve_curtailment_fast: random margins / topologies, both policies
+rng = np.random.default_rng(4242)
+topos, margins, pols, curts = [], [], [], []
+for t in range(400):
+    n = int(rng.integers(2, 7))
+    topo = np.zeros((6, 6))
+    for i in range(n):
+        for j in range(i + 1, n):
+            if rng.random() < 0.5:
+                c = float(rng.integers(10, 300)); topo[i, j] += c; topo[j, i] += c
+    m = np.zeros(6); m[:n] = rng.integers(-400, 400, n)
+    pol = int(t & 1)
+    c = np.zeros(6); c[:n] = J.reference_solve_curtailment(src_ma, topo[:n, :n], m[:n], pol)
+    topos.append(topo); margins.append(m); pols.append(pol); curts.append(c)
+more["solve_curtailment"] = dict(n_areas=np.array([int((np.abs(m) > 0).sum() and len(m)) for m in margins]), topology=np.array(topos),
+                                 margins=np.array(margins), policy=np.array(pols), curtailment=np.array(curts))
+more["solve_curtailment"]["n_areas"] = np.array([max(2, int(np.max(np.nonzero(np.abs(t).sum(0) + np.abs(m))[0]) + 1) if (np.abs(t).sum() + np.abs(m).sum()) > 0 else 2)
+                                                 for t, m in zip(topos, margins)])
+
+# --- run_fast_sequential_simulation, one all-up year at a time, durations = the library's sampler streams of (seed; year, unit)
+def sampler_lists(seed, year, mttf, mttr, K):
+    """D[u][k]: k = 0 the initial time to failure (draw 1 of the stream; draw 0 is the initial-state draw), then repair, failure, ..."""
+    D = np.empty((len(mttf), K))
+    for u in range(len(mttf)):
+        words = []
+        for b in range((K + 1 + 3) // 4):
+            words.extend(int(w) for w in O.philox([year & 0xffffffff, year >> 32, u, b], [seed & 0xffffffff, seed >> 32]))
+        for k in range(K):
+            D[u, k] = O.duration_hours(mttf[u] if k % 2 == 0 else mttr[u], words[k + 1])
+    return D
+
+
+xx = np.linspace(0.0, 2.0 * np.pi, 8760)
+systems = {
+    "demo2": dict(unit_area=np.array([0] * 5 + [1] * 5), cap=np.array([400.0] * 5 + [200.0] * 5), mttf=np.array([1000.0] * 5 + [900.0] * 5),
+                  mttr=np.array([50.0] * 5 + [60.0] * 5), loads=np.stack([np.rint(1000.0 + 500.0 * np.sin(xx)), np.rint(800.0 + 400.0 * np.sin(xx))]),
+                  topology=np.array([[0.0, 200.0], [200.0, 0.0]])),
+    "mesh3": dict(unit_area=np.array([0] * 4 + [1] * 3 + [2] * 4), cap=np.array([300.0, 300, 200, 100, 250, 250, 150, 200, 200, 100, 50]),
+                  mttf=np.array([800.0, 900, 1100, 600, 1000, 700, 500, 950, 850, 400, 300]), mttr=np.array([60.0, 50, 40, 30, 70, 45, 25, 55, 65, 20, 15]),
+                  loads=np.stack([np.rint(620.0 + 200.0 * np.sin(xx)), np.rint(450.0 + 150.0 * np.cos(xx)), np.rint(400.0 + 120.0 * np.sin(2 * xx))]),
+                  topology=np.array([[0.0, 80.0, 60.0], [80.0, 0.0, 40.0], [60.0, 40.0, 0.0]])),
+}
+for name, sy in systems.items():
+    seed, year0, ny = 2026, 3, 4
+    out_l = np.zeros((2, ny, len(sy["loads"]))); out_e = np.zeros_like(out_l)
+    for pol in (0, 1):
+        for y in range(ny):
+            D = sampler_lists(seed, year0 + y, sy["mttf"], sy["mttr"], 96)
+            l, e, hit = J.reference_multi_area_year(src_ma, sy["unit_area"], sy["cap"], sy["mttf"], sy["mttr"], sy["loads"], sy["topology"], pol, D)
+            assert hit == [210, 213], hit
+            out_l[pol, y] = l; out_e[pol, y] = e
+    more["multi_area_" + name] = dict(seed=seed, year0=year0, lole=out_l, eue=out_e, **sy)
+    print("multi-area", name, out_l.sum(axis=1), flush=True)
+
+# --- schedule_maintenance! + run_detailed_mc on the 6-unit system of tail_risk.jl, 3 years, recorded rand() / randn()
+cap6 = np.array([400.0, 300.0, 300.0, 150.0, 200.0, 56.0]); q6 = np.array([0.02, 0.04, 0.04, 0.05, 0.01, 0.10])
+mw6 = np.array([4, 3, 3, 2, 2, 0]); el6 = np.array([np.inf, np.inf, np.inf, np.inf, 200.0 * 50.0, np.inf])
+rng = np.random.default_rng(77)
+hh = np.arange(1, 8761)
+base = np.maximum(0.0, 750.0 + 300.0 * np.sin((hh - 2000) / 8760 * 2 * np.pi) + 50.0 * rng.standard_normal(8760))
+peaks = [base[(w - 1) * 168:min(w * 168, 8760)].max() for w in range(1, 53)]
+ms6 = np.array(J.reference_schedule_maintenance(src_comp, cap6, mw6, peaks))
+unif = rng.random((3, 8760, 6)); norm = rng.standard_normal((3, 8760))
+yl, hf = J.reference_detailed_mc(src_tail, cap6, q6, ms6, mw6, el6, base, 5.0, 3, unif, norm)
+more["detailed_mc"] = dict(cap=cap6, for_rate=q6, maint_weeks=mw6, maint_start=ms6, energy_limit=el6, base_load=base, weekly_peaks=np.array(peaks),
+                           lfu_sigma_percent=5.0, unif=unif.astype(np.float32).astype(np.float64), norm=norm, yearly_lole=np.array(yl), hourly_failure_prob=np.array(hf))
+# (the uniforms are stored with binary32 precision to keep the fixture small; the run above must use the stored values)
+unif = more["detailed_mc"]["unif"]
+yl, hf = J.reference_detailed_mc(src_tail, cap6, q6, ms6, mw6, el6, base, 5.0, 3, unif, norm)
+more["detailed_mc"]["yearly_lole"] = np.array(yl); more["detailed_mc"]["hourly_failure_prob"] = np.array(hf)
+print("detailed MC", yl, "maintenance starts", ms6, flush=True)
+for k, v in more.items():
+    np.savez_compressed(os.path.join(out, f"ref_{k}.npz"), **v)

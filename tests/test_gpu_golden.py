@@ -105,3 +105,31 @@ def test_reference_text_analytical_vectors(engine, step):
     assert np.array_equal(probs, g["probs"])                                  # bit-identical FP64 COPT
     lole, eue = engine.copt_indices(probs, float(g["step"]), float(g["cap"].sum()), g["load"])
     assert abs(lole - float(g["lole"])) <= 1e-9 * lole and abs(eue - float(g["eue"])) <= 1e-9 * eue
+
+
+@pytest.mark.parametrize("name", ["demo2", "mesh3"])
+def test_reference_text_multi_area_vectors(engine, name):
+    """run_fast_sequential_simulation + solve_curtailment_fast of AdequacyAssessmentII.jl (transliterated from the reference
+    text, durations = the sampler streams) against psra_multi_area_mc: per year and area, both policies."""
+    import powersystemsreliabilityassessment_b200 as P
+    g = _ref("multi_area_" + name)
+    ny = g["lole"].shape[1]
+    for pol in (P.ISOLATED, P.INTERCONNECTED):
+        m = engine.multi_area_mc(g["unit_area"], g["cap"], g["mttf"], g["mttr"], g["loads"], g["topology"], pol, ny,
+                                 seed=int(g["seed"]), year0=int(g["year0"]), init_mode=P.INIT_ALL_UP, per_year=True)
+        assert np.array_equal(m["lol_hours"].astype(np.float64), g["lole"][pol])
+        assert np.array_equal(m["ens_fp"].astype(np.float64), g["eue"][pol])
+
+
+def test_reference_text_detailed_mc_vectors(engine):
+    """run_detailed_mc of tail_risk.jl:12-91 (transliterated, recorded rand() / randn()) against psra_detailed_eval_injected."""
+    import powersystemsreliabilityassessment_b200 as P
+    g = _ref("detailed_mc")
+    gens = [P.DetailedGenerator(f"g{i}", float(c), float(q), int(w), float(e))
+            for i, (c, q, w, e) in enumerate(zip(g["cap"], g["for_rate"], g["maint_weeks"], g["energy_limit"]))]
+    P.schedule_maintenance(gens, list(g["weekly_peaks"]))
+    assert [x.scheduled_outage_start for x in gens] == list(g["maint_start"])
+    lfu_std = float(g["base_load"].max()) * (float(g["lfu_sigma_percent"]) / 100.0)
+    yl, hf = engine.detailed_eval_injected(gens, g["base_load"], lfu_std, g["unif"], g["norm"])
+    assert np.array_equal(yl.astype(np.float64), g["yearly_lole"])
+    assert np.array_equal(hf.astype(np.float64) / len(yl), g["hourly_failure_prob"])

@@ -148,3 +148,65 @@ def test_committed_vectors_are_what_the_reference_text_produces():
     assert probs == list(g["probs"]) and res.lole_hours_yr == float(g["lole"]) and res.eue_mwh_yr == float(g["eue"])
     # the known answers of SURVEY.md 8c / BASELINE.md section 3 come out of the reference text
     assert abs(res.lole_hours_yr - 9.420474608) < 1e-8 and abs(res.eue_mwh_yr - 1177.243237) < 1e-5
+
+
+# ============================================================ the "next" rows: AdequacyAssessmentII.jl, tail_risk.jl, comprehensive.jl
+def test_c_oracle_reproduces_the_reference_max_flow_curtailment():
+    """solve_curtailment_fast (AdequacyAssessmentII.jl:73-179, transliterated from the reference text) on 400 random
+    margin / topology cases, both policies: the C oracle returns the same curtailments, bit for bit."""
+    g = _g("solve_curtailment")
+    for topo, m, pol, cur, n in zip(g["topology"], g["margins"], g["policy"], g["curtailment"], g["n_areas"]):
+        n = int(n)
+        got = O.solve_curtailment(np.ascontiguousarray(topo[:n, :n]), m[:n], int(pol))
+        assert np.array_equal(got, cur[:n]), (topo[:n, :n], m[:n], pol)
+    assert (g["curtailment"] > 0).any() and (g["policy"] == 1).any()
+
+
+@pytest.mark.parametrize("name", ["demo2", "mesh3"])
+def test_c_oracle_reproduces_the_reference_multi_area_years(name):
+    """run_fast_sequential_simulation (AdequacyAssessmentII.jl:185-250, transliterated; its two duration draws at :210,213 and
+    the constructor's at :25 injected with the sampler durations of the (seed; year, unit) streams): hours with curtailment
+    and curtailed energy per area and year == the C oracle driven by the same streams, both policies."""
+    g = _g("multi_area_" + name)
+    ny = g["lole"].shape[1]
+    for pol in (0, 1):
+        lol, eue = O.multi_area_philox(g["unit_area"], g["cap"], g["mttf"], g["mttr"], g["loads"], g["topology"], pol,
+                                       int(g["seed"]), int(g["year0"]), ny, init_mode=0)
+        assert np.array_equal(lol, g["lole"][pol]) and np.array_equal(eue, g["eue"][pol])
+    assert g["lole"].sum() > 0 and not np.array_equal(g["eue"][0], g["eue"][1])      # the ties do carry support
+
+
+def test_c_oracle_reproduces_the_reference_detailed_mc_and_maintenance_schedule():
+    """schedule_maintenance! (generating_adequacy_comprehensive.jl:86-112) and run_detailed_mc (tail_risk.jl:12-91), both
+    transliterated from the reference text; rand() / randn() replayed in the reference's own consumption order (no draw for
+    a unit on maintenance).  The oracle's injected layout is per (year, hour, unit) -- the same values reach the same
+    units, so the yearly LOLE counts and the hourly failure probabilities must be identical."""
+    import powersystemsreliabilityassessment_b200.api as A
+    g = _g("detailed_mc")
+    assert O.schedule_maintenance(g["cap"], g["maint_weeks"], g["weekly_peaks"]) == list(g["maint_start"])
+    gens = [A.DetailedGenerator(f"g{i}", float(c), float(q), int(w), float(e))
+            for i, (c, q, w, e) in enumerate(zip(g["cap"], g["for_rate"], g["maint_weeks"], g["energy_limit"]))]
+    A.schedule_maintenance(gens, list(g["weekly_peaks"]))                            # the product's host function
+    assert [x.scheduled_outage_start for x in gens] == list(g["maint_start"])
+    lfu_std = float(g["base_load"].max()) * (float(g["lfu_sigma_percent"]) / 100.0)   # tail_risk.jl:22
+    yl, hf = O.detailed_mc_injected(g["cap"], g["for_rate"], g["maint_start"], g["maint_weeks"], g["energy_limit"], g["base_load"],
+                                    lfu_std, g["unif"], g["norm"])
+    assert np.array_equal(yl, g["yearly_lole"]) and yl.sum() > 0
+    assert np.array_equal(hf / len(yl), g["hourly_failure_prob"])
+
+
+@pytest.mark.skipif(not have_ref, reason="/root/reference is not present (GPU box)")
+def test_next_row_vectors_are_what_the_reference_text_produces():
+    src_ma = J.load_text(REF, J.MULTI_AREA_REL)
+    _, hit = J.apply_substitutions(src_ma, J.MULTI_AREA_DRAW_SUBSTITUTIONS)
+    assert hit == [210, 213]
+    g = _g("solve_curtailment")
+    for k in range(0, 400, 7):
+        n = int(g["n_areas"][k])
+        got = J.reference_solve_curtailment(src_ma, g["topology"][k][:n, :n], g["margins"][k][:n], int(g["policy"][k]))
+        assert got == list(g["curtailment"][k][:n])
+    g = _g("detailed_mc")
+    assert J.reference_schedule_maintenance(J.load_text(REF, J.COMPREHENSIVE_REL), g["cap"], g["maint_weeks"], g["weekly_peaks"]) == list(g["maint_start"])
+    yl, hf = J.reference_detailed_mc(J.load_text(REF, J.TAIL_RISK_REL), g["cap"], g["for_rate"], g["maint_start"], g["maint_weeks"],
+                                     g["energy_limit"], g["base_load"], float(g["lfu_sigma_percent"]), 1, g["unif"][:1], g["norm"][:1])
+    assert yl == [float(g["yearly_lole"][0])]
