@@ -22,6 +22,7 @@ Rules (Julia subset used by PSA.jl:67-269):
   a .* b, a .- b, x[r] .-= c, x ./= c       -> jl_bmul(a, b), jl_bsub(a, b), jl_bsub_at(x, r, c), jl_bdiv_all(x, c)
   a:b as a value                            -> jl_range(a, b)
   push!(v, (k = x, ...)) (named tuple)      -> v.append(dict(k=x, ...))
+  collect(a:s:b), T[] (struct type), x = @sprintf(..)   -> jl_collect_range(a, s, b), JArr([]), x = ""
   g.lambda                                  -> g.lambda_               (Python keyword)
   println(...), @printf(...)                -> pass
 Arithmetic is IEEE binary64 in both languages; `log` is the platform libm (compare durations, not uniforms, across
@@ -63,15 +64,20 @@ def apply_substitutions(src: str, subs: Iterable[Tuple[int, str, str]]) -> Tuple
 
 
 def extract_function(src: str, name: str, nth: int = 0) -> str:
-    """Text of the nth top-level `function name(...) ... end` (column 0 to the matching column-0 `end`)."""
-    starts = [m.start() for m in re.finditer(rf"^function {re.escape(name)}\(", src, flags=re.M)]
-    if len(starts) <= nth:
+    """Text of the nth `function name(...) ... end`: from its `function` line to the `end` at the same indentation (a
+    constructor inside a struct block is indented; the text is returned de-indented)."""
+    ms = list(re.finditer(rf"^([ \t]*)function {re.escape(name)}\(", src, flags=re.M))
+    if len(ms) <= nth:
         raise ValueError(f"function {name} (#{nth}) not found in the reference text")
-    rest = src[starts[nth]:]
-    m = re.search(r"^end\s*$", rest, flags=re.M)
+    ind = ms[nth].group(1)
+    rest = src[ms[nth].start():]
+    m = re.search(rf"^{ind}end\s*$", rest, flags=re.M)
     if not m:
         raise ValueError(f"no closing `end` for function {name}")
-    return rest[:m.end()]
+    text = rest[:m.end()]
+    if ind:
+        text = "\n".join(l[len(ind):] if l.startswith(ind) else l for l in text.split("\n"))
+    return text
 
 
 def _split_comment(line: str) -> Tuple[str, str]:
@@ -109,6 +115,9 @@ def _wrap_array_displays(code: str) -> str:
 
 def _expr(code: str) -> str:
     code = re.sub(r"\b(?:Float64|Int)\[", "[", code)                           # typed array display
+    code = re.sub(r"(?<![\w.])[A-Z][A-Za-z0-9]*\[\]", "[]", code)               # empty array of a struct type
+    code = re.sub(r"=\s*@sprintf\(.*\)\s*$", '= ""', code)                      # strings that only feed printing
+    code = re.sub(r"collect\(\s*([\w.]+)\s*:\s*([\w.]+)\s*:\s*([\w.]+)\s*\)", r"jl_collect_range(\1, \2, \3)", code)
     code = re.sub(r"push!\(\s*([\w.]+)\s*,\s*\(\s*(\w+)\s*=(?!=)", r"\1.append(dict(\2=", code)     # named tuple -> dict
     code = re.sub(r"push!\(\s*([\w.]+)\s*,\s*", r"\1.append(", code)
     code = re.sub(r"\b(\w+)!\(", r"\1_b(", code)                                # fill!(..) -> fill_b(..), popfirst! ...
@@ -174,6 +183,10 @@ def transliterate(jl: str) -> str:
         if m:
             out.append(f"{indent}if {_expr(m.group(1))}: {_expr(m.group(2))}")
             continue
+        m = re.match(r"^for\s+(.+?);\s*(.+?);\s*end$", stmt)          # one-line for
+        if m:
+            out.append(f"{indent}{_expr('for ' + m.group(1))}: {_expr(m.group(2))}")
+            continue
         m = re.match(r"^(if|elseif|while|for)\s+(.+)$", stmt)
         if m:
             kw = "elif" if m.group(1) == "elseif" else m.group(1)
@@ -181,6 +194,9 @@ def transliterate(jl: str) -> str:
             continue
         if stmt == "else":
             out.append(indent + "else:")
+            continue
+        if re.match(r"^new\(", stmt):                                # inner constructor: the value of the block
+            out.append(indent + "return " + _expr(stmt))
             continue
         # several statements on one line
         parts = [p.strip() for p in stmt.split(";") if p.strip()]
@@ -298,7 +314,8 @@ def base_prelude(rand: Callable[[], float], randn: Callable[[], float] = None) -
         sort=lambda x, by=None, rev=False: JArr(sorted(x, key=by, reverse=rev)),
         jl_bmul=lambda a, b: JArr(x * y for x, y in zip(a, b)), jl_bsub=lambda a, b: JArr(x - y for x, y in zip(a, b)),
         jl_bsub_at=_bsub_at, jl_bdiv_all=_bdiv_all, jl_range=lambda a, b: range(int(a), int(b) + 1),
-        enumerate=enumerate, range=range, dict=dict,
+        enumerate=enumerate, range=range, dict=dict, mod=lambda a, b: math.fmod(a, b) if (a >= 0) == (b >= 0) else math.fmod(math.fmod(a, b) + b, b),
+        jl_collect_range=lambda a, st, b: JArr(a + i * st for i in range(int(math.floor((b - a) / st + 1e-12)) + 1)),
     )
 
 
@@ -540,3 +557,49 @@ def reference_detailed_mc(src_tail: str, cap, for_rate, maint_start, maint_weeks
                                  float(for_rate[i]), int(maint_start[i]), JArr([])) for i in range(U))
     yl, hf = env["run_detailed_mc"](gens, jarr(base_load), float(lfu_sigma_percent), int(n_years))
     return list(yl), list(hf)
+
+
+# ---- frequency & duration recursion (generating_adequacy_frequency.jl) and the stand-alone COPT demo (generating_adequacy_assessment.jl)
+FREQUENCY_REL = "GeneratingAdequacy/generating_adequacy_frequency.jl"
+ASSESSMENT_REL = "GeneratingAdequacy/generating_adequacy_assessment.jl"
+
+
+def reference_fd(src_freq: str, cap, mtbf_h, mttr_h, peak_load: float):
+    """GeneratorFD constructor (:21-32), add_unit_educational! (:53-147) and evaluate_risk (:155-186), transliterated.
+    Returns (outage levels, cumulative probabilities, cumulative frequencies, (LOLE hours, LOLF, LOLD))."""
+
+    class GeneratorFD(_Struct):
+        _fields = ("name", "capacity", "mtbf", "mttr", "lambda_", "mu", "p", "q")
+
+    class COPT(_Struct):
+        _fields = ("outage_levels", "cum_prob", "cum_freq")
+
+    env = base_prelude(lambda: 0.0)
+    env.update(COPT=COPT, new=GeneratorFD)
+    compile_functions(src_freq, [("GeneratorFD", 0), ("add_unit_educational!", 0), ("evaluate_risk", 0)], env)
+    copt = COPT(JArr([0.0]), JArr([1.0]), JArr([0.0]))                      # run_educational_demo, :195
+    total = 0.0
+    for i in range(len(cap)):
+        u = env["GeneratorFD"](f"Unit {i + 1}", float(cap[i]), float(mtbf_h[i]), float(mttr_h[i]))
+        copt = env["add_unit_educational_b"](copt, u)
+        total += u.capacity
+    return list(copt.outage_levels), list(copt.cum_prob), list(copt.cum_freq), tuple(env["evaluate_risk"](copt, float(peak_load), total))
+
+
+def reference_gaa(src_assess: str, cap, for_rate, step: float, ldc):
+    """add_unit (:30-107) and calculate_indices (:113-146) of generating_adequacy_assessment.jl, transliterated."""
+
+    class Generator(_Struct):
+        _fields = ("capacity", "for_rate", "name")
+
+    class COPT(_Struct):
+        _fields = ("capacity_outage", "probability")
+
+    env = base_prelude(lambda: 0.0)
+    env.update(Generator=Generator, COPT=COPT)
+    compile_functions(src_assess, [("add_unit", 0), ("calculate_indices", 0)], env)
+    copt = COPT(JArr([0.0]), JArr([1.0]))
+    for i in range(len(cap)):
+        copt = env["add_unit"](copt, Generator(float(cap[i]), float(for_rate[i]), f"G{i + 1}"), float(step))
+    res = env["calculate_indices"](copt, jarr(ldc))
+    return list(copt.probability), tuple(res)

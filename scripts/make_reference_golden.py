@@ -153,3 +153,27 @@ more["detailed_mc"]["yearly_lole"] = np.array(yl); more["detailed_mc"]["hourly_f
 print("detailed MC", yl, "maintenance starts", ms6, flush=True)
 for k, v in more.items():
     np.savez_compressed(os.path.join(out, f"ref_{k}.npz"), **v)
+
+# --- frequency & duration recursion and the stand-alone COPT demo
+src_fd = J.load_text(ref_root, J.FREQUENCY_REL); src_gaa = J.load_text(ref_root, J.ASSESSMENT_REL)
+rng = np.random.default_rng(5150)
+fd_cases = [(np.array([16.0, 16.0]), np.array([4380.0, 4380.0]), np.array([89.39, 89.39]), 20.0)]        # the file's own demo (:199-216)
+for _ in range(3):
+    U = int(rng.integers(3, 7)); c = rng.integers(5, 60, U).astype(np.float64)
+    fd_cases.append((c, rng.uniform(800.0, 5000.0, U), rng.uniform(20.0, 200.0, U), float(np.rint(0.7 * c.sum()))))
+fd = {}
+for k, (c, a, b, peak) in enumerate(fd_cases):
+    lv, Pc, Fc, risk = J.reference_fd(src_fd, c, a, b, peak)
+    fd.update({f"cap{k}": c, f"mtbf{k}": a, f"mttr{k}": b, f"peak{k}": peak, f"P{k}": np.array(Pc), f"F{k}": np.array(Fc), f"risk{k}": np.array(risk)})
+    print("F&D", k, risk, flush=True)
+np.savez_compressed(os.path.join(out, "ref_fd.npz"), n=len(fd_cases), **fd)
+gaa = {}
+gaa_cases = [(np.array([50.0, 50.0, 100.0, 100.0, 200.0]), np.array([0.02, 0.02, 0.03, 0.03, 0.05]), 10.0),
+             (np.array([40.0, 45.0, 75.0, 120.0, 33.0, 12.0]), np.array([0.015, 0.02, 0.04, 0.06, 0.08, 0.1]), 7.0),
+             (np.array([25.0, 25.0, 60.0, 110.0]), np.array([0.02, 0.02, 0.03, 0.04]), 5.0)]
+for k, (c, q, step) in enumerate(gaa_cases):
+    ldc = np.sort(rng.uniform(0.35, 0.95, 300) * c.sum())[::-1].copy()
+    probs, idx = J.reference_gaa(src_gaa, c, q, step, ldc)
+    gaa.update({f"cap{k}": c, f"q{k}": q, f"step{k}": step, f"ldc{k}": ldc, f"probs{k}": np.array(probs), f"idx{k}": np.array(idx)})
+    print("GAA", k, idx, flush=True)
+np.savez_compressed(os.path.join(out, "ref_gaa.npz"), n=len(gaa_cases), **gaa)

@@ -133,3 +133,18 @@ def test_reference_text_detailed_mc_vectors(engine):
     yl, hf = engine.detailed_eval_injected(gens, g["base_load"], lfu_std, g["unif"], g["norm"])
     assert np.array_equal(yl.astype(np.float64), g["yearly_lole"])
     assert np.array_equal(hf.astype(np.float64) / len(yl), g["hourly_failure_prob"])
+
+
+def test_reference_text_fd_and_copt_demo_vectors(engine):
+    """F&D recursion (generating_adequacy_frequency.jl) and the stand-alone COPT indices (generating_adequacy_assessment.jl),
+    vectors from the transliterated reference text, against psra_fd_recursion / psra_copt_indices_strict."""
+    from powersystemsreliabilityassessment_b200 import evaluate_risk
+    g = _ref("fd")
+    for k in range(int(g["n"])):
+        P, F = engine.fd_recursion(g[f"cap{k}"], g[f"mtbf{k}"], g[f"mttr{k}"])
+        assert np.array_equal(P, g[f"P{k}"]) and np.array_equal(F, g[f"F{k}"])           # FP64 tables, bit for bit
+        assert tuple(evaluate_risk(P, F, float(g[f"peak{k}"]), float(g[f"cap{k}"].sum()))) == tuple(g[f"risk{k}"])
+    g = _ref("gaa")
+    for k in range(int(g["n"])):
+        lole, eue = engine.copt_indices_strict(g[f"probs{k}"], float(g[f"step{k}"]), g[f"ldc{k}"])
+        assert abs(lole - g[f"idx{k}"][0]) <= 1e-9 * lole and abs(eue - g[f"idx{k}"][1]) <= 1e-9 * eue

@@ -210,3 +210,23 @@ def test_next_row_vectors_are_what_the_reference_text_produces():
     yl, hf = J.reference_detailed_mc(J.load_text(REF, J.TAIL_RISK_REL), g["cap"], g["for_rate"], g["maint_start"], g["maint_weeks"],
                                      g["energy_limit"], g["base_load"], float(g["lfu_sigma_percent"]), 1, g["unif"][:1], g["norm"][:1])
     assert yl == [float(g["yearly_lole"][0])]
+
+
+def test_c_oracle_reproduces_the_reference_fd_recursion_and_copt_demo():
+    """generating_adequacy_frequency.jl (GeneratorFD constructor, add_unit_educational!, evaluate_risk) and
+    generating_adequacy_assessment.jl (add_unit, calculate_indices), transliterated from the reference text: cumulative
+    probability / frequency tables bit for bit, the risk indices and the COPT indices; the file's own demo gives the
+    346.9045 / 3.8416 / 90.3022 of SURVEY.md 8c."""
+    g = _g("fd")
+    for k in range(int(g["n"])):
+        P, F = O.fd_build(g[f"cap{k}"], g[f"mtbf{k}"], g[f"mttr{k}"])
+        assert np.array_equal(P, g[f"P{k}"]) and np.array_equal(F, g[f"F{k}"])
+        risk = O.fd_evaluate(P, F, float(g[f"peak{k}"]), float(g[f"cap{k}"].sum()))
+        assert tuple(risk) == tuple(g[f"risk{k}"])
+    assert abs(g["risk0"][0] - 346.9045) < 5e-5 and abs(g["risk0"][1] - 3.8416) < 5e-5 and abs(g["risk0"][2] - 90.3022) < 5e-5
+    g = _g("gaa")
+    for k in range(int(g["n"])):
+        probs = O.gaa_build(g[f"cap{k}"], g[f"q{k}"], float(g[f"step{k}"]))
+        assert np.array_equal(probs, g[f"probs{k}"])
+        lole, eue = O.gaa_indices(probs, float(g[f"step{k}"]), g[f"ldc{k}"])
+        assert abs(lole - g[f"idx{k}"][0]) <= 1e-12 * lole and abs(eue - g[f"idx{k}"][1]) <= 1e-12 * eue
