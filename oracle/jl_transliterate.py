@@ -179,6 +179,10 @@ def transliterate(jl: str) -> str:
         if re.match(r"^(println|@printf|print)\b", stmt):
             out.append(indent + "pass")
             continue
+        m = re.match(r"^if\s+(.+?)\s+(break|continue)\s+end$", stmt)   # `if c break end`
+        if m:
+            out.append(f"{indent}if {_expr(m.group(1))}: {m.group(2)}")
+            continue
         m = re.match(r"^if\s+(.+?);\s*(.+?);\s*end$", stmt)           # one-line if
         if m:
             out.append(f"{indent}if {_expr(m.group(1))}: {_expr(m.group(2))}")
@@ -309,7 +313,7 @@ def base_prelude(rand: Callable[[], float], randn: Callable[[], float] = None) -
         maximum=max, minimum=min, max=max, min=min, zeros=_zeros, trues=lambda n: JArr([True] * int(n)),
         fill=lambda v, n: JArr([v] * int(n)), fill_b=lambda x, v: [x.__setitem__(i, v) for i in range(1, len(x) + 1)] and None,
         Int=int, Float64=float, ceil=math.ceil, floor=math.floor, round=round, abs=abs, div=lambda a, b: int(a) // int(b),
-        Inf=float("inf"), sum=_sum, cumsum=_cumsum, reverse=lambda v: JArr(reversed(list(v))), copy=_copy,
+        Inf=float("inf"), exp=math.exp, sum=_sum, cumsum=_cumsum, reverse=lambda v: JArr(reversed(list(v))), copy=_copy,
         findfirst=_findfirst, isnothing=lambda x: x is None, popfirst_b=lambda q: q.v.pop(0), all=lambda f, v: all(f(x) for x in v),
         sort=lambda x, by=None, rev=False: JArr(sorted(x, key=by, reverse=rev)),
         jl_bmul=lambda a, b: JArr(x * y for x, y in zip(a, b)), jl_bsub=lambda a, b: JArr(x - y for x, y in zip(a, b)),
@@ -603,3 +607,69 @@ def reference_gaa(src_assess: str, cap, for_rate, step: float, ldc):
         copt = env["add_unit"](copt, Generator(float(cap[i]), float(for_rate[i]), f"G{i + 1}"), float(step))
     res = env["calculate_indices"](copt, jarr(ldc))
     return list(copt.probability), tuple(res)
+
+
+# ---- Markov_process.jl is a script: two of its top-level blocks, cut out by their first / last line and executed as they stand
+MARKOV_REL = "GeneratingAdequacy/Markov_process.jl"
+
+
+def extract_block(src: str, first: str, last: str, first_line: int = 0) -> str:
+    """The lines from the one that starts with `first` to the next one that is exactly `last` (top-level script code)."""
+    lines = src.split("\n")
+    i0 = next(i for i, l in enumerate(lines) if l.startswith(first))
+    if first_line and i0 + 1 != first_line:
+        raise ValueError(f"reference text changed: `{first}` is on line {i0 + 1}, expected {first_line}")
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].rstrip() == last)
+    return "\n".join(lines[i0:i1 + 1])
+
+
+def reference_failure_times(src_markov: str, lam: float, dt: float, max_time: float, n: int, uniforms):
+    """Markov_process.jl:46-60 (the constant-hazard experiment), rand() replayed from uniforms[component][k]."""
+    state = {"i": -1, "k": 0}
+
+    def rand():
+        k = state["k"]; state["k"] = k + 1
+        return float(uniforms[state["i"]][k])
+
+    env = base_prelude(rand)
+    block = extract_block(src_markov, "failure_times = Float64[]", "end", 46)
+    code = transliterate(block)
+    # the component index is implicit in the reference (one stream); the replay needs it: count the outer loop's iterations
+    code = code.replace("    t = 0.0\n", "    PSRA_INJ_component()\n    t = 0.0\n", 1)
+
+    def nxt():
+        state["i"] += 1; state["k"] = 0
+
+    env.update({"λ": float(lam), "dt": float(dt), "max_time": max_time, "N_samples": int(n), "PSRA_INJ_component": nxt})
+    exec(compile(code, "<transliterated Markov_process.jl:46-60>", "exec"), env)
+    return list(env["failure_times"]), code
+
+
+def reference_dtmc_capacity(src_markov: str, uniforms):
+    """Markov_process.jl:153-195 (five generators, hourly two-state DTMC, 1000 hours) with the script's own unit data;
+    rand() replayed from uniforms[hour][generator].  Returns (capacity series, mttfs, mttrs, capacities)."""
+    it = (float(x) for row in uniforms for x in row)
+    env = base_prelude(lambda: next(it))
+    block = extract_block(src_markov, "num_gens = 5", "end", 153)
+    # the block holds two top-level loops; take everything up to the end of the simulation loop
+    lines = src_markov.split("\n")
+    i0 = next(i for i, l in enumerate(lines) if l.startswith("num_gens = 5"))
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith("    system_available_capacity[t] = current_cap"))
+    code = transliterate("\n".join(lines[i0:i1 + 2]))
+    exec(compile(code, "<transliterated Markov_process.jl:153-195>", "exec"), env)
+    return list(env["system_available_capacity"]), list(env["gen_mttfs"]), list(env["gen_mttrs"]), [float(c) for c in env["gen_capacities"]]
+
+
+def reference_detailed_analytical(src_tail: str, src_comprehensive: str, cap, for_rate, maint_start, maint_weeks, energy_limit,
+                                  base_load, lfu_sigma_percent: float):
+    """run_detailed_analytical (tail_risk.jl:96-141) with add_unit / get_lfu_distribution / calculate_expected_generation /
+    update_elu! of generating_adequacy_comprehensive.jl, all transliterated, text unchanged.
+    Returns (sum of the hourly risk, hourly risk profile, effective FOR per unit, history of the effective FOR per unit)."""
+    env = _detailed_env(lambda: 0.0, lambda: 0.0)
+    compile_functions(src_comprehensive, [("add_unit", 0), ("get_lfu_distribution", 0), ("calculate_expected_generation", 0),
+                                          ("update_elu!", 0)], env)
+    compile_functions(src_tail, [("run_detailed_analytical", 0)], env)
+    gens = JArr(env["Generator"](f"g{i}", float(cap[i]), float(for_rate[i]), int(maint_weeks[i]), float(energy_limit[i]),
+                                 float(for_rate[i]), int(maint_start[i]), JArr([float(for_rate[i])])) for i in range(len(cap)))
+    total, profile = env["run_detailed_analytical"](gens, jarr(base_load), float(lfu_sigma_percent))
+    return total, list(profile), [g.effective_q for g in gens], [list(g.history_q) for g in gens]

@@ -177,3 +177,25 @@ for k, (c, q, step) in enumerate(gaa_cases):
     gaa.update({f"cap{k}": c, f"q{k}": q, f"step{k}": step, f"ldc{k}": ldc, f"probs{k}": np.array(probs), f"idx{k}": np.array(idx)})
     print("GAA", k, idx, flush=True)
 np.savez_compressed(os.path.join(out, "ref_gaa.npz"), n=len(gaa_cases), **gaa)
+
+# --- Markov_process.jl (a script): the constant-hazard experiment (:46-60) and the five-generator DTMC (:153-195)
+src_mk = J.load_text(ref_root, J.MARKOV_REL)
+rng = np.random.default_rng(808)
+u_dt = rng.random((1000, 5)).astype(np.float32).astype(np.float64)
+series, mf, mr, cp = J.reference_dtmc_capacity(src_mk, u_dt)
+lam_ft = 1.0 / 2500.0
+u_ft = rng.random((40, 5002)).astype(np.float32).astype(np.float64)
+ft, _ = J.reference_failure_times(src_mk, lam_ft, 1.0, 5000, 40, u_ft)
+np.savez_compressed(os.path.join(out, "ref_markov.npz"), dtmc_uniforms=u_dt, dtmc_capacity=np.array(series), mttf=np.array(mf), mttr=np.array(mr),
+                    cap=np.array(cp), ft_lambda=lam_ft, ft_uniforms=u_ft, failure_times=np.array(ft))
+print("Markov: DTMC mean capacity", np.mean(series), "failure times", len(ft), "of 40", flush=True)
+
+# --- run_detailed_analytical (tail_risk.jl:96-141) with update_elu! / calculate_expected_generation / add_unit of comprehensive.jl
+d = np.load(os.path.join(out, "ref_detailed_mc.npz"))
+import time as _t
+_t0 = _t.time()
+tot, prof, qeff, hist = J.reference_detailed_analytical(src_tail, src_comp, d["cap"], d["for_rate"], d["maint_start"], d["maint_weeks"],
+                                                        d["energy_limit"], d["base_load"], 5.0)
+np.savez_compressed(os.path.join(out, "ref_detailed_analytical.npz"), total=tot, profile=np.array(prof), effective_q=np.array(qeff),
+                    history_q_elu=np.array(hist[4]))
+print("detailed analytical: total risk", tot, "effective q", qeff, "ELU history", hist[4], f"({_t.time() - _t0:.0f} s)", flush=True)

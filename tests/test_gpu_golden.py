@@ -148,3 +148,24 @@ def test_reference_text_fd_and_copt_demo_vectors(engine):
     for k in range(int(g["n"])):
         lole, eue = engine.copt_indices_strict(g[f"probs{k}"], float(g[f"step{k}"]), g[f"ldc{k}"])
         assert abs(lole - g[f"idx{k}"][0]) <= 1e-9 * lole and abs(eue - g[f"idx{k}"][1]) <= 1e-9 * eue
+
+
+def test_reference_text_markov_script_vectors(engine):
+    g = _ref("markov")
+    assert np.array_equal(engine.dtmc_capacity(g["mttf"], g["mttr"], g["cap"], g["dtmc_uniforms"]), g["dtmc_capacity"])
+    ft = engine.failure_times(float(g["ft_lambda"]), len(g["ft_uniforms"]), 1.0, 5000.0, uniforms=g["ft_uniforms"])
+    assert np.array_equal(ft, g["failure_times"])
+
+
+def test_reference_text_detailed_analytical_vectors(engine):
+    """run_detailed_analytical of tail_risk.jl:96-141 (transliterated with the comprehensive.jl functions it calls) against the
+    product's host functions over psra_copt: ELU effective FOR and the hourly risk profile within 1e-9."""
+    import powersystemsreliabilityassessment_b200 as P
+    g = _ref("detailed_mc"); r = _ref("detailed_analytical")
+    gens = [P.DetailedGenerator(f"g{i}", float(c), float(q), int(w), float(e))
+            for i, (c, q, w, e) in enumerate(zip(g["cap"], g["for_rate"], g["maint_weeks"], g["energy_limit"]))]
+    for x, s in zip(gens, g["maint_start"]):
+        x.scheduled_outage_start = int(s)
+    total, profile = P.run_detailed_analytical(gens, g["base_load"], 5.0, engine=engine)
+    assert np.allclose([x.effective_q for x in gens], r["effective_q"], rtol=1e-9, atol=0)
+    assert np.allclose(profile, r["profile"], rtol=1e-9, atol=1e-300) and abs(total - float(r["total"])) <= 1e-9 * total

@@ -230,3 +230,51 @@ def test_c_oracle_reproduces_the_reference_fd_recursion_and_copt_demo():
         assert np.array_equal(probs, g[f"probs{k}"])
         lole, eue = O.gaa_indices(probs, float(g[f"step{k}"]), g[f"ldc{k}"])
         assert abs(lole - g[f"idx{k}"][0]) <= 1e-12 * lole and abs(eue - g[f"idx{k}"][1]) <= 1e-12 * eue
+
+
+def test_c_oracle_reproduces_the_reference_markov_script_blocks():
+    """Markov_process.jl is a script; its constant-hazard experiment (:46-60) and its five-generator hourly DTMC (:153-195,
+    the script's own unit data) are cut out as they stand, transliterated and run on recorded rand() values."""
+    g = _g("markov")
+    assert np.array_equal(O.dtmc_capacity(g["mttf"], g["mttr"], g["cap"], g["dtmc_uniforms"]), g["dtmc_capacity"])
+    o = O.failure_times(float(g["ft_lambda"]), 1.0, 5000.0, len(g["ft_uniforms"]), uniforms=g["ft_uniforms"])
+    assert np.array_equal(o[o >= 0], g["failure_times"]) and 0 < len(g["failure_times"]) < len(g["ft_uniforms"])
+    if have_ref:
+        src = J.load_text(REF, J.MARKOV_REL)
+        series, mf, mr, cp = J.reference_dtmc_capacity(src, g["dtmc_uniforms"])
+        assert series == list(g["dtmc_capacity"]) and mf == list(g["mttf"]) and cp == list(g["cap"])
+
+
+def test_oracle_pieces_reproduce_the_reference_detailed_analytical():
+    """run_detailed_analytical (tail_risk.jl:96-141) with update_elu! / calculate_expected_generation / add_unit of
+    generating_adequacy_comprehensive.jl, transliterated and run on the six-unit system: the oracle's literal cores
+    (expected_generation, lfu_hourly_risk, copt_build) composed the same way give the ELU fixed point and the hourly risk."""
+    g = _g("detailed_mc"); r = _g("detailed_analytical")
+    cap, q0, ms, mw, el, base = g["cap"], g["for_rate"], g["maint_start"], g["maint_weeks"], g["energy_limit"], g["base_load"]
+    U = len(cap)
+    lfu_mw = float(base.max()) * (5.0 / 100.0)
+    q = q0.copy()
+    hist = [float(q0[4])]
+    for _ in range(5):                                                     # tail_risk.jl:106
+        for i in range(U):
+            if el[i] == np.inf:
+                continue
+            rest = [j for j in range(U) if j != i]
+            probs = O.copt_build(cap[rest], q[rest], 20.0)
+            req = O.expected_generation(probs, 20.0, float(cap[i]), base, lfu_mw)
+            new_q = float(q0[i])
+            if req > el[i]:
+                new_q += (req - el[i]) / (cap[i] * len(base))
+            new_q = min(new_q, 1.0)
+            if abs(new_q - q[i]) > 1e-5:
+                q[i] = new_q
+            hist.append(new_q)
+    assert np.allclose(hist, r["history_q_elu"], rtol=1e-12, atol=0) and np.allclose(q, r["effective_q"], rtol=1e-12, atol=0)
+    assert r["effective_q"][4] > q0[4] + 1e-3                              # the energy limit binds
+    prof = np.zeros(len(base))
+    for w in range(1, 53):
+        week = [j for j in range(U) if not (w >= ms[j] and w < ms[j] + mw[j])]
+        probs = O.copt_build(cap[week], r["effective_q"][week], 20.0)
+        h0, h1 = (w - 1) * 168, min(w * 168, 8760)
+        prof[h0:h1] = O.lfu_hourly_risk(probs, 20.0, base[h0:h1], lfu_mw)
+    assert np.allclose(prof, r["profile"], rtol=1e-12, atol=1e-300) and abs(prof.sum() - float(r["total"])) <= 1e-12 * prof.sum()
