@@ -44,4 +44,16 @@ with P.Engine(unpacked_words=True) as g:
 with P.Engine(force_generic=True) as g:
     g.set_system(cap, mttf, mttr); g.set_load(load)
     print("seq generic", g.seq_mc(2000, seed=1, years_per_chain=4).lole)
+# round 2: in-kernel ENS histogram + one-launch tail, redo path of seq_fast.cu (small event lists), seq_wide.cu with a unit
+# count that is not a multiple of 32 and several block sizes, the staged history read-back
+with P.Engine(ev_cap=704) as s:
+    s.set_system(cap, mttf, mttr); s.set_load(load)
+    r = s.seq_mc(3000, seed=21, per_year=True, fail_count=True, group=10, history=10, tail_hist=True)
+    print("seq fast redo", r.redone, s.tail(None, alphas=(0.5, 0.95))[0]["var"])
+for kw in (dict(), dict(warps_per_block=2), dict(warps_per_block=6), dict(static_blocks=56)):
+    with P.Engine(**kw) as w:
+        k = 70
+        w.set_system(np.tile(cap, 3)[:k], np.tile(mttf, 3)[:k], np.tile(mttr, 3)[:k]); w.set_load(np.rint(2.1 * rts79.load_curve_mw()).astype(np.int32)[:8000])
+        r = w.seq_mc(200, seed=4, per_year=True, fail_count=True, group=10, history=10, tail_hist=True)
+        print("seq wide 70 units", kw, r.lole, w.tail(None, alphas=(0.9,))[0]["var"])
 print("SANITIZE_RUN_OK")
