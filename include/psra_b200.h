@@ -70,7 +70,8 @@ typedef struct psra_config {
                                  transitions; a small value exercises the redo path) */
     int32_t tail_bins;        /* bins (1 fixed-point MWh wide) of the per-year ENS histogram kept for psra_tail;
                                  0 = 64 x the installed capacity, between 2^16 and 2^24 */
-    int32_t reserved2[5];
+    int32_t reserved2[5];     /* reserved2[0] != 0: the launches of a chunked run (long runs with a convergence history) all go to
+                                 one stream instead of alternating between two (comparison builds) */
 } psra_config;
 
 /* lifetime ------------------------------------------------------------------------- */

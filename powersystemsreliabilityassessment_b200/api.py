@@ -138,7 +138,7 @@ class Engine:
 
     def __init__(self, device: int = 0, warps_per_block: int = 0, seg_hours: int = 0, blocks_per_sm: int = 0,
                  force_generic: bool = False, unpacked_words: bool = False, force_team: bool = False,
-                 static_blocks: int = 0, ngpus: int = 1, ev_cap: int = 0, tail_bins: int = 0):
+                 static_blocks: int = 0, ngpus: int = 1, ev_cap: int = 0, tail_bins: int = 0, single_stream: bool = False):
         """ngpus > 1: the handle spans the devices device .. device + ngpus - 1 of this process; the Monte Carlo calls
         shard their year / sample range over them and combine the integers with NCCL inside the library."""
         self._L = _lib.load()
@@ -146,9 +146,10 @@ class Engine:
         cfg = _lib.Config(device=device, warps_per_block=warps_per_block, seg_hours=seg_hours,
                           blocks_per_sm=blocks_per_sm, ngpus=int(ngpus), ev_cap=int(ev_cap), tail_bins=int(tail_bins))
         cfg.reserved[0] = 1 if force_generic else 0
-        cfg.reserved[1] = int(unpacked_words)      # 1: unpacked cross-check variants; 2: force seq_wide.cu's packed timeline
+        cfg.reserved[1] = int(unpacked_words)      # 1: seq_fast.cu keeps its word sums unpacked (cross-check variant)
         cfg.reserved[2] = 1 if force_team else 0
         cfg.reserved[3] = int(static_blocks)
+        cfg.reserved2[0] = 1 if single_stream else 0   # chunked history runs: all launches on one stream (comparison)
         self.ngpus = max(1, int(ngpus))
         rc = self._L.psra_create(C.byref(self._h), C.byref(cfg))
         if rc != 0:

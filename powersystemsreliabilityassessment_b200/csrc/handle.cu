@@ -220,7 +220,14 @@ extern "C" int psra_create(psra_handle **out, const psra_config *cfg)
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
     h->sm_clock_khz = khz;
     PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    {
+        // the scans of finished history ranges must not queue behind the Monte Carlo blocks that are still waiting for an SM
+        int lo = 0, hi = 0;
+        PSRA_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PSRA_CUDA(h, cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi));
+        PSRA_CUDA(h, cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+        PSRA_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
     for (int i = 0; i < PSRA_MAX_CHUNKS; i++) PSRA_CUDA(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < PSRA_MAX_CHUNKS + 2; i++) PSRA_CUDA(h, cudaEventCreateWithFlags(&h->ev_pin[i], cudaEventDisableTiming));
     PSRA_CUDA(h, cudaEventCreate(&h->ev0));
@@ -249,6 +256,8 @@ extern "C" void psra_destroy(psra_handle *h)
     for (int i = 0; i < PSRA_MAX_CHUNKS + 2; i++) if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

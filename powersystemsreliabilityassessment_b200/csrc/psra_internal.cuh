@@ -26,7 +26,9 @@ struct psra_handle {
     int sm_clock_khz = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;              // history scan + read-back, overlapped with the kernels of `stream`
+    cudaStream_t stream2 = nullptr;              // history scan + read-back, overlapped with the kernels of `stream` (highest priority)
+    cudaStream_t stream3 = nullptr;              // every other launch of a chunked run: its blocks fill the SMs the launch before drains
+    cudaEvent_t ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_chunk[PSRA_MAX_CHUNKS] = {nullptr};
     psra_config cfg{};

@@ -623,6 +623,13 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         }
     }
     PSRA_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    // chunked run: the launches alternate between two streams, so the blocks of launch c + 1 fill the SMs that launch c
+    // drains (the launches are independent: disjoint years, atomics on the shared accumulators)
+    const bool alternate = nlaunch > 1 && !h->cfg.reserved2[0];
+    if (alternate) {
+        PSRA_CUDA(h, cudaEventRecord(h->ev_join, h->stream));               // the set-up (memsets, uploads) is on `stream`
+        PSRA_CUDA(h, cudaStreamWaitEvent(h->stream3, h->ev_join, 0));
+    }
     for (int c = 0; c < nlaunch; c++) {
         SeqArgs b = a;
         const long long c0 = (long long)c * chunk_chains;
@@ -636,12 +643,17 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
         long long g = grid;
         const long long need_c = (team ? b.nchains : (b.nchains + wpb - 1) / wpb);
         if (g > need_c) g = need_c;
-        if (fast) seq_fast_launch(b, (unsigned)g, wpb * 32, smem, h->stream);
-        else if (wide) seq_wide_launch(b, (unsigned)g, wpb * 32, smem, h->stream);
-        else if (team) seq_team_launch(b, (unsigned)g, smem, h->stream);
-        else kern<<<(unsigned)g, wpb * 32, smem, h->stream>>>(b);
+        cudaStream_t ls = (alternate && (c & 1)) ? h->stream3 : h->stream;
+        if (fast) seq_fast_launch(b, (unsigned)g, wpb * 32, smem, ls);
+        else if (wide) seq_wide_launch(b, (unsigned)g, wpb * 32, smem, ls);
+        else if (team) seq_team_launch(b, (unsigned)g, smem, ls);
+        else kern<<<(unsigned)g, wpb * 32, smem, ls>>>(b);
         PSRA_CUDA(h, cudaGetLastError());
-        if (nlaunch > 1) PSRA_CUDA(h, cudaEventRecord(h->ev_chunk[c], h->stream));
+        if (nlaunch > 1) PSRA_CUDA(h, cudaEventRecord(h->ev_chunk[c], ls));
+    }
+    if (alternate) {
+        PSRA_CUDA(h, cudaEventRecord(h->ev_join, h->stream3));
+        PSRA_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
     PSRA_CUDA(h, cudaEventRecord(h->ev1, h->stream));
 
