@@ -518,10 +518,11 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
     if (team) {
         wpb = SEQ_TEAM_WARPS;
         if (wide) {
-            // block size of seq_wide.cu: 4 warps measured best from 64 to 1024 units (scripts/sweep_wide_units.py: +10-18 %
-            // over 6 warps at 96-320 units, equal at 1024); psra_config.warps_per_block overrides (at most 4)
-            const int wmax = seq_wide_max_warps();
-            wpb = h->cfg.warps_per_block > 0 ? std::min(wmax, h->cfg.warps_per_block) : std::min(wmax, 4);
+            // block size of seq_wide.cu (scripts/sweep_wide_small.py, round 2): 3 warps up to ~ 300 units (8.8 / 8.6 / 8.3 / 7.5 /
+            // 6.7 e7 years/s at 64 / 96 / 128 / 192 / 256 units against 7.5 / 7.4 / 7.1 / 6.6 / 6.2 with 4), 4 warps above
+            // (5.1 / 4.4 / 3.3 / 2.6 e7 at 384 / 512 / 768 / 1024 units; 3 and 5 warps are 2-8 % slower there);
+            // psra_config.warps_per_block overrides
+            wpb = h->cfg.warps_per_block > 0 ? std::min(wmax, h->cfg.warps_per_block) : std::min(wmax, h->U <= 320 ? 3 : 4);
         }
     }
     if (!fast && !team) wpb = gg.wpb;
