@@ -522,6 +522,7 @@ static int run_seq(psra_handle *h, bool injected, const double *h_dur, int K, lo
             // 6.7 e7 years/s at 64 / 96 / 128 / 192 / 256 units against 7.5 / 7.4 / 7.1 / 6.6 / 6.2 with 4), 4 warps above
             // (5.1 / 4.4 / 3.3 / 2.6 e7 at 384 / 512 / 768 / 1024 units; 3 and 5 warps are 2-8 % slower there);
             // psra_config.warps_per_block overrides
+            const int wmax = seq_wide_max_warps();
             wpb = h->cfg.warps_per_block > 0 ? std::min(wmax, h->cfg.warps_per_block) : std::min(wmax, h->U <= 320 ? 3 : 4);
         }
     }
