@@ -28,9 +28,9 @@
 // no block barrier.
 //
 // Evaluation: the warps reduce the hour deltas to per-32-hour-word sums (lane = word, 128-bit loads,
-// skewed so that a quarter-warp covers all 32 banks); after a barrier every warp scans the word sums
-// into the capacity entering each run of words (redundantly: a few loads per lane); then lane = word
-// again: a word that can contain loss of load (capacity + negative hour deltas < maximum load of the
+// skewed so that a quarter-warp covers all 32 banks) and scan them inside their block of 32 words;
+// after a barrier lane = word again: the capacity entering the word is the capacity at hour 0 plus the
+// sums of the blocks in front plus the prefix inside the block, and a word that can contain loss of load (capacity + negative hour deltas < maximum load of the
 // word) is walked hour by hour by its lane (LOL hours, deficit entries, int64 ENS), and every lane clears
 // its word -- so the rare resolution work is spread over all warps instead of serialising on one of them
 // while the others wait at the barrier (measured: 15 % of the warp time).  The per-year sums meet in
@@ -74,7 +74,7 @@ size_t seq_wide_smem_bytes(int Wd, int U, int nwarps)
     size_t b = sizeof(int32_t) * ((size_t)Wd * 32 + 32);                  // hour timeline + one dummy slot per lane
     // the to-do lists of the generation phase and the word sums / negative sums of the evaluation share one region
     b += std::max(2 * sizeof(int32_t) * Wd4, sizeof(unsigned long long) * (size_t)nwarps * wide_todo_cap(U, nwarps));
-    b += 2 * sizeof(WideShared) + (32 + WIDE_MAX_WARPS) * sizeof(int32_t) + 7 * sizeof(unsigned long long);   // + one always-zero word per lane, queue heads, block totals
+    b += 2 * sizeof(WideShared) + (32 + WIDE_MAX_WARPS + 16) * sizeof(int32_t) + 8 * sizeof(unsigned long long);   // + one always-zero word per lane, queue heads, block totals, word-block sums
     return (b + 15) & ~(size_t)15;
 }
 
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
 
     // block totals (thread 0 only; in shared memory: they would cost 14 registers for one update per year)
     unsigned long long *bacc = reinterpret_cast<unsigned long long *>(qheads + WIDE_MAX_WARPS);   // [7]: LOL, ENS, ENT, YWL, LOL2, ENS2 lo / hi
+    int32_t *bsum = reinterpret_cast<int32_t *>(bacc + 8);               // [16]: sums of the 32-word blocks of the year
     if (threadIdx.x < 7) bacc[threadIdx.x] = 0ull;
     unsigned long long ev64 = 0ull, n_jobs = 0ull;
     unsigned int n_flag = 0;
@@ -179,8 +180,6 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
     const unsigned long long start_m1 = (kDisc ? (1ull << PSRA_TICK_SHIFT) : 0ull) - 1ull;
     const uint32_t thr_mask = a.init_mode == PSRA_INIT_STATIONARY ? 0xffffffffu : 0u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const int wpl = (a.Wd + 31) >> 5;                                  // words per run of the evaluation scan
-    const int wpl_inv = (65536 + wpl - 1) / wpl;
 
 #ifdef WIDE_PROFILE
     unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -286,48 +285,43 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
         __syncthreads();
         WIDE_T(2);
 
-        // ---- word sums of the hour deltas: lane = word, 128-bit loads skewed by the lane (conflict-free)
+        // ---- word sums of the hour deltas: lane = word, 128-bit loads skewed by the lane (conflict-free); the warp scans the
+        //      sums of its 32 words right away: wsum[w] = sum of the words in front of w inside its block of 32 words,
+        //      bsum[block] = sum of the whole block
         for (int w0 = warp * 32; w0 < a.Wd; w0 += nwarps * 32) {
             const int w = w0 + lane;
+            int s = 0, n = 0;
             if (w < a.Wd) {
                 const int4 *row = reinterpret_cast<const int4 *>(tl + w * 32);
-                int s = 0, n = 0;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int4 v = row[(j + lane) & 7];
                     s += (v.x + v.y) + (v.z + v.w);
                     n += (min(v.x, 0) + min(v.y, 0)) + (min(v.z, 0) + min(v.w, 0));
                 }
-                wsum[w] = s; wneg[w] = n;
             }
+            const int incl = warp_incl_scan(s, lane);
+            if (w < a.Wd) { wsum[w] = incl - s; wneg[w] = n; }
+            if (lane == 31) bsum[w0 >> 5] = incl;
         }
         WIDE_T(3);
         __syncthreads();
         WIDE_T(4);
 
-        // ---- evaluation: every warp scans the word sums (lane = run of `wpl` consecutive words) into the capacity
-        //      entering each run; then lane = word again (the mapping of the word sums): the capacity entering the word,
-        //      the conservative test "capacity + negative hour deltas < maximum load of the word", and the lane walks the
+        // ---- evaluation: lane = word again (the mapping of the word sums): the capacity entering the word (capacity at
+        //      hour 0 + the sums of the blocks in front + the prefix inside the block), the conservative test "capacity + negative hour deltas < maximum load of the word", and the lane walks the
         //      32 hours of such a word itself (rare: ~3 words per year, neighbours share one divergent pass; PSA.jl:253
         //      strict compare, deficit entries per calnlc.m:22-34).  Every lane clears its word afterwards.
         {
             unsigned int lolh = 0, entries = 0;
             long long ens_lane = 0;
             const int nwords = a.Wd;
-            const int wb = lane * wpl;
-            int loc = 0;
-            for (int k = 0; k < wpl; k++) {
-                const int w = wb + k;
-                if (w < nwords) loc += wsum[w];
-            }
-            const int incl = warp_incl_scan(loc, lane);
-            const int cs_lane = sh->capacity + incl - loc;          // capacity entering the lane's run
+            const int cap0 = sh->capacity;
             for (int w0 = warp * 32; w0 < nwords; w0 += nwarps * 32) {
                 const bool valid = w0 + lane < nwords;
                 const int w = valid ? w0 + lane : nwords - 1;
-                const int run = (w * wpl_inv) >> 16;                // w / wpl (exact for w < 2^11, wpl <= 16)
-                int c_in = __shfl_sync(0xffffffffu, cs_lane, run);
-                for (int j = run * wpl; j < w; j++) c_in += wsum[j];
+                int c_in = cap0 + wsum[w];                          // capacity entering the word
+                for (int j = 0; j < (w0 >> 5); j++) c_in += bsum[j];
                 const bool need = valid && (c_in + wneg[w] < __ldg(&s_lmax[w]));
                 const uint32_t nm = __ballot_sync(0xffffffffu, need);
                 n_flag += __popc(nm);
