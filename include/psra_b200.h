@@ -277,7 +277,10 @@ typedef struct psra_detailed_system {
 int psra_detailed_mc(psra_handle *h, const psra_detailed_system *sys, const double *base_load_mw,
                      int32_t n_hours, double lfu_std_mw, int64_t year0, int64_t nyears, uint64_t seed,
                      uint32_t *year_lole, uint32_t *hourly_fail, float *kernel_ms);
-/* same loop with injected rand() / randn(): uniforms[(y*H + h)*U + u], normals[y*H + h] */
+/* same loop with injected rand() / randn(): uniforms[(y*H + h)*U + u], normals[y*H + h].  The layout is per (year, hour,
+ * unit) whatever the maintenance schedule; the reference only calls rand() for a unit that is NOT on maintenance in that
+ * hour (tail_risk.jl:39-44), so a stream recorded from the reference is laid out by skipping those units
+ * (tests/golden/ref_detailed_mc.npz is produced that way from the reference text) */
 int psra_detailed_eval_injected(psra_handle *h, const psra_detailed_system *sys, const double *base_load_mw,
                                 int32_t n_hours, double lfu_std_mw, int64_t nyears, const double *uniforms,
                                 const double *normals, uint32_t *year_lole, uint32_t *hourly_fail);

@@ -433,6 +433,7 @@ class Engine:
         return sys, (cap, q, ms, mw, el)
 
     def detailed_mc(self, gens, base_load, lfu_std: float, n_years: int, seed: int = 42, year0: int = 0):
+        """psra_detailed_mc (tail_risk.jl:12-91); at most 30 units (the kernel keeps the per-unit energy state in registers)."""
         sys, keep = self._detailed_sys(gens)
         bl = np.ascontiguousarray(base_load, dtype=np.float64)
         yl = np.zeros(n_years, dtype=np.uint32); hf = np.zeros(len(bl), dtype=np.uint32)
@@ -442,6 +443,8 @@ class Engine:
         return yl, hf, ms.value
 
     def detailed_eval_injected(self, gens, base_load, lfu_std: float, uniforms, normals):
+        """Same loop on injected rand() / randn(): uniforms[year][hour][unit] (a value for EVERY unit; the reference draws
+        none for a unit on maintenance, tail_risk.jl:39-44 -- lay a recorded stream out accordingly), normals[year][hour]."""
         sys, keep = self._detailed_sys(gens)
         bl = np.ascontiguousarray(base_load, dtype=np.float64)
         un = np.ascontiguousarray(uniforms, dtype=np.float64); no = np.ascontiguousarray(normals, dtype=np.float64)
