@@ -42,8 +42,14 @@ struct NsArgs {
 
 enum { NS_PHILOX = 0, NS_STATES = 1, NS_UNIFORMS = 2 };
 
-// U <= 32, total_cap < 65536, H < 65536
-__global__ void __launch_bounds__(256) nonseq_fast_kernel(const NsArgs a)
+// U <= 32, total_cap < 65536, H < 65536.  kBlk = Philox blocks per sample, ceil(U / 4), a compile-time constant: the blocks of a
+// sample are independent, and only in ONE basic block does ptxas interleave their 2 kBlk multiply chains (with a run-time
+// count every block was its own basic block: two chains in flight per warp, issue slots 57 % busy)
+#ifndef NSF_BPS
+#define NSF_BPS 2
+#endif
+template <int kBlk>
+__global__ void __launch_bounds__(256, NSF_BPS) nonseq_fast_kernel(const NsArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *s_btab = reinterpret_cast<int32_t *>(smem_raw);                      // [4][256]
@@ -54,7 +60,6 @@ __global__ void __launch_bounds__(256) nonseq_fast_kernel(const NsArgs a)
     for (int i = threadIdx.x; i <= a.total_cap; i += blockDim.x) s_lol[i] = a.lol_tab[i];
     __syncthreads();
     const uint32_t umask = a.U >= 32 ? 0xffffffffu : ((1u << a.U) - 1u);
-    const int nblk = (a.U + 3) >> 2;
 
     unsigned long long acc_lol = 0, acc_swl = 0, acc_lol2 = 0, acc_e2lo = 0, acc_e2hi = 0;
     long long acc_ens = 0;
@@ -63,16 +68,14 @@ __global__ void __launch_bounds__(256) nonseq_fast_kernel(const NsArgs a)
         const unsigned long long s = (unsigned long long)(a.i0 + i);
         uint32_t word = 0;
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-            if (g < nblk) {                           // uniform
-                uint32_t x[4];
-                philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)g, 0x4E53u, a.k0, a.k1, x);
-                const uint4 t = *reinterpret_cast<const uint4 *>(s_thr + 4 * g);
-                word |= (x[0] >= t.x ? 1u : 0u) << (4 * g);             // PSA.jl:183 in integer form
-                word |= (x[1] >= t.y ? 1u : 0u) << (4 * g + 1);
-                word |= (x[2] >= t.z ? 1u : 0u) << (4 * g + 2);
-                word |= (x[3] >= t.w ? 1u : 0u) << (4 * g + 3);
-            }
+        for (int g = 0; g < kBlk; g++) {
+            uint32_t x[4];
+            philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)g, 0x4E53u, a.k0, a.k1, x);
+            const uint4 t = *reinterpret_cast<const uint4 *>(s_thr + 4 * g);
+            word |= (x[0] >= t.x ? 1u : 0u) << (4 * g);             // PSA.jl:183 in integer form
+            word |= (x[1] >= t.y ? 1u : 0u) << (4 * g + 1);
+            word |= (x[2] >= t.z ? 1u : 0u) << (4 * g + 2);
+            word |= (x[3] >= t.w ? 1u : 0u) << (4 * g + 3);
         }
         word &= umask;
         const int cap = s_btab[word & 255u] + s_btab[256 + ((word >> 8) & 255u)] + s_btab[512 + ((word >> 16) & 255u)] +
@@ -319,7 +322,9 @@ static int run_nonseq(psra_handle *h, int mode, const void *input, long long i0,
     }
     PSRA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * ACC_COUNT, h->stream));
 
-    void (*kern)(NsArgs) = fastp ? nonseq_fast_kernel : mode == NS_PHILOX ? nonseq_kernel<NS_PHILOX>
+    static void (*const fast_kernels[8])(NsArgs) = {nonseq_fast_kernel<1>, nonseq_fast_kernel<2>, nonseq_fast_kernel<3>, nonseq_fast_kernel<4>,
+                                                     nonseq_fast_kernel<5>, nonseq_fast_kernel<6>, nonseq_fast_kernel<7>, nonseq_fast_kernel<8>};
+    void (*kern)(NsArgs) = fastp ? fast_kernels[((h->U + 3) >> 2) - 1] : mode == NS_PHILOX ? nonseq_kernel<NS_PHILOX>
                          : mode == NS_STATES ? nonseq_kernel<NS_STATES> : nonseq_kernel<NS_UNIFORMS>;
     PSRA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = 0;
