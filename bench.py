@@ -417,20 +417,26 @@ def main():
             for g in range(world):
                 flushes.append(flush if g == local_rank else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=torch.device("cuda", g)))
 
+        flush_s = [0.0]
+
         def step_e2e(s):
+            tf = time.perf_counter()
             for g, f in enumerate(flushes):
                 f.zero_()
             for g in range(len(flushes)):
                 torch.cuda.synchronize(torch.device("cuda", g if world > 1 else local_rank))
+            flush_s[0] += time.perf_counter() - tf
             return P.run_sequential_mc(gens, lm, world * Y, seed=args.seed, year0=s * world * Y, engine=e2e_eng, details=True)
 
         step_e2e(1000)
+        flush_s[0] = 0.0
         t0 = time.perf_counter()
         for s in range(args.steps):
             res, r2 = step_e2e(2000 + s)
         e2e_wall = time.perf_counter() - t0
         e2e_info = {"lole_last_step": res.lole_hours_yr, "history_len": int(len(res.convergence_history)),
-                    "years_last_step": int(r2.years), "kernel_ms_last_step": r2.kernel_ms}
+                    "years_last_step": int(r2.years), "kernel_ms_last_step": r2.kernel_ms,
+                    "l2_flush_ms_per_step": 1e3 * flush_s[0] / args.steps}
         if e2e_eng is not eng:
             e2e_eng.close()
         del flushes

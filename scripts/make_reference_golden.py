@@ -199,3 +199,38 @@ tot, prof, qeff, hist = J.reference_detailed_analytical(src_tail, src_comp, d["c
 np.savez_compressed(os.path.join(out, "ref_detailed_analytical.npz"), total=tot, profile=np.array(prof), effective_q=np.array(qeff),
                     history_q_elu=np.array(hist[4]))
 print("detailed analytical: total risk", tot, "effective q", qeff, "ELU history", hist[4], f"({_t.time() - _t0:.0f} s)", flush=True)
+
+# ====================================================================== the MATLAB functions on the path (SURVEY a-8, a-9)
+# seq_mcsampling.m (next-event sampler, round / ceil discretisation, all components UP at hour 0 of every year:
+# seqMain.m:91 calls it with num_years = 1) and calnlc.m, transliterated by oracle/m_transliterate.py.  The two duration draws
+# (:52,59) read the library's sampler durations of the (seed; year, unit) streams; the state matrix is evaluated at HL1
+# (available capacity against the load, strict compare as PSA.jl:253) and calnlc counts the curtailment events.
+from oracle import m_transliterate as MT
+
+m_sampler, _, m_hit = MT.load_seq_mcsampling(ref_root)
+m_calnlc, _ = MT.load_calnlc(ref_root)
+assert m_hit == [52, 59], m_hit
+sha_m = hashlib.sha256((MT._load(ref_root, MT.SAMPLING_REL) + MT._load(ref_root, MT.CALNLC_REL)).encode("utf-8")).hexdigest()
+rng = np.random.default_rng(9119)
+m_cases = {
+    "rts79": dict(cap=cap, mttf=mttf, mttr=mttr, load=rts79.load_curve_int().astype(np.float64), seed=77, year0=32, years=12),
+    # frequent events on a ragged horizon: times to failure that round to 0 hours, repairs that end beyond the year
+    "small": dict(cap=rng.integers(5, 60, 5).astype(np.float64), mttf=rng.uniform(6.0, 40.0, 5), mttr=rng.uniform(0.6, 9.0, 5),
+                  load=rng.integers(60, 150, 301).astype(np.float64), seed=5, year0=0, years=40),
+}
+mat = {}
+for name, c in m_cases.items():
+    U, H = len(c["cap"]), len(c["load"])
+    mf32 = c["mttf"].astype(np.float32).astype(np.float64); mr32 = c["mttr"].astype(np.float32).astype(np.float64)   # the sampler's binary32 means
+    lol = np.zeros(c["years"]); ens = np.zeros(c["years"]); nlc = np.zeros(c["years"]); down = np.zeros((c["years"], U))
+    for y in range(c["years"]):
+        D = sampler_lists(c["seed"], c["year0"] + y, mf32, mr32, 400 if name == "small" else 96)
+        states, used = m_sampler(np.stack([mf32, mr32], axis=1), U, 0, 1, H, D)
+        st = np.array(states)
+        cap_avail = ((1.0 - st) * c["cap"][:, None]).sum(axis=0)        # whole-MW capacities: the sum is exact in any order
+        flag = cap_avail < c["load"]
+        lol[y] = flag.sum(); ens[y] = (c["load"] - cap_avail)[flag].sum(); nlc[y] = m_calnlc(flag.astype(np.float64)); down[y] = st.sum(axis=1)
+    mat.update({f"{name}_{k}": v for k, v in c.items()})
+    mat.update({f"{name}_lol": lol, f"{name}_ens": ens, f"{name}_nlc": nlc, f"{name}_down_hours": down})
+    print("MATLAB sampler", name, "DLC", lol.sum(), "ENS", ens.sum(), "NLC", nlc.sum(), "down hours", down.sum(), flush=True)
+np.savez_compressed(os.path.join(out, "ref_matlab.npz"), reference_sha256=np.array(sha_m), **mat)

@@ -169,3 +169,20 @@ def test_reference_text_detailed_analytical_vectors(engine):
     total, profile = P.run_detailed_analytical(gens, g["base_load"], 5.0, engine=engine)
     assert np.allclose([x.effective_q for x in gens], r["effective_q"], rtol=1e-9, atol=0)
     assert np.allclose(profile, r["profile"], rtol=1e-9, atol=1e-300) and abs(total - float(r["total"])) <= 1e-9 * total
+
+
+@pytest.mark.parametrize("name", ("rts79", "small"))
+def test_matlab_sampler_vectors_from_the_reference_text(engine, name):
+    """ref_matlab.npz: Montecarlo_seq/seq_mcsampling.m + calnlc.m executed from the reference text (oracle/m_transliterate.py) on
+    the sampler's duration streams; the CUDA kernels in MATLAB-discretisation mode return the same DLC / ENS / NLC per year."""
+    from powersystemsreliabilityassessment_b200 import DISC_MATLAB, INIT_ALL_UP, Engine
+    g = _ref("matlab")
+    cap, mttf, mttr, load = g[f"{name}_cap"], g[f"{name}_mttf"], g[f"{name}_mttr"], g[f"{name}_load"]
+    seed, year0, years = int(g[f"{name}_seed"]), int(g[f"{name}_year0"]), int(g[f"{name}_years"])
+    for kw in (dict(), dict(force_generic=True)):
+        with Engine(**kw) as e:
+            e.set_system(cap, mttf, mttr); e.set_load(load.astype(np.int32))
+            r = e.seq_mc(years, seed=seed, year0=year0, init_mode=INIT_ALL_UP | DISC_MATLAB, per_year=True)
+        assert np.array_equal(r.lol_hours.astype(np.float64), g[f"{name}_lol"])
+        assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), g[f"{name}_ens"])
+        assert np.array_equal(r.entries.astype(np.float64), g[f"{name}_nlc"])

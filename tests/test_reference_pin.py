@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 from oracle import jl_transliterate as J
+from oracle import m_transliterate as MT
 from oracle import oracle as O
 from oracle import psa_literal as L
 
@@ -113,6 +114,20 @@ def test_calnlc_and_matlab_sampling_transcriptions():
     # seq_mcsampling.m:40-74: -450 ln(0.5) = 311.9 -> UP for 312 h; -50 ln(0.9) = 5.27 -> DOWN for 6 h from hour 313
     s, used = L.matlab_unit_series(450.0, 50.0, 400, [0.5, 0.9, 0.01, 0.3])
     assert sum(s) == 6 and s[312:318] == [1] * 6 and s[311] == 0 and used == 3
+
+
+MATLAB_CASES = ("rts79", "small")
+
+
+@pytest.mark.parametrize("name", MATLAB_CASES)
+def test_c_oracle_reproduces_the_reference_matlab_sampler_and_calnlc(name):
+    """ref_matlab.npz: seq_mcsampling.m (round / ceil next-event sampler, durations = the sampler streams) evaluated at HL1 and
+    calnlc.m, both executed from the reference text (oracle/m_transliterate.py): DLC, ENS and NLC of every year."""
+    g = _g("matlab")
+    lol, eue, ent = O.seq_matlab_philox(g[f"{name}_cap"], g[f"{name}_mttf"], g[f"{name}_mttr"], g[f"{name}_load"],
+                                        int(g[f"{name}_seed"]), int(g[f"{name}_year0"]), int(g[f"{name}_years"]))
+    assert np.array_equal(lol, g[f"{name}_lol"]) and np.array_equal(eue, g[f"{name}_ens"]) and np.array_equal(ent, g[f"{name}_nlc"])
+    assert lol.sum() > 100 and ent.sum() > 30
 
 
 # ------------------------------------------------------------------------------------ needs the reference checkout
@@ -278,3 +293,39 @@ def test_oracle_pieces_reproduce_the_reference_detailed_analytical():
         h0, h1 = (w - 1) * 168, min(w * 168, 8760)
         prof[h0:h1] = O.lfu_hourly_risk(probs, 20.0, base[h0:h1], lfu_mw)
     assert np.allclose(prof, r["profile"], rtol=1e-12, atol=1e-300) and abs(prof.sum() - float(r["total"])) <= 1e-12 * prof.sum()
+
+
+@pytest.mark.skipif(not have_ref, reason="/root/reference is not present (GPU box)")
+def test_matlab_vectors_are_what_the_reference_text_produces():
+    """seq_mcsampling.m / calnlc.m re-transliterated from the checkout: the two substituted draws sit on :52,59 (once each), the
+    committed vectors come out again (RTS-79: the first 3 years; the small system: all 40), and the hand transcriptions of
+    oracle/psa_literal.py agree with the reference's calnlc on random series."""
+    sampler, _, hit = MT.load_seq_mcsampling(REF)
+    calnlc, _ = MT.load_calnlc(REF)
+    assert hit == [52, 59]
+    g = _g("matlab")
+    sha = hashlib.sha256((MT._load(REF, MT.SAMPLING_REL) + MT._load(REF, MT.CALNLC_REL)).encode("utf-8")).hexdigest()
+    assert sha == str(g["reference_sha256"])
+    for name, years, K in (("rts79", 3, 96), ("small", 40, 400)):
+        cap, load = g[f"{name}_cap"], g[f"{name}_load"]
+        mf = g[f"{name}_mttf"].astype(np.float32).astype(np.float64); mr = g[f"{name}_mttr"].astype(np.float32).astype(np.float64)
+        seed, year0 = int(g[f"{name}_seed"]), int(g[f"{name}_year0"])
+        for y in range(years):
+            D = np.empty((len(cap), K))
+            for u in range(len(cap)):
+                words = []
+                for b in range((K + 1 + 3) // 4):
+                    words.extend(int(w) for w in O.philox([(year0 + y) & 0xffffffff, (year0 + y) >> 32, u, b], [seed & 0xffffffff, seed >> 32]))
+                for k in range(K):
+                    D[u, k] = O.duration_hours(mf[u] if k % 2 == 0 else mr[u], words[k + 1])
+            states, _ = sampler(np.stack([mf, mr], axis=1), len(cap), 0, 1, len(load), D)
+            st = np.array(states)
+            cap_avail = ((1.0 - st) * cap[:, None]).sum(axis=0)
+            flag = cap_avail < load
+            assert flag.sum() == g[f"{name}_lol"][y] and (load - cap_avail)[flag].sum() == g[f"{name}_ens"][y]
+            assert calnlc(flag.astype(np.float64)) == g[f"{name}_nlc"][y]
+            assert np.array_equal(st.sum(axis=1), g[f"{name}_down_hours"][y])
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        s = (rng.random(int(rng.integers(1, 60))) < rng.random()).astype(int).tolist()
+        assert L.calnlc(s) == calnlc([float(x) for x in s])
