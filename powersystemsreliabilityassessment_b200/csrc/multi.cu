@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -184,6 +185,18 @@ static int first_error(psra_handle *h, const std::vector<int> &rc)
     return PSRA_OK;
 }
 
+// PSRA_TRACE=1 in the environment: wall-clock phases of a multi-device call on stderr (host side; the kernels' own time is
+// psra_seq_summary.kernel_ms)
+static bool trace_on()
+{
+    static const bool on = getenv("PSRA_TRACE") != nullptr;
+    return on;
+}
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // Running-mean history of a multi-device call: every device scans its groups (carry = LOL hours of the devices in front of
 // it) and stages them through its pinned buffer; one host thread per device, so the scans, the link transfers and the host
 // copies into the caller's buffer run side by side.
@@ -236,6 +249,8 @@ int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t se
     }
     const bool want_fail = out && out->fail_count, want_hist = out && out->tail_hist;
 
+    const double t_begin = trace_on() ? now_ms() : 0.0;
+    double t_touch = 0.0, t_join = 0.0, t_reduce = 0.0, t_hist = 0.0;
     std::vector<psra_seq_summary> sums((size_t)G);
     std::vector<int> rc((size_t)G, PSRA_OK);
     std::vector<std::thread> th;
@@ -269,7 +284,9 @@ int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t se
     // a page fault per 4 KB at its first write: ~2 ms per 10 MB, which would otherwise sit behind the kernels; the buffer
     // is an output that the call overwrites completely).
     if (out && out->history && nyears / group > 0) memset(out->history, 0, sizeof(double) * (size_t)(nyears / group));
+    if (trace_on()) t_touch = now_ms();
     for (auto &t : th) t.join();
+    if (trace_on()) t_join = now_ms();
     int e = first_error(h, rc);
     if (e) return e;
 
@@ -312,6 +329,7 @@ int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t se
     PSRA_CUDA(h, cudaMemcpyAsync(tot, h->d_red, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
     if (want_fail) PSRA_CUDA(h, cudaMemcpyAsync(out->fail_count, h->d_fail, sizeof(uint32_t) * (size_t)h->H, cudaMemcpyDeviceToHost, h->stream));
 
+    if (trace_on()) t_reduce = now_ms();
     // ---- running mean of the LOL hours (PSA.jl:263-265): every device scans its groups, carry = LOL hours in front of it
     if (out && out->history) {
         const long long nfull = nyears / group;
@@ -330,6 +348,14 @@ int psra_multi_seq_mc(psra_handle *h, int64_t year0, int64_t nyears, uint64_t se
     }
     e = sync_all(h);
     if (e) return e;
+    if (trace_on()) {
+        t_hist = now_ms();
+        double kmax = 0.0;
+        for (int g = 0; g < G; g++) kmax = std::max(kmax, (double)sums[(size_t)g].kernel_ms);
+        fprintf(stderr, "[psra] seq_mc on %d devices, %lld years: first touch of the history buffer %.2f ms | devices done after %.2f ms (kernels %.2f ms) | "
+                        "all-reduce %.2f ms | history scan + read-back %.2f ms | total %.2f ms\n", G, (long long)nyears, t_touch - t_begin,
+                t_join - t_begin, kmax, t_reduce - t_join, t_hist - t_reduce, t_hist - t_begin);
+    }
 
     summary->years = (int64_t)tot[0];
     summary->sum_lol_hours = (int64_t)tot[1];
