@@ -323,32 +323,35 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
                 int c_in = cap0 + wsum[w];                          // capacity entering the word
                 for (int j = 0; j < (w0 >> 5); j++) c_in += bsum[j];
                 const bool need = valid && (c_in + wneg[w] < __ldg(&s_lmax[w]));
-                const uint32_t nm = __ballot_sync(0xffffffffu, need);
+                uint32_t nm = __ballot_sync(0xffffffffu, need);
                 n_flag += __popc(nm);
                 int4 *row = reinterpret_cast<int4 *>(tl + w * 32);
-                if (need) {
-                    const int hy0 = w * 32;
-                    const int4 *ld4 = reinterpret_cast<const int4 *>(a.load + hy0);
-                    int c = c_in;
-                    bool prev = hy0 > 0 && c_in < __ldg(&a.load[hy0 - 1]);
-                    auto hour = [&](int d, int L, int h) {
-                        c += d;
-                        const bool lol = c < L;
-                        if (lol) {
-                            lolh++;
-                            entries += prev ? 0u : 1u;
-                            ens_lane += (long long)(L - c);
-                            if (a.fail) atomicAdd(&a.fail[hy0 + h], 1u);
+                // a flagged word is resolved by the whole warp, lane = hour: one load, one shuffle scan, two ballots
+                // (a single lane walking its 32 hours costs ~8 times the warp-instructions and leaves the other warps
+                // of the block waiting at the barrier behind it)
+                while (nm) {
+                    const int src = __ffs(nm) - 1;
+                    nm &= nm - 1u;
+                    const int wq = w0 + src;
+                    const int cq = __shfl_sync(0xffffffffu, c_in, src);      // capacity entering the word
+                    const int hy = wq * 32 + lane;
+                    const int c = cq + warp_incl_scan(tl[hy], lane);
+                    const int L = __ldg(&a.load[hy]);                        // zero beyond the year: never a loss there
+                    const bool lol = c < L;
+                    const uint32_t lm = __ballot_sync(0xffffffffu, lol);
+                    if (lm) {
+                        const uint32_t prev0 = (wq > 0 && cq < __ldg(&a.load[wq * 32 - 1])) ? 1u : 0u;   // the hour before the word
+                        if (lane == 0) {
+                            lolh += (unsigned int)__popc(lm);
+                            entries += (unsigned int)__popc(lm & ~((lm << 1) | prev0));                 // calnlc.m:22-34
                         }
-                        prev = lol;
-                    };
-#pragma unroll 2
-                    for (int j = 0; j < 8; j++) {
-                        const int4 v = row[j];
-                        const int4 L4 = __ldg(ld4 + j);
-                        hour(v.x, L4.x, 4 * j); hour(v.y, L4.y, 4 * j + 1); hour(v.z, L4.z, 4 * j + 2); hour(v.w, L4.w, 4 * j + 3);
+                        if (lol) {
+                            ens_lane += (long long)(L - c);
+                            if (a.fail) atomicAdd(&a.fail[hy], 1u);
+                        }
                     }
                 }
+                __syncwarp();
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) row[(j + lane) & 7] = make_int4(0, 0, 0, 0);
