@@ -190,11 +190,14 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
 // `one_bits` = 0x3F800000 in a register the compiler cannot see through (asm volatile("" : "+r"(one_bits)) outside the
 // hot loop): with it the mantissa of m is ONE three-input LOP3, (fw & 0x007FFFFF) | one_bits -- with two immediates
 // ptxas emits two.  The overload without it is for code that is not register-bound / not hot.
-// Round 2 note: I2FP here and the F2I.S64 of ticks_rn run on the XU pipe (16 lanes per SM); with four of each per Philox
-// block they cost more than their instruction count (seq_wide.cu without the F2I.S64: +20 %, without the I2FP: +12 %).
+// Round 2 note: I2FP here and the F2I.S64 of ticks_rn run on the XU pipe (16 lanes per SM).  Builds of seq_wide.cu that simply
+// leave them out run 12 % / 20 % faster, but so does leaving out any other eight instructions of the dependent chain: a
+// sampler that REPLACES them (23-bit draw, integer log2 through the float bit pattern, duration by IMAD.WIDE + funnel shifts;
+// scripts/microbench/genloop.cu keeps it) has 13 instructions per block fewer, none on the XU pipe, four more on the ALU pipe --
+// and the same speed: the ALU pipe (2 cycles per warp-instruction) bounds the loop, not the XU pipe.
 // Computing both on the FP64 pipe instead (w as the double 2^52 + w minus 2^52; P widened to a double plus 2^52 + 2^51) is
 // bit-exact -- verified over all 2^32 draws -- but slower on B200 (DADD is a low-rate instruction: seq_fast -4.5 %, seq_wide
-// -9.5 %), and an integer-only RN_int64 needs ~10 instructions; both were dropped (DESIGN.md 3.4).
+// -9.5 %), and an integer-only RN_int64 needs ~10 instructions; both were dropped.
 __device__ __forceinline__ float neglog_u32(uint32_t x, uint32_t one_bits)
 {
     const uint32_t fw = __float_as_uint(__uint2float_rz(x | 1u));

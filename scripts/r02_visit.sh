@@ -12,6 +12,7 @@ bench)  timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.jso
 ref)    timeout 300 python bench.py --impl reference --steps 3 --warmup 1 --ref-budget 30 > gpurun_out/bench_ref.json 2>&1; tail -c 1500 gpurun_out/bench_ref.json ;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; tail -3 gpurun_out/bench_under_ncu.log ;;
 ncuwide) timeout 900 ncu --set full --clock-control none --import-source on -k regex:seq_wide_kernel -s 1 -c 1 -f -o gpurun_out/prof_wide python scripts/profile_wide.py 1e5 > gpurun_out/prof_wide.log 2>&1; tail -3 gpurun_out/prof_wide.log ;;
+ncunonseq) timeout 900 ncu --set full --clock-control none --import-source on -k regex:nonseq_fast_kernel -s 1 -c 1 -f -o gpurun_out/prof_nonseq python scripts/profile_nonseq.py 1e8 > gpurun_out/prof_nonseq.log 2>&1; tail -3 gpurun_out/prof_nonseq.log ;;
 ncufast) timeout 900 ncu --set full --clock-control none --import-source on -k regex:seq_fast_kernel -s 1 -c 1 -f -o gpurun_out/prof_seq python scripts/profile_seq.py 1e6 > gpurun_out/prof_seq.log 2>&1; tail -3 gpurun_out/prof_seq.log ;;
 esac
 done
