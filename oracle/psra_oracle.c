@@ -20,7 +20,10 @@
  *       PSA.jl:183 replayed from a recorded matrix); the vectors they produce are committed
  *       (tests/golden/ref_*.npz, scripts/make_reference_golden.py) and this file reproduces
  *       them bit for bit (tests/test_reference_pin.py), as does an independent naive
- *       transcription (oracle/psa_literal.py);
+ *       transcription (oracle/psa_literal.py); likewise the other Julia files of the path
+ *       (multi-area, detailed MC, F&D, COPT demo, Markov script blocks) and the two MATLAB
+ *       functions (Montecarlo_seq/seq_mcsampling.m, calnlc.m; oracle/m_transliterate.py,
+ *       tests/golden/ref_matlab.npz);
  *   (3) not done here: Julia itself.  tools/patched_reference.jl runs the same three
  *       substitutions in a real Julia for whoever has one.
  * The Monte Carlo STREAMS of the reference (Julia's unversioned default RNG, never seeded)
