@@ -10,6 +10,6 @@ from .api import (DetailedGenerator, SystemParams, run_detailed_mc, run_monte_ca
                   run_nonseq_until_beta, run_sequential_until_cov, run_detailed_analytical, update_elu,
                   calculate_expected_generation, get_lfu_distribution,
                   Engine, Generator, LoadModel, PsraError, ReliabilityResult, SequentialIndices,  # noqa: F401
-                  compare_results, cumulative_series, export_results, unit_importance, evaluate_risk, indices_from_raw, run_analytical,
+                  compare_results, cumulative_series, export_results, export_results_mat, export_nonseq_results_mat, unit_importance, evaluate_risk, indices_from_raw, run_analytical,
                   run_non_sequential_mc, run_sequential_mc,
                   ISOLATED, INTERCONNECTED, AreaGenerator, TieLine, Area, System, run_fast_sequential_simulation)

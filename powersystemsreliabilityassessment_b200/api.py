@@ -824,6 +824,43 @@ def export_results(prefix: str, r: SequentialIndices) -> List[str]:
     return [yearly, idx]
 
 
+def export_results_mat(path: str, r: SequentialIndices, hours_per_year: int, comp_importance=None) -> str:
+    """Montecarlo_seq/seqMain.m:260-262 at HL1: a MATLAB MAT-file (`save('seq_reliability_results.mat', 'results_year',
+    'results_cum', 'nodal_eens_avg', 'comp_importance')`) with the same variable and field names --
+    results_year.{plc, nlc, dlc, ens, dns} as 1 x years row vectors (seqMain.m:160-176: plc = dlc / HOURS_PER_YEAR, dns = ens /
+    HOURS_PER_YEAR), results_cum.{eens, cov} (seqMain.m:180-186) and, when a weak-point run supplies it, comp_importance as a
+    column (seqMain.m:225-231, generators only).  nodal_eens_avg is an HL2 output and is not written.  Needs scipy (host-side
+    file format only); returns the path."""
+    from scipy.io import savemat
+    if r.lol_hours is None or r.ens is None or r.entries is None:
+        raise ValueError("export_results_mat needs a run with per_year=True")
+    H = float(hours_per_year)
+    eens, cov = cumulative_series(r)
+    row = lambda v: np.asarray(v, dtype=np.float64).reshape(1, -1)
+    out = {"results_year": {"plc": row(r.lol_hours) / H, "nlc": row(r.entries), "dlc": row(r.lol_hours), "ens": row(r.ens),
+                            "dns": row(r.ens) / H},
+           "results_cum": {"eens": row(eens), "cov": row(cov)}}
+    if comp_importance is not None:
+        out["comp_importance"] = np.asarray(comp_importance, dtype=np.float64).reshape(-1, 1)
+    savemat(path, out, oned_as="row")
+    return path
+
+
+def export_nonseq_results_mat(path: str, lole_history, edns_history, beta_history, comp_importance=None) -> str:
+    """Montecarlo_nsq_single/nsqMain.m:403-405 at HL1: `save('reliability_results.mat', 'accumulated_edns',
+    'accumulated_lole', 'nodal_eens', 'comp_importance', 'beta_history', 'edns_history')` -- the running series of a
+    non-sequential run (one entry per batch: run_nonseq_until_beta returns the beta series, the caller accumulates LOLE / EDNS
+    the same way) under the reference's variable names; nodal_eens is an HL2 output and is not written."""
+    from scipy.io import savemat
+    row = lambda v: np.asarray(v, dtype=np.float64).reshape(1, -1)
+    out = {"accumulated_lole": row(lole_history), "accumulated_edns": row(edns_history), "edns_history": row(edns_history),
+           "beta_history": row(beta_history)}
+    if comp_importance is not None:
+        out["comp_importance"] = np.asarray(comp_importance, dtype=np.float64).reshape(-1, 1)
+    savemat(path, out, oned_as="row")
+    return path
+
+
 # ------------------------------------------------------------------ adaptive stopping (SURVEY f-2)
 def run_sequential_until_cov(engine: Engine, cov_threshold: float = 0.05, batch_years: int = 1000,
                              max_years: int = 10_000_000, seed: int = 42, init_mode: int = INIT_STATIONARY,

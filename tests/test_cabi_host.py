@@ -183,6 +183,16 @@ def test_cumulative_series_and_export(tmp_path):
     assert int(last[0]) == n and int(last[1]) == int(lol[-1]) and float(last[4]) == eens[-1]
     idx = dict(line.split(",") for line in open(paths[1]).read().strip().split("\n")[1:])
     assert float(idx["lole"]) == r.lole and float(idx["eens"]) == r.eens
+    # the MAT-file of seqMain.m:260-262 with the reference's variable / field names
+    from scipy.io import loadmat
+    mat = loadmat(P.export_results_mat(str(tmp_path / "seq_reliability_results.mat"), r, 8736, comp_importance=[0.5, 0.25, 0.0]),
+                  squeeze_me=True, struct_as_record=False)
+    ry, rc = mat["results_year"], mat["results_cum"]
+    assert np.array_equal(ry.dlc, lol.astype(np.float64)) and np.array_equal(ry.nlc, ent.astype(np.float64)) and np.array_equal(ry.ens, ens)
+    assert np.array_equal(ry.plc, lol / 8736.0) and np.array_equal(ry.dns, ens / 8736.0)
+    assert np.array_equal(rc.eens, eens) and np.array_equal(rc.cov, cov) and list(mat["comp_importance"]) == [0.5, 0.25, 0.0]
+    m2 = loadmat(P.export_nonseq_results_mat(str(tmp_path / "reliability_results.mat"), [9.0, 9.3], [0.13, 0.134], [0.4, 0.2]), squeeze_me=True)
+    assert list(m2["accumulated_lole"]) == [9.0, 9.3] and list(m2["beta_history"]) == [0.4, 0.2] and list(m2["edns_history"]) == [0.13, 0.134]
 
 
 def test_injected_fixture_export_for_the_patched_reference(tmp_path):
