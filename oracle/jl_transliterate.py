@@ -645,6 +645,43 @@ def reference_failure_times(src_markov: str, lam: float, dt: float, max_time: fl
     return list(env["failure_times"]), code
 
 
+# Markov_process.jl:83-110 (PART 4): the 2 x 2 transition matrix and its 1 x 2 row-vector product.  Julia's matrix syntax is
+# outside the transliterator's subset, so the three matrix expressions of the block are replaced textually (one hit each,
+# asserted) by helpers that spell the same products out; everything else is transliterated as it stands.
+MARKOV2_SUBSTITUTIONS: Tuple[Tuple[int, str, str], ...] = (
+    (94, "P = [p00 p01; \n     p10 p11]", "P = jl_mat2x2(p00, p01, p10, p11)"),
+    # lines 103 and 108 of the file; one less here because the two-line matrix literal above has become one line
+    (102, "current_state_prob = [1.0 0.0]", "current_state_prob = jl_rowvec(1.0, 0.0)"),
+    (107, "current_state_prob = current_state_prob * P", "current_state_prob = jl_row_times_mat(current_state_prob, P)"),
+)
+
+
+def reference_markov2(src_markov: str, mttf: float = None, mttr: float = None, steps: int = None):
+    """Markov_process.jl:83-110: probability of the DOWN state after t = 1..steps hourly transitions of a two-state chain that
+    starts UP.  λ, μ, dt come from the script's own definitions (:16-22, :42) unless mttf / mttr are given; `steps` overrides
+    the script's 200.  Returns (prob_down list, λ, μ, dt)."""
+    src, hit = apply_substitutions(src_markov, MARKOV2_SUBSTITUTIONS)
+    lines = src.split("\n")
+    head = [l for l in lines[:45] if re.match(r"^(MTTF_val|MTTR_val|λ|μ|dt)\s*=", l)]
+    if len(head) != 5:
+        raise ValueError("reference text changed: MTTF_val / MTTR_val / λ / μ / dt definitions not found in the script head")
+    block = extract_block(src, "p01 = 1 - exp", "end", 89)          # ... to the `end` of the evolution loop (:110)
+    block = "\n".join(l for l in block.split("\n") if not re.match(r"^\s*(display\(|global )", l))
+    env = base_prelude(lambda: 0.5)
+    env.update(jl_mat2x2=lambda a, b, c, d: JArr([JArr([a, b]), JArr([c, d])]), jl_rowvec=lambda a, b: JArr([a, b]),
+               jl_row_times_mat=lambda v, M: JArr([v[1] * M[1, 1] + v[2] * M[2, 1], v[1] * M[1, 2] + v[2] * M[2, 2]]))
+    exec(compile(transliterate("\n".join(head)), "<Markov_process.jl head>", "exec"), env)
+    if mttf is not None:
+        env["λ"] = 1 / float(mttf); env["μ"] = 1 / float(mttr)
+    code = transliterate(block)
+    if steps is not None:
+        if code.count("steps = 200") != 1:
+            raise ValueError("reference text changed: `steps = 200` not found once")
+        code = code.replace("steps = 200", f"steps = {int(steps)}")
+    exec(compile(code, "<transliterated Markov_process.jl:89-110>", "exec"), env)
+    return list(env["prob_down_analytical"]), env["λ"], env["μ"], env["dt"], hit
+
+
 def reference_dtmc_capacity(src_markov: str, uniforms):
     """Markov_process.jl:153-195 (five generators, hourly two-state DTMC, 1000 hours) with the script's own unit data;
     rand() replayed from uniforms[hour][generator].  Returns (capacity series, mttfs, mttrs, capacities)."""

@@ -186,8 +186,14 @@ series, mf, mr, cp = J.reference_dtmc_capacity(src_mk, u_dt)
 lam_ft = 1.0 / 2500.0
 u_ft = rng.random((40, 5002)).astype(np.float32).astype(np.float64)
 ft, _ = J.reference_failure_times(src_mk, lam_ft, 1.0, 5000, 40, u_ft)
+# the two-state chain of PART 4 (:83-110): the script's own MTTF / MTTR / dt / 200 steps, and a second parameter set
+m2a, lam2, mu2, dt2, m2_hit = J.reference_markov2(src_mk)
+assert m2_hit == [94, 102, 107], m2_hit
+m2b, _, _, _, _ = J.reference_markov2(src_mk, 450.0, 20.0, 500)
 np.savez_compressed(os.path.join(out, "ref_markov.npz"), dtmc_uniforms=u_dt, dtmc_capacity=np.array(series), mttf=np.array(mf), mttr=np.array(mr),
-                    cap=np.array(cp), ft_lambda=lam_ft, ft_uniforms=u_ft, failure_times=np.array(ft))
+                    cap=np.array(cp), ft_lambda=lam_ft, ft_uniforms=u_ft, failure_times=np.array(ft),
+                    markov2_script=np.array(m2a), markov2_script_params=np.array([1.0 / lam2, 1.0 / mu2, dt2]), markov2_b=np.array(m2b),
+                    markov2_b_params=np.array([450.0, 20.0, 1.0]))
 print("Markov: DTMC mean capacity", np.mean(series), "failure times", len(ft), "of 40", flush=True)
 
 # --- run_detailed_analytical (tail_risk.jl:96-141) with update_elu! / calculate_expected_generation / add_unit of comprehensive.jl

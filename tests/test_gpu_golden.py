@@ -186,3 +186,12 @@ def test_matlab_sampler_vectors_from_the_reference_text(engine, name):
         assert np.array_equal(r.lol_hours.astype(np.float64), g[f"{name}_lol"])
         assert np.array_equal(r.raw["ens_fp_vector"].astype(np.float64), g[f"{name}_ens"])
         assert np.array_equal(r.entries.astype(np.float64), g[f"{name}_nlc"])
+
+
+def test_two_state_markov_chain_from_the_reference_text(engine):
+    """ref_markov.npz: Markov_process.jl:83-110 executed from the reference text; psra_markov2 returns the same series."""
+    g = _ref("markov")
+    for key in ("markov2_script", "markov2_b"):
+        mttf, mttr, dt = g[key + "_params"]
+        m = engine.markov2(float(mttf), float(mttr), float(dt), len(g[key]))
+        assert np.allclose(m, g[key], rtol=0, atol=1e-15)

@@ -248,16 +248,25 @@ def test_c_oracle_reproduces_the_reference_fd_recursion_and_copt_demo():
 
 
 def test_c_oracle_reproduces_the_reference_markov_script_blocks():
-    """Markov_process.jl is a script; its constant-hazard experiment (:46-60) and its five-generator hourly DTMC (:153-195,
-    the script's own unit data) are cut out as they stand, transliterated and run on recorded rand() values."""
+    """Markov_process.jl is a script; its constant-hazard experiment (:46-60), its two-state chain (:83-110) and its
+    five-generator hourly DTMC (:153-195, the script's own unit data) are cut out as they stand, transliterated and run (on
+    recorded rand() values where they draw)."""
     g = _g("markov")
     assert np.array_equal(O.dtmc_capacity(g["mttf"], g["mttr"], g["cap"], g["dtmc_uniforms"]), g["dtmc_capacity"])
     o = O.failure_times(float(g["ft_lambda"]), 1.0, 5000.0, len(g["ft_uniforms"]), uniforms=g["ft_uniforms"])
     assert np.array_equal(o[o >= 0], g["failure_times"]) and 0 < len(g["failure_times"]) < len(g["ft_uniforms"])
+    # PART 4 (:83-110): the two-state chain, probability of DOWN after 1..steps hours (script parameters 1000 / 50 h, 200 steps)
+    for key in ("markov2_script", "markov2_b"):
+        mttf, mttr, dt = g[key + "_params"]
+        assert np.array_equal(O.markov2(float(mttf), float(mttr), float(dt), len(g[key])), g[key])
+    assert abs(g["markov2_script"][-1] - 0.047333337093) < 1e-12 and list(g["markov2_script_params"]) == [1000.0, 50.0, 1.0]
     if have_ref:
         src = J.load_text(REF, J.MARKOV_REL)
         series, mf, mr, cp = J.reference_dtmc_capacity(src, g["dtmc_uniforms"])
         assert series == list(g["dtmc_capacity"]) and mf == list(g["mttf"]) and cp == list(g["cap"])
+        pd, lam, mu, dt, hit = J.reference_markov2(src)
+        assert hit == [94, 102, 107] and pd == list(g["markov2_script"]) and (1 / lam, 1 / mu, dt) == (1000.0, 50.0, 1.0)
+        assert J.reference_markov2(src, 450.0, 20.0, 500)[0] == list(g["markov2_b"])
 
 
 def test_oracle_pieces_reproduce_the_reference_detailed_analytical():
