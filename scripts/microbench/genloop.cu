@@ -53,7 +53,8 @@ __device__ __forceinline__ unsigned long long dur_ticks3(uint32_t w, uint32_t ei
 }
 
 // flags: 1 = Philox, 2 = sampler (log + duration + time), 4 = hour + address + predicate, 8 = the atomic itself,
-// 16 = the experimental v3 sampler instead of the product's
+// 16 = the experimental v3 sampler instead of the product's, 32 = v3 with event times in per-unit quanta (duration and accumulation
+// are one IMAD.WIDE with a 64-bit addend, the hour one shift of the high word)
 template <int F>
 __global__ void __launch_bounds__(128, 5) gen(unsigned long long *out, long long *cyc, const uint32_t *rk_g, uint32_t wa, uint32_t wb)
 {
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(128, 5) gen(unsigned long long *out, long long
     (void)rk_s;
     const uint32_t tl_s = (uint32_t)__cvta_generic_to_shared(tl);
     uint32_t dummy_s = tl_s + 4u * (TL_WORDS + (threadIdx.x & 31));
-    uint32_t one_bits = 0x3F800000u, magic_bits = 0x4B000000u, H = TL_WORDS;
-    asm volatile("" : "+r"(one_bits), "+r"(magic_bits), "+r"(dummy_s), "+r"(H));
+    uint32_t one_bits = 0x3F800000u, magic_bits = 0x4B000000u, H = TL_WORDS, qshift = 5u;
+    asm volatile("" : "+r"(one_bits), "+r"(magic_bits), "+r"(dummy_s), "+r"(H), "+r"(qshift));
     unsigned long long tm1 = ~0ull;
     unsigned int ne = 0;
     uint32_t u = blockIdx.x * blockDim.x + threadIdx.x, acc = 0;
@@ -86,6 +87,11 @@ __global__ void __launch_bounds__(128, 5) gen(unsigned long long *out, long long
             t2 = t1 + ticks_rn(fmaxf(__fmul_rn(mb, neglog_u32(x[1], one_bits)), 1.0f));
             t3 = t2 + ticks_rn(fmaxf(__fmul_rn(ma, neglog_u32(x[2], one_bits)), 1.0f));
             t4 = t3 + ticks_rn(fmaxf(__fmul_rn(mb, neglog_u32(x[3], one_bits)), 1.0f));
+        } else if ((F & 2) && (F & 32)) {
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t1) : "r"(wa), "r"(exp_fix_u32(x[0], one_bits, magic_bits)), "l"(tm1));
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t2) : "r"(wb), "r"(exp_fix_u32(x[1], one_bits, magic_bits)), "l"(t1));
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t3) : "r"(wa), "r"(exp_fix_u32(x[2], one_bits, magic_bits)), "l"(t2));
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t4) : "r"(wb), "r"(exp_fix_u32(x[3], one_bits, magic_bits)), "l"(t3));
         } else if (F & 2) {
             t1 = tm1 + dur_ticks3(wa, exp_fix_u32(x[0], one_bits, magic_bits));
             t2 = t1 + dur_ticks3(wb, exp_fix_u32(x[1], one_bits, magic_bits));
@@ -96,10 +102,17 @@ __global__ void __launch_bounds__(128, 5) gen(unsigned long long *out, long long
             t3 = t2 + ((unsigned long long)x[2] << 8); t4 = t3 + ((unsigned long long)x[3] << 8);
         }
         tm1 = t4;
-        if (tm1 > (7000ull << 24)) tm1 -= (7000ull << 24);      // stay inside the year: the events land all over the timeline
+        if (F & 32) { if (tm1 > (7000ull << 37)) tm1 -= (7000ull << 37); }
+        else if (tm1 > (7000ull << 24)) tm1 -= (7000ull << 24);      // stay inside the year: the events land all over the timeline
         if (F & 4) {
-            const uint32_t h[4] = {__funnelshift_r((uint32_t)t1, (uint32_t)(t1 >> 32), 24), __funnelshift_r((uint32_t)t2, (uint32_t)(t2 >> 32), 24),
-                                   __funnelshift_r((uint32_t)t3, (uint32_t)(t3 >> 32), 24), __funnelshift_r((uint32_t)t4, (uint32_t)(t4 >> 32), 24)};
+            uint32_t h[4];
+            if (F & 32) {        // quantum 2^-37 h: the hour is the high word shifted by a per-unit amount
+                h[0] = (uint32_t)(t1 >> 32) >> qshift; h[1] = (uint32_t)(t2 >> 32) >> qshift;
+                h[2] = (uint32_t)(t3 >> 32) >> qshift; h[3] = (uint32_t)(t4 >> 32) >> qshift;
+            } else {
+                h[0] = __funnelshift_r((uint32_t)t1, (uint32_t)(t1 >> 32), 24); h[1] = __funnelshift_r((uint32_t)t2, (uint32_t)(t2 >> 32), 24);
+                h[2] = __funnelshift_r((uint32_t)t3, (uint32_t)(t3 >> 32), 24); h[3] = __funnelshift_r((uint32_t)t4, (uint32_t)(t4 >> 32), 24);
+            }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (F & 8) {
@@ -133,6 +146,7 @@ void run(const char *name, int bps, int threads)
     const size_t smem = 4 * (TL_WORDS + 32);
     cudaFuncSetAttribute(gen<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     uint32_t wa = sampler_word(2940.0f), wb = sampler_word(60.0f);
+    if (F & 32) { wa = (uint32_t)llrint(2940.0 * PSRA_CEFF * 8192.0); wb = (uint32_t)llrint(60.0 * PSRA_CEFF * 8192.0); }   // mean * C * 2^(37 - 24)
     if (!(F & 16)) { const float fa = 2940.0f * 16777216.0f, fb = 60.0f * 16777216.0f; memcpy(&wa, &fa, 4); memcpy(&wb, &fb, 4); }
     for (int rep = 0; rep < 2; rep++) gen<F><<<grid, threads, smem>>>(out, cyc, rk, wa, wb);
     std::vector<long long> h(grid);
@@ -158,5 +172,7 @@ int main()
     run<15>("full loop body", 1, 128);
     run<31>("full loop body, experimental v3 sampler", 5, 128);
     run<18>("v3 sampler only", 5, 128);
+    run<63>("full loop body, v3 sampler, per-unit quanta", 5, 128);
+    run<50>("v3 sampler in per-unit quanta only", 5, 128);
     return 0;
 }
