@@ -290,6 +290,10 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
         //      bsum[block] = sum of the whole block
         for (int w0 = warp * 32; w0 < a.Wd; w0 += nwarps * 32) {
             const int w = w0 + lane;
+            // the word's maximum load goes into the stored negative sum here: the global load (what is left of the L1 beside five
+            // timelines does not keep the table) completes under the shared-memory work of this phase instead of sitting
+            // on the critical path of the evaluation behind the barrier
+            const int lmx = w < a.Wd ? __ldg(&s_lmax[w]) : 0;
             int s = 0, n = 0;
             if (w < a.Wd) {
                 const int4 *row = reinterpret_cast<const int4 *>(tl + w * 32);
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
                 }
             }
             const int incl = warp_incl_scan(s, lane);
-            if (w < a.Wd) { wsum[w] = incl - s; wneg[w] = n; }
+            if (w < a.Wd) { wsum[w] = incl - s; wneg[w] = n - lmx; }
             if (lane == 31) bsum[w0 >> 5] = incl;
         }
         WIDE_T(3);
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
                 const int w = valid ? w0 + lane : nwords - 1;
                 int c_in = cap0 + wsum[w];                          // capacity entering the word
                 for (int j = 0; j < (w0 >> 5); j++) c_in += bsum[j];
-                const bool need = valid && (c_in + wneg[w] < __ldg(&s_lmax[w]));
+                const bool need = valid && (c_in + wneg[w] < 0);        // capacity + negative hour deltas < maximum load of the word
                 uint32_t nm = __ballot_sync(0xffffffffu, need);
                 n_flag += __popc(nm);
                 int4 *row = reinterpret_cast<int4 *>(tl + w * 32);
@@ -335,12 +339,13 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 4 ? WIDE_BPS4 : kWarps 
                     const int wq = w0 + src;
                     const int cq = __shfl_sync(0xffffffffu, c_in, src);      // capacity entering the word
                     const int hy = wq * 32 + lane;
-                    const int c = cq + warp_incl_scan(tl[hy], lane);
                     const int L = __ldg(&a.load[hy]);                        // zero beyond the year: never a loss there
+                    const int Lprev = __ldg(&a.load[max(wq * 32 - 1, 0)]);   // issued with it: one L2 round trip, not two
+                    const int c = cq + warp_incl_scan(tl[hy], lane);
                     const bool lol = c < L;
                     const uint32_t lm = __ballot_sync(0xffffffffu, lol);
                     if (lm) {
-                        const uint32_t prev0 = (wq > 0 && cq < __ldg(&a.load[wq * 32 - 1])) ? 1u : 0u;   // the hour before the word
+                        const uint32_t prev0 = (wq > 0 && cq < Lprev) ? 1u : 0u;                      // the hour before the word
                         if (lane == 0) {
                             lolh += (unsigned int)__popc(lm);
                             entries += (unsigned int)__popc(lm & ~((lm << 1) | prev0));                 // calnlc.m:22-34
